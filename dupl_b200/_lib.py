@@ -1,0 +1,153 @@
+"""ctypes binding of libdupl.so (include/dupl.h).
+
+The product path has NO fallback: if the CUDA library is missing or a call fails, a
+RuntimeError is raised.  PyTorch is used for storage only (device buffers, streams).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdupl.so")
+
+MAX_SEGMENTS = 8
+MAX_GROUPS = 2
+PAR_MAX_DIL = 8
+
+EPI_F32, EPI_SPLIT, EPI_GELU_SPLIT, EPI_RESID, EPI_PATCH = 0, 1, 2, 3, 4
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+
+
+class Segment(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("gh", C.c_int32), ("gw", C.c_int32), ("tokens", C.c_int32),
+                ("row_offset", C.c_int32), ("patch_row_offset", C.c_int32)]
+
+
+class GemmGroup(C.Structure):
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+                ("bias", C.c_void_p), ("resid", C.c_void_p), ("out_f32", C.c_void_p),
+                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("pos", C.c_void_p * MAX_SEGMENTS)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("groups", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("lda", C.c_int32), ("ldo", C.c_int32), ("epilogue", C.c_int32), ("nseg", C.c_int32),
+                ("seg", Segment * MAX_SEGMENTS), ("g", GemmGroup * MAX_GROUPS)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("nseg", C.c_int32), ("seg", Segment * MAX_SEGMENTS), ("M", C.c_int32), ("heads", C.c_int32),
+                ("scale", C.c_float), ("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p),
+                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p)]
+
+
+class MscamArgs(C.Structure):
+    _fields_ = [("nscale", C.c_int32), ("lowres", C.c_void_p * MAX_SEGMENTS),
+                ("gh", C.c_int32 * MAX_SEGMENTS), ("gw", C.c_int32 * MAX_SEGMENTS),
+                ("b", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("out", C.c_void_p), ("minmax", C.c_void_p)]
+
+
+class CamToLabelArgs(C.Structure):
+    _fields_ = [("cam", C.c_void_p), ("cls_label", C.c_void_p), ("img_box", C.c_void_p), ("high_thre", C.c_void_p),
+                ("high_thre_scalar", C.c_float), ("low_thre", C.c_float), ("bkg_thre", C.c_float),
+                ("ignore_mid", C.c_int32), ("ignore_index", C.c_int64),
+                ("b", C.c_int32), ("K", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("valid_cam", C.c_void_p), ("label", C.c_void_p)]
+
+
+class RefinePrologueArgs(C.Structure):
+    _fields_ = [("images", C.c_void_p), ("cams", C.c_void_p), ("cls_label", C.c_void_p), ("bkg_h", C.c_void_p),
+                ("bkg_h_scalar", C.c_float), ("bkg_l_scalar", C.c_float),
+                ("b", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("images_ds", C.c_void_p), ("masks", C.c_void_p), ("nactive", C.c_void_p)]
+
+
+class RefineEpilogueArgs(C.Structure):
+    _fields_ = [("masks", C.c_void_p), ("cls_label", C.c_void_p), ("img_box", C.c_void_p),
+                ("b", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("ignore_index", C.c_float), ("label", C.c_void_p), ("label_h", C.c_void_p), ("label_l", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/dupl.h
+_PROTOTYPES = {
+    "dupl_version": (C.c_int, []),
+    "dupl_last_error": (C.c_char_p, []),
+    "dupl_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dupl_gemm_bf16x3": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "dupl_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "dupl_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
+    "dupl_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Segment), C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dupl_pos_embed_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "dupl_cls_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Segment), C.c_int32,
+                                C.c_int32, C.c_void_p]),
+    "dupl_cam_contract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.POINTER(Segment), C.c_int32, C.c_void_p, c_i64p, C.c_void_p]),
+    "dupl_mscam_post": (C.c_int, [C.POINTER(MscamArgs), C.c_void_p]),
+    "dupl_cam_to_label": (C.c_int, [C.POINTER(CamToLabelArgs), C.c_void_p]),
+    "dupl_label_to_aff_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "dupl_par_affinity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p,
+                                    C.c_int32, C.c_float, C.c_float, C.c_void_p]),
+    "dupl_par_propagate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_void_p]),
+    "dupl_refine_prologue": (C.c_int, [C.POINTER(RefinePrologueArgs), C.c_void_p]),
+    "dupl_refine_epilogue": (C.c_int, [C.POINTER(RefineEpilogueArgs), C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+def lib():
+    """Loads libdupl.so once; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built. Run "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+                f"dupl_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dupl_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dupl_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+
+
+def f32c(t):
+    """contiguous fp32 view/copy (storage plumbing only)."""
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()

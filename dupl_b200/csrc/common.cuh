@@ -1,0 +1,46 @@
+// Host-side helpers shared by every translation unit of libdupl.so:
+// error convention of the C-ABI (include/dupl.h) and TMA tensor-map construction.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dupl.h"
+
+namespace dupl {
+
+// Thread-local message returned by dupl_last_error().
+void set_error(const char* fmt, ...);
+
+#define DUPL_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::dupl::set_error(__VA_ARGS__);    \
+      return DUPL_ERR_INVALID_ARGUMENT;  \
+    }                                    \
+  } while (0)
+
+#define DUPL_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::dupl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DUPL_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+
+// Checks the launch itself (not asynchronous execution errors: the library never synchronises).
+#define DUPL_LAUNCH_OK() DUPL_CUDA_OK(cudaGetLastError())
+
+// 2-D bf16 tensor map: `rows` x `cols` elements, row stride `ld` elements, box = box_rows x 64
+// columns (128 bytes) with the 128-byte swizzle; out-of-bounds elements read as zero.
+// Returns 0 on success (DUPL_ERR_* otherwise).
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows);
+
+int sm_count();
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace dupl

@@ -1,0 +1,383 @@
+// Pixel-adaptive refinement (model/PAR.py:64-91) and the refine_cams_with_* wrappers around it
+// (utils/cam_helper.py:338-440).  The reference gathers neighbours with 66 one-hot dilated
+// convolutions per call and materialises [1,c,48,h,w] tensors; here neighbours are gathered
+// directly (replicate border = index clamp), the 48-way affinity is computed once per image and
+// shared by every mask set that is propagated over that image, and all channel planes of all
+// images advance together in one launch per iteration.
+#include <math.h>
+
+#include "common.cuh"
+#include "resample.cuh"
+
+namespace dupl {
+
+constexpr int PAR_MAX_N = 8 * DUPL_PAR_MAX_DIL;
+
+struct ParGeom {
+  int dil[DUPL_PAR_MAX_DIL];
+  int ndil;
+};
+
+// offsets in the order of PAR.get_kernel (PAR.py:10-24): (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
+__device__ __constant__ int c_par_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+__device__ __constant__ int c_par_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+
+struct ParPos {
+  float v[PAR_MAX_N];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Affinity: one thread per pixel, the 8*ndil neighbour values of one channel live in registers.
+// ---------------------------------------------------------------------------------------------
+template <int NDIL>
+__global__ void __launch_bounds__(256) par_affinity_kernel(const float* __restrict__ imgs, float* __restrict__ aff,
+                                                           int C, int h, int w, ParGeom g, ParPos pos, float w1,
+                                                           float w2) {
+  constexpr int N = 8 * NDIL;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z;
+  if (x >= w || y >= h) return;
+  const long hw = static_cast<long>(h) * w;
+  float a[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) a[n] = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float* plane = imgs + (static_cast<long>(b) * C + c) * hw;
+    const float ctr = __ldg(plane + static_cast<long>(y) * w + x);
+    float v[N];
+    float sum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < NDIL; ++di) {
+      const int d = g.dil[di];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int yy = min(max(y + c_par_dy[j] * d, 0), h - 1);
+        const int xx = min(max(x + c_par_dx[j] * d, 0), w - 1);
+        v[di * 8 + j] = __ldg(plane + static_cast<long>(yy) * w + xx);
+        sum += v[di * 8 + j];
+      }
+    }
+    const float mean = sum / N;
+    float ss = 0.0f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float dlt = v[n] - mean;
+      ss = fmaf(dlt, dlt, ss);
+    }
+    const float sd = sqrtf(ss / (N - 1)) + 1e-8f;  // torch.std is unbiased
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float t = __fdiv_rn(__fdiv_rn(fabsf(v[n] - ctr), sd), w1);
+      a[n] -= t * t;
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    a[n] = a[n] / C;  // mean over channels
+    mx = fmaxf(mx, a[n]);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    a[n] = expf(a[n] - mx);
+    s += a[n];
+  }
+  float* o = aff + static_cast<long>(b) * N * hw + static_cast<long>(y) * w + x;
+#pragma unroll
+  for (int n = 0; n < N; ++n) o[n * hw] = __fdiv_rn(a[n], s) + w2 * pos.v[n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// One propagation step for up to CH planes of one image per thread block column (blockIdx.z).
+// nactive (device, optional): number of live planes of each image; chunks past it exit.
+// ---------------------------------------------------------------------------------------------
+template <int NDIL, int CH>
+__global__ void __launch_bounds__(256) par_propagate_kernel(const float* __restrict__ aff, const float* __restrict__ src,
+                                                            float* __restrict__ dst, const int* __restrict__ nactive,
+                                                            int P, int chunks, int h, int w, ParGeom g) {
+  constexpr int N = 8 * NDIL;
+  const int b = blockIdx.z / chunks;
+  const int chunk = blockIdx.z % chunks;
+  const int live = nactive != nullptr ? min(__ldg(nactive + b), P) : P;
+  const int p0 = chunk * CH;
+  if (p0 >= live) return;
+  const int np = min(CH, live - p0);
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const long hw = static_cast<long>(h) * w;
+  const float* A = aff + static_cast<long>(b) * N * hw + static_cast<long>(y) * w + x;
+  const float* S = src + (static_cast<long>(b) * P + p0) * hw;
+  float acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int di = 0; di < NDIL; ++di) {
+    const int d = g.dil[di];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int yy = min(max(y + c_par_dy[j] * d, 0), h - 1);
+      const int xx = min(max(x + c_par_dx[j] * d, 0), w - 1);
+      const float a = __ldg(A + (di * 8 + j) * hw);
+      const float* q = S + static_cast<long>(yy) * w + xx;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (c < np) acc[c] = fmaf(a, __ldg(q + c * hw), acc[c]);
+    }
+  }
+  float* D = dst + (static_cast<long>(b) * P + p0) * hw + static_cast<long>(y) * w + x;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (c < np) D[c * hw] = acc[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refine prologue: one thread per half-resolution pixel.
+// Live planes of image i: a = v*nch + slot, v in {high, low}, slot 0 = background, slot s>0 = s-th
+// present class in ascending order (== valid_key of the reference), nch = 1 + #present.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mean2x2(const float* __restrict__ p, int W) {
+  // bilinear(align_corners=False) to exactly half size: l0 = l1 = 0.5 on both axes, torch op order
+  const float2 r0 = __ldg(reinterpret_cast<const float2*>(p));
+  const float2 r1 = __ldg(reinterpret_cast<const float2*>(p + W));
+  const float t0 = __fmaf_rn(0.5f, r0.x, __fmul_rn(0.5f, r0.y));
+  const float t1 = __fmaf_rn(0.5f, r1.x, __fmul_rn(0.5f, r1.y));
+  return __fmaf_rn(0.5f, t0, __fmul_rn(0.5f, t1));
+}
+
+__global__ void __launch_bounds__(256) refine_prologue_kernel(dupl_refine_prologue_args a, int* __restrict__ nactive) {
+  const int h2 = a.H / 2, w2 = a.W / 2;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z;
+  if (x >= w2 || y >= h2) return;
+  const long HW = static_cast<long>(a.H) * a.W;
+  const long hw = static_cast<long>(h2) * w2;
+  const long src_off = static_cast<long>(2 * y) * a.W + 2 * x;
+  const long dst_off = static_cast<long>(y) * w2 + x;
+  const int P = 2 * (a.K + 1);
+
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    a.images_ds[(static_cast<long>(b) * 3 + c) * hw + dst_off] = mean2x2(a.images + (static_cast<long>(b) * 3 + c) * HW + src_off, a.W);
+
+  const float* cl = a.cls_label + static_cast<long>(b) * a.K;
+  int nch = 1;
+  for (int k = 0; k < a.K; ++k) nch += (__ldg(cl + k) != 0.0f);
+  if (x == 0 && y == 0) nactive[b] = 2 * nch;
+
+  const float bh = a.bkg_h != nullptr ? mean2x2(a.bkg_h + static_cast<long>(b) * HW + src_off, a.W) : a.bkg_h_scalar;
+  const float bl = a.bkg_l_scalar;
+  float* mh = a.masks + static_cast<long>(b) * P * hw + dst_off;  // variant high: planes [0, nch)
+  float* ml = mh + static_cast<long>(nch) * hw;                   // variant low : planes [nch, 2 nch)
+
+  // pass 1: down-sampled class scores -> planes (raw), running max
+  float mx = -INFINITY;
+  int slot = 1;
+  for (int k = 0; k < a.K; ++k) {
+    if (__ldg(cl + k) != 0.0f) {
+      const float v = mean2x2(a.cams + (static_cast<long>(b) * a.K + k) * HW + src_off, a.W);
+      mh[slot * hw] = v;
+      mx = fmaxf(mx, v);
+      ++slot;
+    }
+  }
+  const float mxh = fmaxf(mx, bh), mxl = fmaxf(mx, bl);
+  // pass 2: exp and sums
+  const float eh0 = expf(bh - mxh), el0 = expf(bl - mxl);
+  float sh = eh0, sl = el0;
+  for (int s = 1; s < nch; ++s) {
+    const float v = mh[s * hw];
+    const float eh = expf(v - mxh), el = expf(v - mxl);
+    mh[s * hw] = eh;
+    ml[s * hw] = el;
+    sh += eh;
+    sl += el;
+  }
+  // pass 3: normalise
+  mh[0] = __fdiv_rn(eh0, sh);
+  ml[0] = __fdiv_rn(el0, sl);
+  for (int s = 1; s < nch; ++s) {
+    mh[s * hw] = __fdiv_rn(mh[s * hw], sh);
+    ml[s * hw] = __fdiv_rn(ml[s * hw], sl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refine epilogue: one thread per full-resolution pixel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void py_slice2(int a, int b, int n, int& lo, int& hi) {
+  lo = a < 0 ? max(a + n, 0) : min(a, n);
+  hi = b < 0 ? max(b + n, 0) : min(b, n);
+}
+
+__global__ void __launch_bounds__(256) refine_epilogue_kernel(dupl_refine_epilogue_args a) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z;
+  if (x >= a.W || y >= a.H) return;
+  const int h2 = a.H / 2, w2 = a.W / 2;
+  const long hw = static_cast<long>(h2) * w2;
+  const int P = 2 * (a.K + 1);
+  const float* cl = a.cls_label + static_cast<long>(b) * a.K;
+  int nch = 1;
+  for (int k = 0; k < a.K; ++k) nch += (__ldg(cl + k) != 0.0f);
+
+  const Lin ly = lin_coord(y, h2, static_cast<float>(h2) / a.H);
+  const Lin lx = lin_coord(x, w2, static_cast<float>(w2) / a.W);
+  const float* base = a.masks + static_cast<long>(b) * P * hw;
+  int arg[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    float best = 0.0f;
+    int bi = 0;
+    for (int s = 0; s < nch; ++s) {
+      const float val = bilerp(base + static_cast<long>(v * nch + s) * hw, w2, ly, lx);
+      if (s == 0 || val > best) {  // first index on ties (torch.argmax)
+        best = val;
+        bi = s;
+      }
+    }
+    arg[v] = bi;
+  }
+  // valid_key lookup: slot s > 0 -> (index of the s-th present class) + 1
+  float key[2] = {0.0f, 0.0f};
+  int slot = 0;
+  for (int k = 0; k < a.K; ++k) {
+    if (__ldg(cl + k) != 0.0f) {
+      ++slot;
+      if (arg[0] == slot) key[0] = static_cast<float>(k + 1);
+      if (arg[1] == slot) key[1] = static_cast<float>(k + 1);
+    }
+  }
+  const int* bx = a.img_box + 4 * b;
+  int y0, y1, x0, x1;
+  py_slice2(bx[0], bx[1], a.H, y0, y1);
+  py_slice2(bx[2], bx[3], a.W, x0, x1);
+  const bool inside = y >= y0 && y < y1 && x >= x0 && x < x1;
+  const float lh = inside ? key[0] : a.ignore_index;
+  const float ll = inside ? key[1] : a.ignore_index;
+  float out = lh;
+  if (lh == 0.0f) out = a.ignore_index;
+  if (lh + ll == 0.0f) out = 0.0f;
+  const long o = (static_cast<long>(b) * a.H + y) * a.W + x;
+  a.label[o] = out;
+  if (a.label_h != nullptr) a.label_h[o] = lh;
+  if (a.label_l != nullptr) a.label_l[o] = ll;
+}
+
+static int fill_geom(const int32_t* dil, int ndil, ParGeom& g) {
+  if (dil == nullptr || ndil < 1 || ndil > DUPL_PAR_MAX_DIL) {
+    set_error("PAR: ndil=%d (1..%d supported)", ndil, DUPL_PAR_MAX_DIL);
+    return DUPL_ERR_INVALID_ARGUMENT;
+  }
+  g.ndil = ndil;
+  for (int i = 0; i < DUPL_PAR_MAX_DIL; ++i) g.dil[i] = i < ndil ? dil[i] : 0;
+  return DUPL_OK;
+}
+
+// softmax_n(-(pos/(std+1e-8)/w1)^2) of PAR.get_pos (PAR.py:51-62, 84-87): a constant vector.
+static void pos_prior(const ParGeom& g, float w1, ParPos& out) {
+  const int N = 8 * g.ndil;
+  float pos[PAR_MAX_N];
+  const float r2 = static_cast<float>(sqrt(2.0));
+  static const int diag[8] = {1, 0, 1, 0, 0, 1, 0, 1};
+  for (int di = 0; di < g.ndil; ++di)
+    for (int j = 0; j < 8; ++j) pos[di * 8 + j] = (diag[j] ? r2 : 1.0f) * static_cast<float>(g.dil[di]);
+  double mean = 0.0;
+  for (int n = 0; n < N; ++n) mean += pos[n];
+  mean /= N;
+  double ss = 0.0;
+  for (int n = 0; n < N; ++n) ss += (pos[n] - mean) * (pos[n] - mean);
+  const float sd = static_cast<float>(sqrt(ss / (N - 1)));
+  float e[PAR_MAX_N], mx = -INFINITY;
+  for (int n = 0; n < N; ++n) {
+    const float t = pos[n] / (sd + 1e-8f) / w1;
+    e[n] = -(t * t);
+    mx = fmaxf(mx, e[n]);
+  }
+  float s = 0.0f;
+  for (int n = 0; n < N; ++n) {
+    e[n] = expf(e[n] - mx);
+    s += e[n];
+  }
+  for (int n = 0; n < PAR_MAX_N; ++n) out.v[n] = n < N ? e[n] / s : 0.0f;
+}
+
+}  // namespace dupl
+
+using namespace dupl;
+
+extern "C" int dupl_par_affinity(const float* imgs, float* aff, int32_t B, int32_t C, int32_t h, int32_t w,
+                                 const int32_t* dilations_host, int32_t ndil, float w1, float w2, void* stream) {
+  DUPL_CHECK_ARG(imgs && aff && B > 0 && C > 0 && h > 0 && w > 0, "dupl_par_affinity: bad arguments");
+  ParGeom g;
+  int rc = fill_geom(dilations_host, ndil, g);
+  if (rc) return rc;
+  ParPos pos;
+  pos_prior(g, w1, pos);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8), B), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (ndil) {
+#define AFF_CASE(ND) case ND: par_affinity_kernel<ND><<<grid, block, 0, st>>>(imgs, aff, C, h, w, g, pos, w1, w2); break;
+    AFF_CASE(1) AFF_CASE(2) AFF_CASE(3) AFF_CASE(4) AFF_CASE(5) AFF_CASE(6) AFF_CASE(7) AFF_CASE(8)
+#undef AFF_CASE
+  }
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_par_propagate(const float* aff, float* masks, float* scratch, const int32_t* nactive, int32_t B,
+                                  int32_t P, int32_t h, int32_t w, const int32_t* dilations_host, int32_t ndil,
+                                  int32_t num_iter, int32_t* result_in_scratch_host, void* stream) {
+  DUPL_CHECK_ARG(aff && masks && scratch && B > 0 && P > 0 && h > 0 && w > 0 && num_iter >= 0,
+                 "dupl_par_propagate: bad arguments");
+  ParGeom g;
+  int rc = fill_geom(dilations_host, ndil, g);
+  if (rc) return rc;
+  constexpr int CH = 8;
+  const int chunks = cdiv(P, CH);
+  DUPL_CHECK_ARG(static_cast<long>(B) * chunks <= 65535, "dupl_par_propagate: B*chunks=%ld exceeds the launch grid",
+                 static_cast<long>(B) * chunks);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8), B * chunks), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* src = masks;
+  float* dst = scratch;
+  for (int it = 0; it < num_iter; ++it) {
+    switch (ndil) {
+#define PROP_CASE(ND) \
+  case ND: par_propagate_kernel<ND, CH><<<grid, block, 0, st>>>(aff, src, dst, nactive, P, chunks, h, w, g); break;
+      PROP_CASE(1) PROP_CASE(2) PROP_CASE(3) PROP_CASE(4) PROP_CASE(5) PROP_CASE(6) PROP_CASE(7) PROP_CASE(8)
+#undef PROP_CASE
+    }
+    DUPL_LAUNCH_OK();
+    float* t = src; src = dst; dst = t;
+  }
+  if (result_in_scratch_host != nullptr) *result_in_scratch_host = (src == scratch) ? 1 : 0;
+  return DUPL_OK;
+}
+
+extern "C" int dupl_refine_prologue(const dupl_refine_prologue_args* a, void* stream) {
+  DUPL_CHECK_ARG(a != nullptr, "dupl_refine_prologue: args is NULL");
+  DUPL_CHECK_ARG(a->images && a->cams && a->cls_label && a->images_ds && a->masks && a->nactive,
+                 "dupl_refine_prologue: NULL pointer");
+  DUPL_CHECK_ARG(a->b > 0 && a->K > 0 && a->H > 0 && a->W > 0 && a->H % 2 == 0 && a->W % 2 == 0,
+                 "dupl_refine_prologue: bad shape b=%d K=%d H=%d W=%d (H, W must be even)", a->b, a->K, a->H, a->W);
+  dim3 grid(cdiv(a->W / 2, 32), cdiv(a->H / 2, 8), a->b), block(32, 8);
+  refine_prologue_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*a, a->nactive);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_refine_epilogue(const dupl_refine_epilogue_args* a, void* stream) {
+  DUPL_CHECK_ARG(a != nullptr, "dupl_refine_epilogue: args is NULL");
+  DUPL_CHECK_ARG(a->masks && a->cls_label && a->img_box && a->label, "dupl_refine_epilogue: NULL pointer");
+  DUPL_CHECK_ARG(a->b > 0 && a->K > 0 && a->H > 0 && a->W > 0 && a->H % 2 == 0 && a->W % 2 == 0,
+                 "dupl_refine_epilogue: bad shape");
+  dim3 grid(cdiv(a->W, 32), cdiv(a->H, 8), a->b), block(32, 8);
+  refine_epilogue_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}

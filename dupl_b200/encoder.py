@@ -1,0 +1,118 @@
+"""Host-side driver of the ViT-B/16 encoder kernels (reference: model/backbone/vit.py:289-326).
+
+All images of all scales are laid out as segments of ONE token matrix per student, so each linear
+layer of each block is a single grouped tcgen05 GEMM launch covering every scale and both students
+(dupl.h: dupl_segment).  This module only sequences launches and owns buffers; arithmetic is in
+libdupl.so.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+EMBED = 768
+HEADS = 12
+DEPTH = 12
+LN_EPS = 1e-6  # deit.py:100
+
+
+class StudentPlanes:
+    """split-bf16 planes of one student's encoder weights, refreshed lazily when a parameter changes
+    (torch bumps `_version` on every in-place update, e.g. by the optimizer)."""
+
+    GEMM_WEIGHTS = ("patch_embed.proj.weight",) + tuple(
+        f"blocks.{i}.{n}.weight" for i in range(DEPTH) for n in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2"))
+
+    def __init__(self, encoder):
+        self.encoder = encoder
+        self._planes = {}
+        self._pos = {}
+
+    def _params(self):
+        return dict(self.encoder.named_parameters())
+
+    def plane(self, name):
+        p = self._params()[name]
+        L.require_cuda(p)
+        key = (p.data_ptr(), p._version)
+        hit = self._planes.get(name)
+        if hit is None or hit[0] != key:
+            w = p.detach().reshape(p.shape[0], -1)
+            hit = (key, ops.split_bf16(w))
+            self._planes[name] = hit
+        return hit[1]
+
+    def vec(self, name):
+        return self._params()[name].detach()
+
+    def pos(self, gh, gw):
+        p = self.encoder.pos_embed
+        key = (p.data_ptr(), p._version)
+        hit = self._pos.get((gh, gw))
+        if hit is None or hit[0] != key:
+            hit = (key, ops.pos_embed_resize(p.detach(), gh, gw))
+            self._pos[(gh, gw)] = hit
+        return hit[1]
+
+
+class EncoderOutput:
+    __slots__ = ("segs", "tok", "aux_tok", "M")
+
+
+def run_encoder(planes, images_per_seg, seg_shapes, flip_twin, aux_index, on_aux=None):
+    """Runs the 12 blocks for every student in `planes` over the given segments.
+
+    images_per_seg: list of source image tensors [b,3,H,W] (fp32, cuda); segment i is patchified from
+    images_per_seg[i] resized to (16*gh_i, 16*gw_i), with a flipped twin batch when flip_twin.
+    seg_shapes: list of (batch, gh, gw).
+    aux_index: block index whose output feeds the aux head (embeds[aux_layer], vit.py:319-326).
+    on_aux(g, tok_g, segs): called right after block `aux_index` (0-based) for every student when that
+    index is not the last block (the last entry of `embeds` is the final-normed tensor, vit.py:323-324).
+    Returns (segs, [tok_g]) with tok_g the fp32 residual stream BEFORE the final LayerNorm.
+    """
+    G = len(planes)
+    segs, M, Mp = ops.make_segments(seg_shapes)
+    dev = images_per_seg[0].device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    patch_hi = torch.empty(Mp, EMBED, **bf)
+    patch_lo = torch.empty(Mp, EMBED, **bf)
+    for s, img in zip(segs, images_per_seg):
+        ops.patchify(L.f32c(img), s, flip_twin, patch_hi, patch_lo)
+
+    tok = [torch.empty(M, EMBED, **f32) for _ in range(G)]
+    xn = [(torch.empty(M, EMBED, **bf), torch.empty(M, EMBED, **bf)) for _ in range(G)]
+    qkv = [(torch.empty(M, 3 * EMBED, **bf), torch.empty(M, 3 * EMBED, **bf)) for _ in range(G)]
+    att = [(torch.empty(M, EMBED, **bf), torch.empty(M, EMBED, **bf)) for _ in range(G)]
+    hid = [(torch.empty(M, 4 * EMBED, **bf), torch.empty(M, 4 * EMBED, **bf)) for _ in range(G)]
+
+    pos = [[pl.pos(s.gh, s.gw) for s in segs] for pl in planes]
+    ops.gemm_bf16x3(
+        [dict(a=(patch_hi, patch_lo), w=pl.plane("patch_embed.proj.weight"), bias=pl.vec("patch_embed.proj.bias"),
+              out_f32=tok[g], pos=pos[g]) for g, pl in enumerate(planes)],
+        Mp, EMBED, EMBED, L.EPI_PATCH, segs=segs)
+    for g, pl in enumerate(planes):
+        ops.cls_rows(tok[g], pl.vec("cls_token").reshape(-1), pos[g], segs)
+
+    scale = (EMBED // HEADS) ** -0.5
+    for i in range(DEPTH):
+        bp = f"blocks.{i}."
+        for g, pl in enumerate(planes):
+            ops.layernorm_split(tok[g], pl.vec(bp + "norm1.weight"), pl.vec(bp + "norm1.bias"), *xn[g], eps=LN_EPS)
+        ops.gemm_bf16x3([dict(a=xn[g], w=pl.plane(bp + "attn.qkv.weight"), bias=pl.vec(bp + "attn.qkv.bias"), out=qkv[g])
+                         for g, pl in enumerate(planes)], M, 3 * EMBED, EMBED, L.EPI_SPLIT)
+        for g in range(G):
+            ops.attention_fwd(qkv[g][0], qkv[g][1], att[g][0], att[g][1], segs, HEADS, scale)
+        ops.gemm_bf16x3([dict(a=att[g], w=pl.plane(bp + "attn.proj.weight"), bias=pl.vec(bp + "attn.proj.bias"),
+                              resid=tok[g], out_f32=tok[g]) for g, pl in enumerate(planes)], M, EMBED, EMBED, L.EPI_RESID)
+        for g, pl in enumerate(planes):
+            ops.layernorm_split(tok[g], pl.vec(bp + "norm2.weight"), pl.vec(bp + "norm2.bias"), *xn[g], eps=LN_EPS)
+        ops.gemm_bf16x3([dict(a=xn[g], w=pl.plane(bp + "mlp.fc1.weight"), bias=pl.vec(bp + "mlp.fc1.bias"), out=hid[g])
+                         for g, pl in enumerate(planes)], M, 4 * EMBED, EMBED, L.EPI_GELU_SPLIT)
+        ops.gemm_bf16x3([dict(a=hid[g], w=pl.plane(bp + "mlp.fc2.weight"), bias=pl.vec(bp + "mlp.fc2.bias"),
+                              resid=tok[g], out_f32=tok[g]) for g, pl in enumerate(planes)], M, EMBED, 4 * EMBED, L.EPI_RESID)
+        if on_aux is not None and i == aux_index and i != DEPTH - 1:
+            for g in range(G):
+                on_aux(g, tok[g], segs)
+    return segs, tok

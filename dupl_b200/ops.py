@@ -1,0 +1,262 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers, launch on the
+current stream.  No arithmetic happens in Python/PyTorch here."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _segs(seg_list):
+    arr = (L.Segment * L.MAX_SEGMENTS)()
+    for i, s in enumerate(seg_list):
+        arr[i] = s
+    return arr
+
+
+def make_segments(shapes):
+    """shapes: list of (batch, gh, gw) -> (list[Segment], total token rows, total patch rows)."""
+    if not 1 <= len(shapes) <= L.MAX_SEGMENTS:
+        raise ValueError(f"1..{L.MAX_SEGMENTS} segments supported, got {len(shapes)}")
+    segs, row, prow = [], 0, 0
+    for (b, gh, gw) in shapes:
+        tokens = 1 + gh * gw
+        segs.append(L.Segment(b, gh, gw, tokens, row, prow))
+        row += b * tokens
+        prow += b * gh * gw
+    return segs, row, prow
+
+
+# ------------------------------------------------------------------ dense path
+def split_bf16(x):
+    L.require_cuda(x)
+    x = L.f32c(x)
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    L.check(L.lib().dupl_split_bf16(L.ptr(x), L.ptr(hi), L.ptr(lo), x.numel(), L.stream_ptr(x.device)), "dupl_split_bf16")
+    return hi, lo
+
+
+def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None):
+    """groups: list of dicts with keys a=(hi,lo), w=(hi,lo), bias, resid, out_f32, out=(hi,lo), pos=[...]."""
+    a = L.GemmArgs()
+    a.groups, a.M, a.N, a.K = len(groups), M, N, K
+    a.lda = K if lda is None else lda
+    a.ldo = N if ldo is None else ldo
+    a.epilogue = epilogue
+    a.nseg = 0
+    if segs is not None:
+        a.nseg = len(segs)
+        for i, s in enumerate(segs):
+            a.seg[i] = s
+    dev = None
+    for gi, g in enumerate(groups):
+        G = a.g[gi]
+        dev = g["a"][0].device
+        G.a_hi, G.a_lo = g["a"][0].data_ptr(), g["a"][1].data_ptr()
+        G.w_hi, G.w_lo = g["w"][0].data_ptr(), g["w"][1].data_ptr()
+        G.bias = g["bias"].data_ptr() if g.get("bias") is not None else None
+        G.resid = g["resid"].data_ptr() if g.get("resid") is not None else None
+        G.out_f32 = g["out_f32"].data_ptr() if g.get("out_f32") is not None else None
+        if g.get("out") is not None:
+            G.out_hi, G.out_lo = g["out"][0].data_ptr(), g["out"][1].data_ptr()
+        for i, p in enumerate(g.get("pos") or []):
+            G.pos[i] = p.data_ptr()
+    L.check(L.lib().dupl_gemm_bf16x3(C.byref(a), L.stream_ptr(dev)), "dupl_gemm_bf16x3")
+
+
+def layernorm_split(x, gamma, beta, out_hi, out_lo, eps=1e-6):
+    rows, cols = x.shape
+    L.check(L.lib().dupl_layernorm_split(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(out_hi), L.ptr(out_lo),
+                                         rows, cols, eps, L.stream_ptr(x.device)), "dupl_layernorm_split")
+
+
+def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale):
+    a = L.AttentionArgs()
+    a.nseg = len(segs)
+    for i, s in enumerate(segs):
+        a.seg[i] = s
+    a.M, a.heads, a.scale = qkv_hi.shape[0], heads, scale
+    a.qkv_hi, a.qkv_lo = qkv_hi.data_ptr(), qkv_lo.data_ptr()
+    a.out_hi, a.out_lo = out_hi.data_ptr(), out_lo.data_ptr()
+    L.check(L.lib().dupl_attention_fwd(C.byref(a), L.stream_ptr(qkv_hi.device)), "dupl_attention_fwd")
+
+
+def patchify(images, seg, flip_twin, out_hi, out_lo):
+    b, _, H, W = images.shape
+    L.check(L.lib().dupl_patchify(L.ptr(images), b, H, W, C.byref(seg), 1 if flip_twin else 0, L.ptr(out_hi),
+                                  L.ptr(out_lo), L.stream_ptr(images.device)), "dupl_patchify")
+
+
+def pos_embed_resize(pos_embed, gh, gw):
+    """pos_embed [1, 1+S*S, D] -> [1+gh*gw, D]"""
+    pe = L.f32c(pos_embed).reshape(pos_embed.shape[-2], pos_embed.shape[-1])
+    S = int(round((pe.shape[0] - 1) ** 0.5))
+    out = torch.empty(1 + gh * gw, pe.shape[1], dtype=torch.float32, device=pe.device)
+    L.check(L.lib().dupl_pos_embed_resize(L.ptr(pe), L.ptr(out), S, gh, gw, pe.shape[1], L.stream_ptr(pe.device)),
+            "dupl_pos_embed_resize")
+    return out
+
+
+def cls_rows(tok, cls_token, pos_list, segs):
+    arr = (C.c_void_p * len(segs))(*[p.data_ptr() for p in pos_list])
+    L.check(L.lib().dupl_cls_rows(L.ptr(tok), L.ptr(cls_token), arr, _segs(segs), len(segs), tok.shape[1],
+                                  L.stream_ptr(tok.device)), "dupl_cls_rows")
+
+
+def cam_contract(tok, gamma, beta, w, segs, eps=1e-6):
+    """-> list of [batch, K, gh, gw] tensors (views of one buffer), one per segment."""
+    K, D = w.shape[0], tok.shape[1]
+    sizes = [s.batch * K * s.gh * s.gw for s in segs]
+    out = torch.empty(sum(sizes), dtype=torch.float32, device=tok.device)
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o)
+        o += n
+    off_arr = (C.c_int64 * len(segs))(*offs)
+    L.check(L.lib().dupl_cam_contract(L.ptr(tok), L.ptr(gamma), L.ptr(beta), eps, L.ptr(w), K, D, _segs(segs), len(segs),
+                                      L.ptr(out), off_arr, L.stream_ptr(tok.device)), "dupl_cam_contract")
+    return [out[o:o + n].view(s.batch, K, s.gh, s.gw) for o, n, s in zip(offs, sizes, segs)]
+
+
+# ------------------------------------------------------------------ CAM post / labels
+def mscam_post(lowres, b, H, W):
+    """lowres: list of [2b, K, gh, gw] (scale 1.0 first) -> [b, K, H, W]"""
+    K = lowres[0].shape[1]
+    dev = lowres[0].device
+    a = L.MscamArgs()
+    a.nscale = len(lowres)
+    keep = []
+    for i, t in enumerate(lowres):
+        t = L.f32c(t)
+        keep.append(t)
+        if t.shape[0] != 2 * b or t.shape[1] != K:
+            raise ValueError("mscam_post: every scale must be [2b, K, gh, gw]")
+        a.lowres[i] = t.data_ptr()
+        a.gh[i], a.gw[i] = t.shape[2], t.shape[3]
+    out = torch.empty(b, K, H, W, dtype=torch.float32, device=dev)
+    mm = torch.empty(b * K * 2, dtype=torch.float32, device=dev)
+    a.b, a.K, a.H, a.W = b, K, H, W
+    a.out, a.minmax = out.data_ptr(), mm.data_ptr()
+    L.check(L.lib().dupl_mscam_post(C.byref(a), L.stream_ptr(dev)), "dupl_mscam_post")
+    return out
+
+
+def box_to_device(img_box, device):
+    """img_box [b,4] (int16 CPU tensor in the reference's loader) -> int32 device tensor."""
+    t = torch.as_tensor(img_box)
+    return t.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+
+
+def cam_to_label(cam, cls_label, img_box, bkg_thre, high_thre, low_thre, ignore_mid, ignore_index, want_valid):
+    L.require_cuda(cam)
+    cam = L.f32c(cam)
+    b, K, h, w = cam.shape
+    dev = cam.device
+    cls = L.f32c(cls_label.to(dev))
+    a = L.CamToLabelArgs()
+    a.cam, a.cls_label = cam.data_ptr(), cls.data_ptr()
+    box = None
+    if img_box is not None:
+        box = box_to_device(img_box, dev)
+        a.img_box = box.data_ptr()
+    ht = None
+    if torch.is_tensor(high_thre):
+        ht = L.f32c(high_thre.to(dev)).reshape(-1)
+        if ht.numel() != b:
+            raise ValueError("high_thre tensor must have one entry per image")
+        a.high_thre = ht.data_ptr()
+    else:
+        a.high_thre_scalar = float(high_thre) if high_thre is not None else 0.0
+    a.low_thre = float(low_thre) if low_thre is not None else 0.0
+    a.bkg_thre = float(bkg_thre)
+    a.ignore_mid = 1 if ignore_mid else 0
+    a.ignore_index = int(ignore_index) if ignore_index is not None else 0
+    a.b, a.K, a.h, a.w = b, K, h, w
+    valid = torch.empty_like(cam) if want_valid else None
+    label = torch.empty(b, h, w, dtype=torch.int64, device=dev)
+    a.valid_cam = valid.data_ptr() if valid is not None else None
+    a.label = label.data_ptr()
+    L.check(L.lib().dupl_cam_to_label(C.byref(a), L.stream_ptr(dev)), "dupl_cam_to_label")
+    return valid, label
+
+
+def label_to_aff_mask(label, ignore_index):
+    L.require_cuda(label)
+    lab = label.to(torch.int64).contiguous()
+    b = lab.shape[0]
+    n = lab[0].numel()
+    aff = torch.empty(b, n, n, dtype=torch.int64, device=lab.device)
+    L.check(L.lib().dupl_label_to_aff_mask(L.ptr(lab), L.ptr(aff), b, n, int(ignore_index), L.stream_ptr(lab.device)),
+            "dupl_label_to_aff_mask")
+    return aff
+
+
+# ------------------------------------------------------------------ PAR / refine
+def _dil(dilations):
+    return (C.c_int32 * len(dilations))(*[int(d) for d in dilations]), len(dilations)
+
+
+def par_affinity(imgs, dilations, w1=0.3, w2=0.01):
+    imgs = L.f32c(imgs)
+    B, Cc, h, w = imgs.shape
+    arr, nd = _dil(dilations)
+    aff = torch.empty(B, 8 * nd, h, w, dtype=torch.float32, device=imgs.device)
+    L.check(L.lib().dupl_par_affinity(L.ptr(imgs), L.ptr(aff), B, Cc, h, w, arr, nd, w1, w2, L.stream_ptr(imgs.device)),
+            "dupl_par_affinity")
+    return aff
+
+
+def par_propagate(aff, masks, dilations, num_iter, nactive=None):
+    """masks [B,P,h,w] fp32 contiguous (consumed as scratch) -> propagated masks [B,P,h,w]."""
+    B, P, h, w = masks.shape
+    arr, nd = _dil(dilations)
+    scratch = torch.empty_like(masks) if nactive is None else torch.zeros_like(masks)
+    where = C.c_int32(0)
+    L.check(L.lib().dupl_par_propagate(L.ptr(aff), L.ptr(masks), L.ptr(scratch), L.ptr(nactive), B, P, h, w, arr, nd,
+                                       int(num_iter), C.byref(where), L.stream_ptr(masks.device)), "dupl_par_propagate")
+    return scratch if where.value else masks
+
+
+def refine_prologue(images, cams, cls_label, bkg_h, bkg_l):
+    images, cams = L.f32c(images), L.f32c(cams)
+    b, K, H, W = cams.shape
+    dev = cams.device
+    cls = L.f32c(cls_label.to(dev))
+    a = L.RefinePrologueArgs()
+    a.images, a.cams, a.cls_label = images.data_ptr(), cams.data_ptr(), cls.data_ptr()
+    keep = None
+    if torch.is_tensor(bkg_h):
+        keep = L.f32c(bkg_h.to(dev))
+        if keep.numel() != b * H * W:
+            raise ValueError("high_thre_map must be [b,1,H,W]")
+        a.bkg_h = keep.data_ptr()
+    else:
+        a.bkg_h_scalar = float(bkg_h)
+    a.bkg_l_scalar = float(bkg_l)
+    a.b, a.K, a.H, a.W = b, K, H, W
+    images_ds = torch.empty(b, 3, H // 2, W // 2, dtype=torch.float32, device=dev)
+    masks = torch.empty(b, 2 * (K + 1), H // 2, W // 2, dtype=torch.float32, device=dev)
+    nactive = torch.empty(b, dtype=torch.int32, device=dev)
+    a.images_ds, a.masks, a.nactive = images_ds.data_ptr(), masks.data_ptr(), nactive.data_ptr()
+    L.check(L.lib().dupl_refine_prologue(C.byref(a), L.stream_ptr(dev)), "dupl_refine_prologue")
+    return images_ds, masks, nactive, cls
+
+
+def refine_epilogue(masks, cls, img_box, H, W, ignore_index, want_parts=False):
+    b, P = masks.shape[0], masks.shape[1]
+    K = P // 2 - 1
+    dev = masks.device
+    box = box_to_device(img_box, dev)
+    a = L.RefineEpilogueArgs()
+    a.masks, a.cls_label, a.img_box = masks.data_ptr(), cls.data_ptr(), box.data_ptr()
+    a.b, a.K, a.H, a.W = b, K, H, W
+    a.ignore_index = float(ignore_index)
+    label = torch.empty(b, H, W, dtype=torch.float32, device=dev)
+    a.label = label.data_ptr()
+    lh = ll = None
+    if want_parts:
+        lh, ll = torch.empty_like(label), torch.empty_like(label)
+        a.label_h, a.label_l = lh.data_ptr(), ll.data_ptr()
+    L.check(L.lib().dupl_refine_epilogue(C.byref(a), L.stream_ptr(dev)), "dupl_refine_epilogue")
+    return (label, lh, ll) if want_parts else label

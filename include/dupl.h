@@ -1,0 +1,245 @@
+/* libdupl.so — C ABI of the B200-native DuPL hot path.
+ *
+ * The reference (Wu0409/DuPL) is pure Python: its "operator API" for this path is the module
+ * surface model/model_dupl.py, utils/cam_helper.py (= utils/camutils.py), model/PAR.py,
+ * model/losses.py, utils/dcrf.py.  There is no FFI in the reference; each entry point below
+ * names the reference function (file:line, relative to the reference root) whose arithmetic it
+ * replaces.  dupl_b200/ binds these with ctypes and re-exports the reference's Python
+ * signatures.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch's
+ *    caching allocator) owns every buffer, including workspaces; the library never allocates
+ *    or frees device memory and keeps no pointer across calls;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *    and no call reads device data on the host;
+ *  - tensors are dense row-major ("contiguous") in the stated shape, fp32 unless stated;
+ *    "split bf16" means two bf16 planes hi/lo with x ~= hi + lo (|err| <= 2^-17 |x|), the
+ *    operand format of the 3-pass tcgen05 GEMMs (hi*hi + hi*lo + lo*hi, fp32 accumulate);
+ *  - return value 0 = success, negative = DUPL_ERR_*; dupl_last_error() returns a
+ *    thread-local message for the last failure on the calling thread.
+ */
+#ifndef DUPL_H_
+#define DUPL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUPL_ABI_VERSION 1
+
+#define DUPL_OK 0
+#define DUPL_ERR_INVALID_ARGUMENT (-1)
+#define DUPL_ERR_CUDA (-2)
+#define DUPL_ERR_UNSUPPORTED (-3)
+
+int dupl_version(void);
+const char* dupl_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense path: ViT-B/16 encoder (model/backbone/vit.py:87-184,223-334) and the CAM contraction
+ * (model/model_dupl.py:69-84).
+ * ---------------------------------------------------------------------------------------- */
+
+#define DUPL_MAX_SEGMENTS 8
+#define DUPL_MAX_GROUPS 2
+
+/* A "segment" is a batch of equally-sized images flowing through the encoder: `batch` images of
+ * `tokens` = 1 + gh*gw tokens each, stored at rows [row_offset, row_offset + batch*tokens) of the
+ * token matrix (cls token first within each image, as vit.py:299-301).  The three scales of
+ * multi_scale_cam2_siamese (utils/cam_helper.py:164-204) are three segments of one matrix, so
+ * every linear layer is ONE GEMM over all scales. */
+typedef struct {
+  int32_t batch;
+  int32_t gh, gw;      /* patch grid (H/16, W/16) */
+  int32_t tokens;      /* 1 + gh*gw */
+  int32_t row_offset;  /* first token row of this segment */
+  int32_t patch_row_offset; /* first row of this segment in the patch matrix (no cls rows) */
+} dupl_segment;
+
+/* x (fp32) -> split bf16 planes.  n elements. */
+int dupl_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+
+/* Epilogues of dupl_gemm_bf16x3 */
+#define DUPL_EPI_F32 0        /* out_f32 = acc + bias                                         */
+#define DUPL_EPI_SPLIT 1      /* out_hi/lo = split(acc + bias)            (qkv: vit.py:122)     */
+#define DUPL_EPI_GELU_SPLIT 2 /* out_hi/lo = split(gelu_erf(acc + bias))  (fc1+act: vit.py:98-99) */
+#define DUPL_EPI_RESID 3      /* out_f32 = resid + acc + bias  (proj / fc2 + residual: vit.py:158-159) */
+#define DUPL_EPI_PATCH 4      /* out_f32[token row] = acc + bias + pos_embed (vit.py:292-304)  */
+
+typedef struct {
+  const void* a_hi;
+  const void* a_lo; /* [M, K] split bf16, row stride lda */
+  const void* w_hi;
+  const void* w_lo;    /* [N, K] split bf16 (nn.Linear weight layout), row stride K */
+  const float* bias;   /* [N] or NULL */
+  const float* resid;  /* DUPL_EPI_RESID: [M, ldo] (may alias out_f32) */
+  float* out_f32;      /* F32 / RESID / PATCH */
+  void* out_hi;
+  void* out_lo;        /* SPLIT / GELU_SPLIT: [M, ldo] */
+  const float* pos[DUPL_MAX_SEGMENTS]; /* PATCH: per segment [tokens, N] resized pos_embed */
+} dupl_gemm_group;
+
+/* C[M,N] = A[M,K] * W[N,K]^T for `groups` independent problems of identical shape (the two
+ * students).  K % 64 == 0, N % 16 == 0, 16-byte aligned planes and row strides. */
+typedef struct {
+  int32_t groups;
+  int32_t M, N, K;
+  int32_t lda, ldo;
+  int32_t epilogue;
+  int32_t nseg;                         /* PATCH only */
+  dupl_segment seg[DUPL_MAX_SEGMENTS];  /* PATCH only: patch row -> token row mapping */
+  dupl_gemm_group g[DUPL_MAX_GROUPS];
+} dupl_gemm_args;
+
+int dupl_gemm_bf16x3(const dupl_gemm_args* args, void* stream);
+
+/* LayerNorm over the last dim (biased variance, eps inside the sqrt; vit.py:146,152,256 with
+ * eps=1e-6 from deit.py:100) of x[rows, cols] -> split bf16 planes (cols % 128 == 0, <= 1024). */
+int dupl_layernorm_split(const float* x, const float* gamma, const float* beta, void* out_hi, void* out_lo,
+                         int32_t rows, int32_t cols, float eps, void* stream);
+
+/* softmax(Q K^T * scale) V per (image, head)  (vit.py:120-135), fused flash-style.
+ * qkv planes: [M, 3*heads*64] split bf16 as produced by the qkv GEMM (q | k | v, head-major);
+ * out planes: [M, heads*64] split bf16.  Attention never crosses an image boundary. */
+typedef struct {
+  int32_t nseg;
+  dupl_segment seg[DUPL_MAX_SEGMENTS];
+  int32_t M;
+  int32_t heads; /* head_dim is fixed at 64 */
+  float scale;
+  const void* qkv_hi;
+  const void* qkv_lo;
+  void* out_hi;
+  void* out_lo;
+} dupl_attention_args;
+
+int dupl_attention_fwd(const dupl_attention_args* args, void* stream);
+
+/* Image -> patch matrix rows (PatchEmbed's im2col, vit.py:176-183), fused with the bilinear
+ * (align_corners=False) resize of the input and the horizontal flip that
+ * multi_scale_cam2_siamese applies (cam_helper.py:168,183-184).
+ * images [b,3,H,W] fp32; segment gets 2b images when flip_twin != 0 (second half flipped).
+ * Output rows [patch_row_offset ...) of split-bf16 planes [*, 768], column = c*256 + py*16 + px. */
+int dupl_patchify(const float* images, int32_t b, int32_t H, int32_t W, const dupl_segment* seg,
+                  int32_t flip_twin, void* out_hi, void* out_lo, void* stream);
+
+/* Bicubic (A=-0.75, align_corners=False) resize of the 14x14 grid of pos_embed[197, D] to gh x gw,
+ * cls row copied (vit.py:294-298). out [1 + gh*gw, D]. */
+int dupl_pos_embed_resize(const float* pos_embed, float* out, int32_t src, int32_t gh, int32_t gw, int32_t D,
+                          void* stream);
+
+/* Writes the cls rows of the token matrix: tok[row_offset + i*tokens] = cls_token + pos[0]. */
+int dupl_cls_rows(float* tok, const float* cls_token, const float* const* pos, const dupl_segment* seg,
+                  int32_t nseg, int32_t D, void* stream);
+
+/* The feature x class-weight contraction of cam_only (model_dupl.py:82-83): for every patch token
+ * (cls rows skipped) cam[img, k, p] = sum_d f(tok[row, d]) * w[k, d], with f = final LayerNorm
+ * (vit.py:322) when gamma != NULL, identity otherwise (aux CAM from the un-normed block-9 output).
+ * out: per segment a dense [batch, K, gh, gw] block at out + out_offset[s] floats. */
+int dupl_cam_contract(const float* tok, const float* gamma, const float* beta, float eps, const float* w,
+                      int32_t K, int32_t D, const dupl_segment* seg, int32_t nseg, float* out,
+                      const int64_t* out_offset_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * multi_scale_cam2_siamese post-processing (utils/cam_helper.py:173-202): per scale bilinear
+ * up-sample to (H,W), max with the flipped twin, ReLU; sum over scales; per-(b,k) min-shift and
+ * max-normalise (+1e-5).  lowres[s]: [2b, K, gh_s, gw_s]; out [b, K, H, W].
+ * minmax: workspace of 2*b*K floats.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t nscale;
+  const float* lowres[DUPL_MAX_SEGMENTS];
+  int32_t gh[DUPL_MAX_SEGMENTS], gw[DUPL_MAX_SEGMENTS];
+  int32_t b, K, H, W;
+  float* out;
+  float* minmax;
+} dupl_mscam_args;
+
+int dupl_mscam_post(const dupl_mscam_args* args, void* stream);
+
+/* cam_to_label / cam_to_label_dynamic_cls (utils/cam_helper.py:8-55).
+ * cam [b,K,h,w]; cls_label [b,K] fp32; img_box [b,4] int32 (y0,y1,x0,x1) or NULL;
+ * high_thre: per-image [b] (device) or NULL to use high_thre_scalar.
+ * valid_cam (optional) [b,K,h,w]; label int64 [b,h,w]. */
+typedef struct {
+  const float* cam;
+  const float* cls_label;
+  const int32_t* img_box;
+  const float* high_thre;
+  float high_thre_scalar, low_thre, bkg_thre;
+  int32_t ignore_mid;
+  int64_t ignore_index;
+  int32_t b, K, h, w;
+  float* valid_cam;
+  int64_t* label;
+} dupl_cam_to_label_args;
+
+int dupl_cam_to_label(const dupl_cam_to_label_args* args, void* stream);
+
+/* label_to_aff_mask (utils/cam_helper.py:323-335): label int64 [b,n] -> aff int64 [b,n,n]. */
+int dupl_label_to_aff_mask(const int64_t* label, int64_t* aff, int32_t b, int32_t n, int64_t ignore_index,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PAR (model/PAR.py:64-91) and refine_cams_with_* (utils/cam_helper.py:338-440)
+ * ---------------------------------------------------------------------------------------- */
+#define DUPL_PAR_MAX_DIL 8
+
+/* aff[B, 8*ndil, h, w] = softmax_n(-mean_c((|I_c(n)-I_c(p)|/(std_c(p)+1e-8)/w1)^2)) + w2*softmax_n(pos prior)
+ * (PAR.py:70-89), replicate border. imgs [B,C,h,w]. */
+int dupl_par_affinity(const float* imgs, float* aff, int32_t B, int32_t C, int32_t h, int32_t w,
+                      const int32_t* dilations_host, int32_t ndil, float w1, float w2, void* stream);
+
+/* num_iter x: m_c(p) <- sum_n aff(p,n) m_c(nbr_n(p)) (PAR.py:88-90).  masks / scratch: [B, P, h, w]
+ * plane stacks used as ping-pong buffers; nactive (device int32 [B], may be NULL = all P) gives the
+ * number of leading live planes per image, the rest is neither read nor written.
+ * *result_in_scratch_host (host, optional) reports where the result lives (num_iter odd => scratch). */
+int dupl_par_propagate(const float* aff, float* masks, float* scratch, const int32_t* nactive, int32_t B, int32_t P,
+                       int32_t h, int32_t w, const int32_t* dilations_host, int32_t ndil, int32_t num_iter,
+                       int32_t* result_in_scratch_host, void* stream);
+
+/* Prologue of refine_cams_with_dynamic_thres / _bkg_v2 (cam_helper.py:338-417): 2x2-mean
+ * down-sample of the image and of [bkg | cams], softmax over the PRESENT channels (bkg + classes
+ * with cls_label != 0; absent channels excluded exactly like the reference's nonzero+gather),
+ * for the high and the low background variant — without the reference's torch.nonzero host sync.
+ * images [b,3,H,W]; cams [b,K,H,W]; cls_label [b,K]; bkg_h: map [b,1,H,W] or NULL (use bkg_h_scalar).
+ * out: images_ds [b,3,H/2,W/2]; masks [b, P = 2*(K+1), H/2, W/2]: live planes of image i are
+ * a = v*nch_i + slot with v in {0: high, 1: low}, slot 0 = background, slot s = s-th present class in
+ * ascending order (the reference's valid_key), nch_i = 1 + #present; nactive[i] = 2*nch_i (device). */
+typedef struct {
+  const float* images;
+  const float* cams;
+  const float* cls_label;
+  const float* bkg_h;
+  float bkg_h_scalar, bkg_l_scalar;
+  int32_t b, K, H, W;
+  float* images_ds;
+  float* masks;
+  int32_t* nactive;
+} dupl_refine_prologue_args;
+
+int dupl_refine_prologue(const dupl_refine_prologue_args* args, void* stream);
+
+/* Epilogue (cam_helper.py:419-431,434-440): bilinear x2 up-sample of the propagated masks, arg-max
+ * over the live channels (first index on ties), valid_key lookup, img_box paste on an ignore canvas,
+ * high/low merge.  masks as above -> label fp32 [b,H,W] in {0..K, ignore}. */
+typedef struct {
+  const float* masks;
+  const float* cls_label;
+  const int32_t* img_box;
+  int32_t b, K, H, W;
+  float ignore_index;
+  float* label;
+  float* label_h; /* optional per-variant outputs (may be NULL) */
+  float* label_l;
+} dupl_refine_epilogue_args;
+
+int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUPL_H_ */

@@ -1,0 +1,143 @@
+"""GPU parity tests of the dense path (tcgen05 GEMM, LayerNorm, attention, encoder) through the C ABI.
+Oracle: torch fp64 on the same inputs for single kernels, oracle/dupl_oracle.py for the encoder."""
+import pytest
+import torch
+
+from helpers import init_state_dict, rel_err, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from dupl_b200 import _lib as L, ops
+    return L, ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def test_split_bf16_reconstructs_to_2e_minus_16():
+    L, ops = _ops()
+    x = _rand(1000, 37, seed=1)
+    hi, lo = ops.split_bf16(x)
+    rec = hi.float() + lo.float()
+    assert ((rec - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(128, 256, 64, 1), (300, 256, 128, 1), (1000, 768, 768, 2), (129, 2304, 768, 1),
+                                           (517, 3072, 768, 2), (777, 768, 3072, 1), (260, 128, 256, 1), (200, 32, 768, 2)])
+def test_gemm_f32_bias(M, N, K, groups):
+    L, ops = _ops()
+    gs, refs = [], []
+    for g in range(groups):
+        a, w, bias = _rand(M, K, seed=10 + g), _rand(N, K, seed=20 + g, scale=0.05), _rand(N, seed=30 + g)
+        out = torch.full((M, N), float("nan"), device="cuda")
+        gs.append(dict(a=ops.split_bf16(a), w=ops.split_bf16(w), bias=bias, out_f32=out))
+        refs.append((a.double() @ w.double().t() + bias.double()))
+    ops.gemm_bf16x3(gs, M, N, K, L.EPI_F32)
+    torch.cuda.synchronize()
+    for g in range(groups):
+        assert torch.isfinite(gs[g]["out_f32"]).all()
+        assert rel_err(gs[g]["out_f32"], refs[g]) < 3e-5
+
+
+def test_gemm_epilogues():
+    L, ops = _ops()
+    M, N, K = 391, 768, 256
+    a, w, bias, resid = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.1), _rand(N, seed=3), _rand(M, N, seed=4)
+    ref = a.double() @ w.double().t() + bias.double()
+    A, W = ops.split_bf16(a), ops.split_bf16(w)
+    # SPLIT
+    hi, lo = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"), torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_bf16x3([dict(a=A, w=W, bias=bias, out=(hi, lo))], M, N, K, L.EPI_SPLIT)
+    assert rel_err(hi.float() + lo.float(), ref) < 5e-5
+    # GELU_SPLIT
+    ops.gemm_bf16x3([dict(a=A, w=W, bias=bias, out=(hi, lo))], M, N, K, L.EPI_GELU_SPLIT)
+    assert rel_err(hi.float() + lo.float(), torch.nn.functional.gelu(ref)) < 5e-5
+    # RESID in place
+    out = resid.clone()
+    ops.gemm_bf16x3([dict(a=A, w=W, bias=bias, resid=out, out_f32=out)], M, N, K, L.EPI_RESID)
+    assert rel_err(out, ref + resid.double()) < 3e-5
+
+
+def test_gemm_rejects_bad_arguments():
+    L, ops = _ops()
+    a, w = _rand(16, 60), _rand(16, 60)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.gemm_bf16x3([dict(a=ops.split_bf16(a), w=ops.split_bf16(w), out_f32=torch.empty(16, 16, device="cuda"))],
+                        16, 16, 60, L.EPI_F32)
+
+
+def test_layernorm_split():
+    L, ops = _ops()
+    x = _rand(333, 768, seed=5) * 3 + 1
+    g, b = _rand(768, seed=6), _rand(768, seed=7)
+    hi = torch.empty(333, 768, dtype=torch.bfloat16, device="cuda")
+    lo = torch.empty_like(hi)
+    ops.layernorm_split(x, g, b, hi, lo, eps=1e-6)
+    ref = torch.nn.functional.layer_norm(x.double(), (768,), g.double(), b.double(), eps=1e-6)
+    assert rel_err(hi.float() + lo.float(), ref) < 3e-5
+
+
+@pytest.mark.parametrize("shapes", [[(2, 3, 3)], [(1, 14, 14)], [(2, 8, 9), (1, 2, 2)], [(1, 28, 28)], [(2, 5, 7), (1, 14, 14), (3, 1, 1)]])
+def test_attention_matches_fp64_softmax_attention(shapes):
+    L, ops = _ops()
+    segs, M, _ = ops.make_segments(shapes)
+    qkv = _rand(M, 2304, seed=8)
+    qh, ql = ops.split_bf16(qkv)
+    oh = torch.zeros(M, 768, dtype=torch.bfloat16, device="cuda")
+    ol = torch.zeros_like(oh)
+    ops.attention_fwd(qh, ql, oh, ol, segs, 12, 0.125)
+    out = oh.float() + ol.float()
+    x = qkv.double()
+    for s in segs:
+        for i in range(s.batch):
+            r0 = s.row_offset + i * s.tokens
+            blk = x[r0:r0 + s.tokens].reshape(s.tokens, 3, 12, 64).permute(1, 2, 0, 3)
+            att = torch.softmax(blk[0] @ blk[1].transpose(-1, -2) * 0.125, -1)
+            ref = (att @ blk[2]).permute(1, 0, 2).reshape(s.tokens, 768)
+            assert rel_err(out[r0:r0 + s.tokens], ref) < 1e-4
+
+
+def _load_model(num_classes=21):
+    from dupl_b200.model.model_dupl import siamese_network
+    P = init_state_dict(num_classes)
+    m = siamese_network("deit_base_patch16_224", num_classes=num_classes, pretrained=False, aux_layer=-3)
+    m.load_state_dict(P, strict=True)
+    return m.cuda().eval(), P
+
+
+def test_cam_only_matches_oracle():
+    """network.forward(cam_only=True) (model_dupl.py:69-84): CAM / aux-CAM within 1e-3 relative of fp32."""
+    from oracle import dupl_oracle as O
+    m, P = _load_model()
+    x = synth_images(2, 64, 96, seed=3)
+    with torch.no_grad():
+        ca1, c1, ca2, c2 = m(x.cuda(), cam_only=True)
+        oa1, o1 = O.network_cam_only(P, 1, x)
+        oa2, o2 = O.network_cam_only(P, 2, x)
+    for got, want in ((c1, o1), (ca1, oa1), (c2, o2), (ca2, oa2)):
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 1e-3
+    ca, c = m(x.cuda(), cam_only=True, branch=2)
+    assert rel_err(c, o2) < 1e-3 and rel_err(ca, oa2) < 1e-3
+
+
+def test_multi_scale_cam_matches_oracle():
+    """multi_scale_cam2_siamese (cam_helper.py:164-204): normalised CAMs within 1e-3 absolute (range [0,1))."""
+    from dupl_b200.utils import cam_helper
+    from oracle import dupl_oracle as O
+    m, P = _load_model()
+    x = synth_images(2, 64, 64, seed=4)
+    with torch.no_grad():
+        cam, aux = cam_helper.multi_scale_cam2_siamese(m, x.cuda(), (1.0, 0.5, 1.5), branch=1)
+        ocam, oaux = O.multi_scale_cam(P, 1, x, (1.0, 0.5, 1.5))
+    assert cam.shape == ocam.shape == (2, 20, 64, 64)
+    assert (cam.cpu() - ocam).abs().max().item() < 1e-3
+    assert (aux.cpu() - oaux).abs().max().item() < 1e-3
+    (c1, a1), (c2, a2) = cam_helper.multi_scale_cam2_pair(m, x.cuda(), (1.0, 0.5, 1.5))
+    assert torch.equal(c1, cam) and torch.equal(a1, aux)
+    ocam2, _ = O.multi_scale_cam(P, 2, x, (1.0, 0.5, 1.5))
+    assert (c2.cpu() - ocam2).abs().max().item() < 1e-3
