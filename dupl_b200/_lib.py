@@ -77,6 +77,7 @@ class RefineEpilogueArgs(C.Structure):
 _PROTOTYPES = {
     "dupl_version": (C.c_int, []),
     "dupl_last_error": (C.c_char_p, []),
+    "dupl_launch_count": (C.c_int64, []),
     "dupl_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dupl_gemm_bf16x3": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "dupl_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

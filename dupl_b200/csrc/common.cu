@@ -3,11 +3,15 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace dupl {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -78,3 +82,4 @@ int sm_count() {
 
 extern "C" int dupl_version(void) { return DUPL_ABI_VERSION; }
 extern "C" const char* dupl_last_error(void) { return dupl::g_err; }
+extern "C" int64_t dupl_launch_count(void) { return dupl::g_launches.load(); }

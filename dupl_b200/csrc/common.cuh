@@ -31,7 +31,14 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // Checks the launch itself (not asynchronous execution errors: the library never synchronises).
-#define DUPL_LAUNCH_OK() DUPL_CUDA_OK(cudaGetLastError())
+#define DUPL_LAUNCH_OK()            \
+  do {                              \
+    ::dupl::count_launch();         \
+    DUPL_CUDA_OK(cudaGetLastError()); \
+  } while (0)
+
+// Number of kernels this library has launched in the process (dupl_launch_count()).
+void count_launch();
 
 // 2-D bf16 tensor map: `rows` x `cols` elements, row stride `ld` elements, box = box_rows x 64
 // columns (128 bytes) with the 128-byte swizzle; out-of-bounds elements read as zero.

@@ -1,0 +1,58 @@
+"""The CAM -> PAR -> pseudo-label step of the training loop as ONE call:
+what train_final_voc.py:263-343 does between `inputs.to(device)` and the segmentation loss, with the
+script-side glue (denormalize_img2, cls_label broadcast, threshold map) included so that callers who
+do not keep the reference's inline loop get the same labels from the same inputs.
+
+Nothing here is new arithmetic: it sequences the drop-in functions of utils/cam_helper.py.
+"""
+import torch
+
+from .model.PAR import PAR
+from .utils import cam_helper
+
+IMG_MEAN = (123.675, 116.28, 103.53)
+IMG_STD = (58.395, 57.12, 57.375)
+
+
+def denormalize_img2(imgs):
+    """utils/imutils.py:17-31 (script-side, feeds PAR): x*std+mean -> uint8 truncation -> /255.
+    Plain torch elementwise ops, exactly as the reference's caller executes them."""
+    out = torch.zeros_like(imgs)
+    for c in range(3):
+        out[:, c] = imgs[:, c] * IMG_STD[c] + IMG_MEAN[c]
+    return out.type(torch.uint8) / 255.0
+
+
+class CamParStep:
+    """multi_scale_cam2_siamese for both students + refine_cams_with_dynamic_thres for both students."""
+
+    def __init__(self, model, cam_scales=(1.0, 0.5, 1.5), low_thre=0.25, ignore_index=255,
+                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False):
+        self.model = model
+        self.scales = tuple(cam_scales)
+        self.low_thre = low_thre
+        self.ignore_index = ignore_index
+        self.par = PAR(num_iter=num_iter, dilations=list(dilations))  # train_final_voc.py:160
+        self.fuse_students = fuse_students
+
+    @torch.no_grad()
+    def __call__(self, inputs, cls_label, img_box, high_thres):
+        """inputs [b,3,H,W] normalised, cls_label [b,K], img_box [b,4] (CPU int16 as the loader yields it),
+        high_thres [b] per-image high threshold (train_final_voc.py:263-275).
+        Returns (label_1, label_2, cams_1, cams_2): refined labels float32 [b,H,W] in {0..K,255}."""
+        b, _, h, w = inputs.shape
+        inputs_denorm = denormalize_img2(inputs.clone())
+        if self.fuse_students:
+            (cams_1, aux_1), (cams_2, aux_2) = cam_helper.multi_scale_cam2_pair(self.model, inputs, self.scales)
+        else:
+            cams_1, aux_1 = cam_helper.multi_scale_cam2_siamese(self.model, inputs, self.scales, branch=1)
+            cams_2, aux_2 = cam_helper.multi_scale_cam2_siamese(self.model, inputs, self.scales, branch=2)
+        # train_final_voc.py:330-335 multiplies the CAMs by the broadcast cls_label before refining.
+        # cls_label is one-hot {0,1}: present classes are multiplied by exactly 1.0 and absent classes are
+        # never read by the refine kernels, so the 64 MB elementwise pass is skipped without changing a bit.
+        thr_map = high_thres.to(inputs.device, torch.float32).reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
+        kw = dict(cls_labels=cls_label, high_thre_map=thr_map, low_thre=self.low_thre,
+                  ignore_index=self.ignore_index, img_box=img_box)
+        lab_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1, **kw)
+        lab_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2, **kw)
+        return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)

@@ -37,6 +37,8 @@ extern "C" {
 
 int dupl_version(void);
 const char* dupl_last_error(void);
+/* Number of CUDA kernels launched by this library in the calling process so far. */
+int64_t dupl_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Dense path: ViT-B/16 encoder (model/backbone/vit.py:87-184,223-334) and the CAM contraction
