@@ -83,8 +83,8 @@ _PROTOTYPES = {
     "dupl_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "dupl_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
-    "dupl_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Segment), C.c_int32,
-                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dupl_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Segment), C.c_int32, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dupl_pos_embed_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dupl_cls_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(Segment), C.c_int32,
                                 C.c_int32, C.c_void_p]),

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
 // ------------------------------------------------------------------------------ patchify
 // One thread = 8 consecutive kx of one (patch row, c, ky): 16 B to each plane.
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ images, int b, int H, int W,
-                                                       dupl_segment sg, int flip_twin,
+                                                       dupl_segment sg, int hs, int ws, int flip_twin,
                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int np = sg.gh * sg.gw;
   const long total = static_cast<long>(sg.batch) * np * 96;
@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   const int pidx = static_cast<int>(prow % np);
   const int py = pidx / sg.gw, px = pidx % sg.gw;
   const int c = chunk / 32, ky = (chunk % 32) / 2, kx0 = (chunk % 2) * 8;
-  const int hs = sg.gh * 16, ws = sg.gw * 16;
   const bool flipped = flip_twin && img >= b;
   const int src_img = flipped ? img - b : img;
   const float* plane = images + (static_cast<long>(src_img) * 3 + c) * H * W;
@@ -291,14 +290,16 @@ extern "C" int dupl_layernorm_split(const float* x, const float* gamma, const fl
 }
 
 extern "C" int dupl_patchify(const float* images, int32_t b, int32_t H, int32_t W, const dupl_segment* seg,
-                             int32_t flip_twin, void* out_hi, void* out_lo, void* stream) {
+                             int32_t hs, int32_t ws, int32_t flip_twin, void* out_hi, void* out_lo, void* stream) {
   DUPL_CHECK_ARG(images && seg && out_hi && out_lo, "dupl_patchify: NULL pointer");
   DUPL_CHECK_ARG(b > 0 && H > 0 && W > 0 && seg->gh > 0 && seg->gw > 0, "dupl_patchify: bad shape");
+  DUPL_CHECK_ARG(hs / 16 == seg->gh && ws / 16 == seg->gw, "dupl_patchify: resized size %dx%d does not give a %dx%d patch grid",
+                 hs, ws, seg->gh, seg->gw);
   DUPL_CHECK_ARG(seg->batch == (flip_twin ? 2 * b : b), "dupl_patchify: segment batch %d != %d", seg->batch,
                  flip_twin ? 2 * b : b);
   const long total = static_cast<long>(seg->batch) * seg->gh * seg->gw * 96;
   patchify_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      images, b, H, W, *seg, flip_twin, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
+      images, b, H, W, *seg, hs, ws, flip_twin, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -59,27 +59,27 @@ class EncoderOutput:
     __slots__ = ("segs", "tok", "aux_tok", "M")
 
 
-def run_encoder(planes, images_per_seg, seg_shapes, flip_twin, aux_index, on_aux=None):
+def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=None):
     """Runs the 12 blocks for every student in `planes` over the given segments.
 
     images_per_seg: list of source image tensors [b,3,H,W] (fp32, cuda); segment i is patchified from
-    images_per_seg[i] resized to (16*gh_i, 16*gw_i), with a flipped twin batch when flip_twin.
-    seg_shapes: list of (batch, gh, gw).
+    images_per_seg[i] resized to seg_sizes[i] = (hs, ws), with a flipped twin batch when flip_twin.
     aux_index: block index whose output feeds the aux head (embeds[aux_layer], vit.py:319-326).
     on_aux(g, tok_g, segs): called right after block `aux_index` (0-based) for every student when that
     index is not the last block (the last entry of `embeds` is the final-normed tensor, vit.py:323-324).
     Returns (segs, [tok_g]) with tok_g the fp32 residual stream BEFORE the final LayerNorm.
     """
     G = len(planes)
-    segs, M, Mp = ops.make_segments(seg_shapes)
+    mult = 2 if flip_twin else 1
+    segs, M, Mp = ops.make_segments([(mult * img.shape[0], hs // 16, ws // 16) for img, (hs, ws) in zip(images_per_seg, seg_sizes)])
     dev = images_per_seg[0].device
     bf = dict(dtype=torch.bfloat16, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
 
     patch_hi = torch.empty(Mp, EMBED, **bf)
     patch_lo = torch.empty(Mp, EMBED, **bf)
-    for s, img in zip(segs, images_per_seg):
-        ops.patchify(L.f32c(img), s, flip_twin, patch_hi, patch_lo)
+    for s, img, size in zip(segs, images_per_seg, seg_sizes):
+        ops.patchify(L.f32c(img), s, size, flip_twin, patch_hi, patch_lo)
 
     tok = [torch.empty(M, EMBED, **f32) for _ in range(G)]
     xn = [(torch.empty(M, EMBED, **bf), torch.empty(M, EMBED, **bf)) for _ in range(G)]

@@ -56,20 +56,19 @@ class network(nn.Module):
         return dense.network_forward(self, x, val=val, cam_with_grad=cam_with_grad)
 
 
-def cam_only_forward(nets, x, seg_images=None, seg_shapes=None, flip_twin=False):
+def cam_only_forward(nets, x, seg_images=None, seg_sizes=None, flip_twin=False):
     """cam_only path of `network.forward` (model_dupl.py:69-84) for one or two students at once.
 
     Default: one segment holding the batch `x` as given.  multi_scale_cam2_siamese passes several
     segments (one per scale, with flipped twins) so that all scales share each GEMM launch.
-    Returns, per student, (cam_aux, cam) as lists over segments when seg_shapes is given, else tensors.
+    Returns, per student, (cam_aux, cam) as lists over segments when seg_sizes is given, else tensors.
     """
     L.require_cuda(x)
-    single = seg_shapes is None
+    single = seg_sizes is None
     if single:
-        B, _, H, W = x.shape
-        if H % 16 or W % 16:
-            raise ValueError("input height/width must be multiples of the 16-pixel patch size")
-        seg_images, seg_shapes = [x], [(B, H // 16, W // 16)]
+        seg_images, seg_sizes = [x], [tuple(x.shape[-2:])]
+    if any(hs < 16 or ws < 16 for hs, ws in seg_sizes):
+        raise ValueError("inputs must be at least one 16x16 patch large")
     with torch.no_grad():
         planes = [n.planes() for n in nets]
         aux_idx = nets[0].encoder.aux_block_index()
@@ -79,7 +78,7 @@ def cam_only_forward(nets, x, seg_images=None, seg_shapes=None, flip_twin=False)
             w = nets[g].aux_classifier.weight.detach().reshape(nets[g].num_classes - 1, -1)
             aux_out[g] = ops.cam_contract(tok_g, None, None, L.f32c(w), segs)
 
-        segs, tok = E.run_encoder(planes, seg_images, seg_shapes, flip_twin, aux_idx, on_aux)
+        segs, tok = E.run_encoder(planes, seg_images, seg_sizes, flip_twin, aux_idx, on_aux)
         res = []
         for g, n in enumerate(nets):
             gam, bet = n.encoder.norm.weight.detach(), n.encoder.norm.bias.detach()

@@ -82,9 +82,10 @@ def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale):
     L.check(L.lib().dupl_attention_fwd(C.byref(a), L.stream_ptr(qkv_hi.device)), "dupl_attention_fwd")
 
 
-def patchify(images, seg, flip_twin, out_hi, out_lo):
+def patchify(images, seg, size, flip_twin, out_hi, out_lo):
+    """size = (hs, ws): the resolution the images are resized to before the 16x16 patch grid is cut."""
     b, _, H, W = images.shape
-    L.check(L.lib().dupl_patchify(L.ptr(images), b, H, W, C.byref(seg), 1 if flip_twin else 0, L.ptr(out_hi),
+    L.check(L.lib().dupl_patchify(L.ptr(images), b, H, W, C.byref(seg), size[0], size[1], 1 if flip_twin else 0, L.ptr(out_hi),
                                   L.ptr(out_lo), L.stream_ptr(images.device)), "dupl_patchify")
 
 

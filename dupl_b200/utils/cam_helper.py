@@ -53,13 +53,8 @@ def _fused_mscam(nets, inputs, scales):
     from ..model.model_dupl import cam_only_forward
     inputs = L.f32c(inputs)
     b, _, h, w = inputs.shape
-    shapes = []
-    for s in _scale_order(scales):
-        hs, ws = int(s * h), int(s * w)
-        if hs % 16 or ws % 16:
-            raise ValueError(f"scaled input {hs}x{ws} is not a multiple of the 16-pixel patch size")
-        shapes.append((2 * b, hs // 16, ws // 16))
-    res = cam_only_forward(nets, inputs, seg_images=[inputs] * len(shapes), seg_shapes=shapes, flip_twin=True)
+    sizes = [(int(s * h), int(s * w)) for s in _scale_order(scales)]  # cam_helper.py:183
+    res = cam_only_forward(nets, inputs, seg_images=[inputs] * len(sizes), seg_sizes=sizes, flip_twin=True)
     return [(ops.mscam_post(cams, b, h, w), ops.mscam_post(aux, b, h, w)) for (aux, cams) in res]
 
 

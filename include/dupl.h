@@ -123,10 +123,12 @@ int dupl_attention_fwd(const dupl_attention_args* args, void* stream);
 /* Image -> patch matrix rows (PatchEmbed's im2col, vit.py:176-183), fused with the bilinear
  * (align_corners=False) resize of the input and the horizontal flip that
  * multi_scale_cam2_siamese applies (cam_helper.py:168,183-184).
- * images [b,3,H,W] fp32; segment gets 2b images when flip_twin != 0 (second half flipped).
+ * images [b,3,H,W] fp32 are resized to hs x ws (hs == H and ws == W: no resize); the patch grid is
+ * gh = hs/16, gw = ws/16 (a ragged right/bottom border is ignored, like the stride-16 conv does);
+ * the segment gets 2b images when flip_twin != 0 (second half = resized images flipped along x).
  * Output rows [patch_row_offset ...) of split-bf16 planes [*, 768], column = c*256 + py*16 + px. */
-int dupl_patchify(const float* images, int32_t b, int32_t H, int32_t W, const dupl_segment* seg,
-                  int32_t flip_twin, void* out_hi, void* out_lo, void* stream);
+int dupl_patchify(const float* images, int32_t b, int32_t H, int32_t W, const dupl_segment* seg, int32_t hs,
+                  int32_t ws, int32_t flip_twin, void* out_hi, void* out_lo, void* stream);
 
 /* Bicubic (A=-0.75, align_corners=False) resize of the 14x14 grid of pos_embed[197, D] to gh x gw,
  * cls row copied (vit.py:294-298). out [1 + gh*gw, D]. */

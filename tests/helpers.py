@@ -83,3 +83,11 @@ def init_state_dict(num_classes=21, seed=0, students=(1, 2)):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def mscam_err(got, want, want_sum):
+    """max over planes of |got - want| divided by the plane's conditioning 1/(range+1e-5), i.e. the error
+    expressed in units of the UN-normalised CAM (see oracle.mscam_condition)."""
+    from oracle import dupl_oracle as O
+    e = (got.detach().cpu().float() - want).abs().amax((2, 3), keepdim=True) / O.mscam_condition(want_sum)
+    return e.max().item()

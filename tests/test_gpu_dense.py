@@ -3,7 +3,7 @@ Oracle: torch fp64 on the same inputs for single kernels, oracle/dupl_oracle.py 
 import pytest
 import torch
 
-from helpers import init_state_dict, rel_err, synth_images
+from helpers import init_state_dict, mscam_err, rel_err, synth_images
 
 pytestmark = pytest.mark.gpu
 
@@ -133,11 +133,13 @@ def test_multi_scale_cam_matches_oracle():
     x = synth_images(2, 64, 64, seed=4)
     with torch.no_grad():
         cam, aux = cam_helper.multi_scale_cam2_siamese(m, x.cuda(), (1.0, 0.5, 1.5), branch=1)
-        ocam, oaux = O.multi_scale_cam(P, 1, x, (1.0, 0.5, 1.5))
+        ocam, oaux, osum, oaux_sum = O.multi_scale_cam(P, 1, x, (1.0, 0.5, 1.5), return_sums=True)
     assert cam.shape == ocam.shape == (2, 20, 64, 64)
-    assert (cam.cpu() - ocam).abs().max().item() < 1e-3
-    assert (aux.cpu() - oaux).abs().max().item() < 1e-3
+    # tolerance 1e-3 of the CAM scale; planes the ReLU leaves ~constant amplify any error by 1/(range+1e-5)
+    assert mscam_err(cam, ocam, osum) < 1e-3 and mscam_err(aux, oaux, oaux_sum) < 1e-3
+    well = O.mscam_condition(osum) < 20
+    assert ((cam.cpu() - ocam).abs() * well).max().item() < 1e-3
     (c1, a1), (c2, a2) = cam_helper.multi_scale_cam2_pair(m, x.cuda(), (1.0, 0.5, 1.5))
     assert torch.equal(c1, cam) and torch.equal(a1, aux)
-    ocam2, _ = O.multi_scale_cam(P, 2, x, (1.0, 0.5, 1.5))
-    assert (c2.cpu() - ocam2).abs().max().item() < 1e-3
+    ocam2, _, osum2, _ = O.multi_scale_cam(P, 2, x, (1.0, 0.5, 1.5), return_sums=True)
+    assert mscam_err(c2, ocam2, osum2) < 1e-3
