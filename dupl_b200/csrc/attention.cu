@@ -1,17 +1,19 @@
 // Fused attention forward for the ViT blocks (reference vit.py:120-135 materialises
 // the [B,12,N,N] matrix): softmax(Q K^T * scale) V per (image, head), flash-style on tcgen05.
 //
-// One CTA = one (image, head, 128-query tile); 128 threads, thread t owns query row t end to end:
-//   S = Q K^T        tcgen05.mma 128x64x16, split-bf16 (hi*hi + hi*lo + lo*hi), fp32 in TMEM
-//   softmax          tcgen05.ld gives each thread its whole row -> running max / sum in registers,
-//                    no shuffles; P is split to bf16 hi/lo and written to shared memory in the
-//                    128-byte-swizzled K-major layout the tensor core reads
-//   O_tile = P V     V tile used in place as an MN-major operand (no transpose pass), fp32 in TMEM,
-//                    then O = O*alpha + O_tile in registers
-// Q/K/V tiles are staged by TMA straight out of the qkv GEMM's [M, 2304] planes.  K and V are
-// single-buffered but each load is issued as soon as its buffer drains (K(j+1) after S(j) is
-// complete, V(j+1) after P V(j)), so the copies hide behind the softmax; shared memory is 96 KB so
-// two CTAs share an SM and one CTA's softmax overlaps the other's MMAs.
+// One CTA = one (image, head) and TWO 128-query tiles A and B that share every K/V tile
+// ("ping-pong"): while the softmax warps of tile A work on S_A(j), the tensor core computes
+// S_B(j), P_A V, S_A(j+1) ... so neither pipe waits for the other in steady state.
+//   warps 0-3   softmax of tile A      thread t owns query row t end to end: tcgen05.ld hands it the
+//   warps 4-7   softmax of tile B      whole row of S -> running max / sum in registers, no shuffles;
+//                                      P is split to bf16 hi/lo and written to shared memory in the
+//                                      128-byte-swizzled K-major layout the tensor core reads;
+//                                      O = O*alpha + (P V) is accumulated in registers from the fresh
+//                                      per-tile product, so TMEM is never rescaled
+//   warp 8      TMA producer: Q_A, Q_B once, then K(j) / V(j) tiles, 2 stages each, straight out of
+//               the qkv GEMM's [M, 2304] split-bf16 planes (V is consumed in place as an MN-major operand)
+//   warp 9      MMA issuer (one lane): S = Q K^T and P V as 3-pass split-bf16 tcgen05.mma 128x64x16
+// TMEM: S_A | S_B | O_A | O_B, 64 fp32 columns each.  Shared memory 192 KB: one CTA per SM.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -20,11 +22,17 @@ namespace dupl {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // one plane 16 KB
-constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;  // one plane 8 KB
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // one plane 16 KB
-constexpr int ATT_SMEM = 2 * ATT_Q_BYTES + 4 * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024 + 128;
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // one plane of one query tile: 16 KB
+constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;  // one plane of one K or V tile: 8 KB
+constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // one plane of one P tile: 16 KB
+constexpr int ATT_STAGES = 2;
+// Q: 2 tiles x 2 planes | K: stages x 2 planes | V: stages x 2 planes | P: 2 tiles x 2 planes
+constexpr int ATT_OFF_K = 4 * ATT_Q_BYTES;
+constexpr int ATT_OFF_V = ATT_OFF_K + ATT_STAGES * 2 * ATT_KV_BYTES;
+constexpr int ATT_OFF_P = ATT_OFF_V + ATT_STAGES * 2 * ATT_KV_BYTES;
+constexpr int ATT_OFF_BAR = ATT_OFF_P + 4 * ATT_P_BYTES;
+constexpr int ATT_SMEM = ATT_OFF_BAR + 256 + 1024;
 
 struct AttnParamsDev {
   CUtensorMap tm_q_hi, tm_q_lo, tm_kv_hi, tm_kv_lo;
@@ -36,33 +44,50 @@ struct AttnParamsDev {
   __nv_bfloat16* out_lo;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2) attention_fwd_kernel(const __grid_constant__ AttnParamsDev p) {
+enum {  // mbarrier slots
+  BAR_Q = 0,
+  BAR_K_FULL = 1,                       // [stages]
+  BAR_K_EMPTY = BAR_K_FULL + ATT_STAGES,
+  BAR_V_FULL = BAR_K_EMPTY + ATT_STAGES,
+  BAR_V_EMPTY = BAR_V_FULL + ATT_STAGES,
+  BAR_S_FULL = BAR_V_EMPTY + ATT_STAGES,  // [2 tiles]
+  BAR_S_FREE = BAR_S_FULL + 2,
+  BAR_P_READY = BAR_S_FREE + 2,
+  BAR_O_FULL = BAR_P_READY + 2,
+  BAR_COUNT = BAR_O_FULL + 2
+};
+
+__device__ __forceinline__ void issue_split_mma(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                uint32_t b_lo, uint32_t idesc, uint32_t b_kstep) {
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = (pass == 2) ? a_lo : a_hi;
+    const uint32_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) = 64-deep contraction
+      tc_mma_f16(d_tmem, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __grid_constant__ AttnParamsDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                       // hi | lo
-  uint8_t* sK = sQ + 2 * ATT_Q_BYTES;       // hi | lo
-  uint8_t* sV = sK + 2 * ATT_KV_BYTES;      // hi | lo
-  uint8_t* sP = sV + 2 * ATT_KV_BYTES;      // hi | lo
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_P_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int lane = tid & 31;
 
-  // ---- which (segment, image, head, q-tile) is this CTA?
+  // ---- which (segment, image, head, pair of q-tiles) is this CTA?
   int si = 0;
   for (int s = 1; s < p.nseg; ++s)
     if (static_cast<int>(blockIdx.x) >= p.cta_start[s]) si = s;
   const dupl_segment sg = p.seg[si];
-  const int q_tiles = (sg.tokens + ATT_BQ - 1) / ATT_BQ;
+  const int q_pairs = (sg.tokens + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
   int local = blockIdx.x - p.cta_start[si];
-  const int qt = local % q_tiles;
-  local /= q_tiles;
+  const int qp = local % q_pairs;
+  local /= q_pairs;
   const int head = local % p.heads;
   const int img = local / p.heads;
   const int img_row0 = sg.row_offset + img * sg.tokens;
@@ -70,179 +95,221 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_fwd_kernel(const __g
   const int hd = p.heads * ATT_D;  // 768
 
   if (tid == 0) {
-    tma_prefetch_desc(&p.tm_q_hi);
-    tma_prefetch_desc(&p.tm_q_lo);
-    tma_prefetch_desc(&p.tm_kv_hi);
-    tma_prefetch_desc(&p.tm_kv_lo);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < BAR_COUNT; ++i) {
+      const bool wg_arrives = (i >= BAR_S_FREE && i < BAR_O_FULL);  // s_free / p_ready: all 128 softmax threads
+      mbar_init(&bars[i], wg_arrives ? 128u : 1u);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, 128);
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // 64 fp32 columns
-  const uint32_t tmem_o = tmem_base + 64;   // 64 fp32 columns
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * ATT_Q_BYTES);
-    tma_load_2d(sQ, &p.tm_q_hi, bar_q, head * ATT_D, img_row0 + qt * ATT_BQ);
-    tma_load_2d(sQ + ATT_Q_BYTES, &p.tm_q_lo, bar_q, head * ATT_D, img_row0 + qt * ATT_BQ);
-    mbar_arrive_expect_tx(bar_k, 2 * ATT_KV_BYTES);
-    tma_load_2d(sK, &p.tm_kv_hi, bar_k, hd + head * ATT_D, img_row0);
-    tma_load_2d(sK + ATT_KV_BYTES, &p.tm_kv_lo, bar_k, hd + head * ATT_D, img_row0);
-    mbar_arrive_expect_tx(bar_v, 2 * ATT_KV_BYTES);
-    tma_load_2d(sV, &p.tm_kv_hi, bar_v, 2 * hd + head * ATT_D, img_row0);
-    tma_load_2d(sV + ATT_KV_BYTES, &p.tm_kv_lo, bar_v, 2 * hd + head * ATT_D, img_row0);
-    mbar_wait(bar_q, 0);
-  }
-
-  constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BKV, 0, 0);  // A = Q (K-major), B = K (K-major), N = 64 keys
-  constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_D, 0, 1);    // A = P (K-major), B = V (MN-major), N = 64 dims
-
-  float o[ATT_D];
-#pragma unroll
-  for (int d = 0; d < ATT_D; ++d) o[d] = 0.0f;
-  float m_run = -INFINITY, l_run = 0.0f;
-
-  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV), sP_u = smem_u32(sP);
-  const uint32_t sw = static_cast<uint32_t>(tid & 7);
-  uint8_t* p_row_hi = sP + tid * 128;
-  uint8_t* p_row_lo = sP + ATT_P_BYTES + tid * 128;
-
-  for (int j = 0; j < n_kv; ++j) {
-    const uint32_t ph = static_cast<uint32_t>(j & 1);
-    // ---- S = Q K^T
-    if (tid == 0) {
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = sQ_u + ((pass == 2) ? ATT_Q_BYTES : 0);
-        const uint32_t b = sK_u + ((pass == 1) ? ATT_KV_BYTES : 0);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          tc_mma_f16(tmem_s, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc_qk,
-                     (pass | k) != 0 ? 1u : 0u);
+  if (warp == 8) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tm_q_hi);
+      tma_prefetch_desc(&p.tm_q_lo);
+      tma_prefetch_desc(&p.tm_kv_hi);
+      tma_prefetch_desc(&p.tm_kv_lo);
+      mbar_arrive_expect_tx(&bars[BAR_Q], 4 * ATT_Q_BYTES);
+      for (int t = 0; t < 2; ++t) {
+        const int row = img_row0 + (2 * qp + t) * ATT_BQ;
+        tma_load_2d(smem + (2 * t) * ATT_Q_BYTES, &p.tm_q_hi, &bars[BAR_Q], head * ATT_D, row);
+        tma_load_2d(smem + (2 * t + 1) * ATT_Q_BYTES, &p.tm_q_lo, &bars[BAR_Q], head * ATT_D, row);
       }
-      tc_commit(bar_s);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+        const int row = img_row0 + j * ATT_BKV;
+        uint8_t* sk = smem + ATT_OFF_K + st * 2 * ATT_KV_BYTES;
+        uint8_t* sv = smem + ATT_OFF_V + st * 2 * ATT_KV_BYTES;
+        mbar_wait(&bars[BAR_K_EMPTY + st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[BAR_K_FULL + st], 2 * ATT_KV_BYTES);
+        tma_load_2d(sk, &p.tm_kv_hi, &bars[BAR_K_FULL + st], hd + head * ATT_D, row);
+        tma_load_2d(sk + ATT_KV_BYTES, &p.tm_kv_lo, &bars[BAR_K_FULL + st], hd + head * ATT_D, row);
+        mbar_wait(&bars[BAR_V_EMPTY + st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[BAR_V_FULL + st], 2 * ATT_KV_BYTES);
+        tma_load_2d(sv, &p.tm_kv_hi, &bars[BAR_V_FULL + st], 2 * hd + head * ATT_D, row);
+        tma_load_2d(sv + ATT_KV_BYTES, &p.tm_kv_lo, &bars[BAR_V_FULL + st], 2 * hd + head * ATT_D, row);
+      }
     }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // K buffer drained: prefetch the next K tile under the softmax
-      mbar_arrive_expect_tx(bar_k, 2 * ATT_KV_BYTES);
-      tma_load_2d(sK, &p.tm_kv_hi, bar_k, hd + head * ATT_D, img_row0 + (j + 1) * ATT_BKV);
-      tma_load_2d(sK + ATT_KV_BYTES, &p.tm_kv_lo, bar_k, hd + head * ATT_D, img_row0 + (j + 1) * ATT_BKV);
+  } else if (warp == 9) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BKV, 0, 0);  // A = Q (K-major), B = K (K-major), N = 64 keys
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_D, 0, 1);    // A = P (K-major), B = V (MN-major), N = 64 dims
+      const uint32_t sQ = smem_u32(smem), sK = smem_u32(smem + ATT_OFF_K), sV = smem_u32(smem + ATT_OFF_V),
+                     sP = smem_u32(smem + ATT_OFF_P);
+      auto qk = [&](int t, int j) {  // S_t = Q_t K(j)^T
+        const uint32_t k = sK + (j % ATT_STAGES) * 2 * ATT_KV_BYTES;
+        issue_split_mma(tmem_base + t * 64, sQ + (2 * t) * ATT_Q_BYTES, sQ + (2 * t + 1) * ATT_Q_BYTES, k,
+                        k + ATT_KV_BYTES, idesc_qk, 32);
+        tc_commit(&bars[BAR_S_FULL + t]);
+      };
+      auto pv = [&](int t, int j) {  // O_t = P_t V(j)
+        const uint32_t v = sV + (j % ATT_STAGES) * 2 * ATT_KV_BYTES;
+        issue_split_mma(tmem_base + 128 + t * 64, sP + (2 * t) * ATT_P_BYTES, sP + (2 * t + 1) * ATT_P_BYTES, v,
+                        v + ATT_KV_BYTES, idesc_pv, 2048);
+        tc_commit(&bars[BAR_O_FULL + t]);
+      };
+      mbar_wait(&bars[BAR_Q], 0);
+      mbar_wait(&bars[BAR_K_FULL + 0], 0);
+      tc_fence_after();
+      qk(0, 0);
+      qk(1, 0);
+      tc_commit(&bars[BAR_K_EMPTY + 0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = static_cast<uint32_t>(j & 1);
+        const int st = j % ATT_STAGES;
+        const uint32_t st_ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+        const bool more = j + 1 < n_kv;
+        const int st1 = (j + 1) % ATT_STAGES;
+        const uint32_t st1_ph = static_cast<uint32_t>(((j + 1) / ATT_STAGES) & 1);
+        if (more) {
+          mbar_wait(&bars[BAR_K_FULL + st1], st1_ph);
+          mbar_wait(&bars[BAR_S_FREE + 0], ph);  // tile A has pulled S_A(j) into registers
+          tc_fence_after();
+          qk(0, j + 1);
+        }
+        mbar_wait(&bars[BAR_V_FULL + st], st_ph);
+        mbar_wait(&bars[BAR_P_READY + 0], ph);
+        tc_fence_after();
+        pv(0, j);
+        if (more) {
+          mbar_wait(&bars[BAR_S_FREE + 1], ph);
+          tc_fence_after();
+          qk(1, j + 1);
+          tc_commit(&bars[BAR_K_EMPTY + st1]);
+        }
+        mbar_wait(&bars[BAR_P_READY + 1], ph);
+        tc_fence_after();
+        pv(1, j);
+        tc_commit(&bars[BAR_V_EMPTY + st]);
+      }
     }
+  } else {
+    // =========================================================== softmax warpgroups (tile 0: warps 0-3, tile 1: warps 4-7)
+    const int t = warp >> 2;
+    const int r = tid & 127;  // query row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + t * 64 + lane_base;
+    const uint32_t tmem_o = tmem_base + 128 + t * 64 + lane_base;
+    uint8_t* p_row_hi = smem + ATT_OFF_P + (2 * t) * ATT_P_BYTES + r * 128;
+    uint8_t* p_row_lo = p_row_hi + ATT_P_BYTES;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
 
-    // ---- softmax on this thread's row
-    uint32_t sv[2][32];
-    tmem_ld_32x32(tmem_s + lane_base, sv[0]);
-    tmem_ld_32x32(tmem_s + lane_base + 32, sv[1]);
-    tc_wait_ld();
-    const int kv_valid = sg.tokens - j * ATT_BKV;  // keys >= kv_valid belong to another image / padding
-    float s[ATT_BKV];
-    float m_tile = -INFINITY;
+    float o[ATT_D];
 #pragma unroll
-    for (int c = 0; c < ATT_BKV; ++c) {
-      const float x = __uint_as_float(sv[c >> 5][c & 31]);
-      s[c] = (c < kv_valid) ? x : -INFINITY;
-      m_tile = fmaxf(m_tile, s[c]);
-    }
-    const float m_new = fmaxf(m_run, m_tile);
-    const float alpha = exp2f((m_run - m_new) * p.scale_log2e);
-    const float mb = m_new * p.scale_log2e;
-    float l_tile = 0.0f;
+    for (int d = 0; d < ATT_D; ++d) o[d] = 0.0f;
+    float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = static_cast<uint32_t>(j & 1);
+      // ---- S row -> registers, then hand the TMEM buffer back to the tensor core
+      uint32_t sv[2][32];
+      mbar_wait(&bars[BAR_S_FULL + t], ph);
+      tc_fence_after();
+      tmem_ld_32x32(tmem_s, sv[0]);
+      tmem_ld_32x32(tmem_s + 32, sv[1]);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_S_FREE + t]);
+
+      float s[ATT_BKV];
 #pragma unroll
-    for (int c8 = 0; c8 < ATT_BKV / 8; ++c8) {
-      uint32_t hw[4], lw[4];
+      for (int c = 0; c < ATT_BKV; ++c) s[c] = __uint_as_float(sv[c >> 5][c & 31]);
+      const int kv_valid = sg.tokens - j * ATT_BKV;  // keys >= kv_valid belong to another image / padding
+      if (kv_valid < ATT_BKV) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float p0 = exp2f(fmaf(s[c8 * 8 + 2 * e], p.scale_log2e, -mb));
-        const float p1 = exp2f(fmaf(s[c8 * 8 + 2 * e + 1], p.scale_log2e, -mb));
+        for (int c = 0; c < ATT_BKV; ++c)
+          if (c >= kv_valid) s[c] = -INFINITY;
+      }
+      float m_tile = s[0];
+#pragma unroll
+      for (int c = 1; c < ATT_BKV; ++c) m_tile = fmaxf(m_tile, s[c]);
+      const float m_new = fmaxf(m_run, m_tile);
+      const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);
+      const float mb = m_new * p.scale_log2e;
+      m_run = m_new;
+
+      // ---- P = exp2(s*scale*log2e - mb), split to bf16 hi/lo (packed), row sum from the fp32 values
+      uint32_t phi[ATT_BKV / 2], plo[ATT_BKV / 2];
+      float l_tile = 0.0f;
+#pragma unroll
+      for (int c = 0; c < ATT_BKV; c += 2) {
+        const float p0 = fast_exp2(fmaf(s[c], p.scale_log2e, -mb));
+        const float p1 = fast_exp2(fmaf(s[c + 1], p.scale_log2e, -mb));
         l_tile += p0 + p1;
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(p0, h0, l0);
-        split_bf16(p1, h1, l1);
-        hw[e] = pack_bf16(h0, h1);
-        lw[e] = pack_bf16(l0, l1);
+        split2_bf16(p0, p1, phi[c >> 1], plo[c >> 1]);
       }
-      const uint32_t off = (static_cast<uint32_t>(c8) ^ sw) * 16;  // Swizzle<3,4,3>: 16-byte chunk ^= row % 8
-      *reinterpret_cast<uint4*>(p_row_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(p_row_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    }
-    l_run = l_run * alpha + l_tile;
-    m_run = m_new;
-    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-    tc_fence_before();
-    __syncthreads();
+      l_run = fmaf(l_run, alpha, l_tile);
 
-    // ---- O_tile = P V
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_v, ph);
-      tc_fence_after();
+      // ---- fold in the previous tile's P V (its MMAs have long finished; also frees the P buffer)
+      if (j > 0) {
+        mbar_wait(&bars[BAR_O_FULL + t], ph ^ 1);
+        tc_fence_after();
 #pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = sP_u + ((pass == 2) ? ATT_P_BYTES : 0);
-        const uint32_t b = sV_u + ((pass == 1) ? ATT_KV_BYTES : 0);
+        for (int half = 0; half < 2; ++half) {  // 32 columns at a time keeps the register peak below the cap
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_o + half * 32, ov);
+          tc_wait_ld();
 #pragma unroll
-        for (int k = 0; k < ATT_BKV / 16; ++k)
-          tc_mma_f16(tmem_o, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 2048), idesc_pv,
-                     (pass | k) != 0 ? 1u : 0u);
+          for (int d = 0; d < 32; ++d) o[half * 32 + d] = fmaf(o[half * 32 + d], alpha_prev, __uint_as_float(ov[d]));
+        }
       }
-      tc_commit(bar_o);
+      alpha_prev = alpha;
+
+      // ---- publish P(j) in the swizzled K-major layout: 16-byte chunk index ^= row % 8
+#pragma unroll
+      for (int c8 = 0; c8 < ATT_BKV / 8; ++c8) {
+        const uint32_t off = (static_cast<uint32_t>(c8) ^ sw) * 16;
+        *reinterpret_cast<uint4*>(p_row_hi + off) = make_uint4(phi[4 * c8], phi[4 * c8 + 1], phi[4 * c8 + 2], phi[4 * c8 + 3]);
+        *reinterpret_cast<uint4*>(p_row_lo + off) = make_uint4(plo[4 * c8], plo[4 * c8 + 1], plo[4 * c8 + 2], plo[4 * c8 + 3]);
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+      tc_fence_before();         // orders the O-tile TMEM reads above before the next P V is issued
+      mbar_arrive(&bars[BAR_P_READY + t]);
     }
-    mbar_wait(bar_o, ph);
+
+    // ---- last tile's P V, normalise, store this thread's row as split bf16
+    mbar_wait(&bars[BAR_O_FULL + t], static_cast<uint32_t>((n_kv - 1) & 1));
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // V and P buffers drained
-      mbar_arrive_expect_tx(bar_v, 2 * ATT_KV_BYTES);
-      tma_load_2d(sV, &p.tm_kv_hi, bar_v, 2 * hd + head * ATT_D, img_row0 + (j + 1) * ATT_BKV);
-      tma_load_2d(sV + ATT_KV_BYTES, &p.tm_kv_lo, bar_v, 2 * hd + head * ATT_D, img_row0 + (j + 1) * ATT_BKV);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + half * 32, ov);
+      tc_wait_ld();
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[half * 32 + d] = fmaf(o[half * 32 + d], alpha_prev, __uint_as_float(ov[d]));
     }
-    uint32_t ov[2][32];
-    tmem_ld_32x32(tmem_o + lane_base, ov[0]);
-    tmem_ld_32x32(tmem_o + lane_base + 32, ov[1]);
-    tc_wait_ld();
+    const int qrow = (2 * qp + t) * ATT_BQ + r;
+    if (qrow < sg.tokens) {
+      const float inv = 1.0f / l_run;
+      const long off = static_cast<long>(img_row0 + qrow) * hd + head * ATT_D;
+      __nv_bfloat16* oh = p.out_hi + off;
+      __nv_bfloat16* ol = p.out_lo + off;
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(ov[d >> 5][d & 31]));
-    tc_fence_before();  // orders these TMEM reads before the next iteration's MMAs (issued after a __syncthreads)
-  }
-
-  // ---- normalise and store this thread's row as split bf16
-  const int qrow = qt * ATT_BQ + tid;
-  if (qrow < sg.tokens) {
-    const float inv = 1.0f / l_run;
-    const long off = static_cast<long>(img_row0 + qrow) * hd + head * ATT_D;
-    __nv_bfloat16* oh = p.out_hi + off;
-    __nv_bfloat16* ol = p.out_lo + off;
+      for (int d8 = 0; d8 < ATT_D / 8; ++d8) {
+        uint32_t hw[4], lw[4];
 #pragma unroll
-    for (int d8 = 0; d8 < ATT_D / 8; ++d8) {
-      uint32_t hw[4], lw[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(o[d8 * 8 + 2 * e] * inv, h0, l0);
-        split_bf16(o[d8 * 8 + 2 * e + 1] * inv, h1, l1);
-        hw[e] = pack_bf16(h0, h1);
-        lw[e] = pack_bf16(l0, l1);
+        for (int e = 0; e < 4; ++e) split2_bf16(o[d8 * 8 + 2 * e] * inv, o[d8 * 8 + 2 * e + 1] * inv, hw[e], lw[e]);
+        *reinterpret_cast<uint4*>(oh + d8 * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(ol + d8 * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      *reinterpret_cast<uint4*>(oh + d8 * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(ol + d8 * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -278,7 +345,7 @@ extern "C" int dupl_attention_fwd(const dupl_attention_args* a, void* stream) {
                    "dupl_attention_fwd: segment %d out of range", order[s]);
     P.seg[s] = sg;
     P.cta_start[s] = total;
-    total += sg.batch * a->heads * cdiv(sg.tokens, ATT_BQ);
+    total += sg.batch * a->heads * cdiv(sg.tokens, 2 * ATT_BQ);
   }
   P.cta_start[a->nseg] = total;
   P.nseg = a->nseg;

@@ -242,13 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
               if (j < ncols) {
                 uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  split_bf16(f[j + 2 * e], h0, l0);
-                  split_bf16(f[j + 2 * e + 1], h1, l1);
-                  hw[e] = pack_bf16(h0, h1);
-                  lw[e] = pack_bf16(l0, l1);
-                }
+                for (int e = 0; e < 4; ++e) split2_bf16(f[j + 2 * e], f[j + 2 * e + 1], hw[e], lw[e]);
                 *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }

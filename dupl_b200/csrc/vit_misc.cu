@@ -14,13 +14,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c, float d) {
-  __nv_bfloat16 h[4], l[4];
-  split_bf16(a, h[0], l[0]);
-  split_bf16(b, h[1], l[1]);
-  split_bf16(c, h[2], l[2]);
-  split_bf16(d, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-  *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+  uint32_t h0, l0, h1, l1;
+  split2_bf16(a, b, h0, l0);
+  split2_bf16(c, d, h1, l1);
+  *reinterpret_cast<uint2*>(hi) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo) = make_uint2(l0, l1);
 }
 
 // ------------------------------------------------------------------------------ split
