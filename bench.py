@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="dupl_b200", choices=["dupl_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fuse-students", action="store_true", help="both students per grouped GEMM launch")
+    ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 0)
     if args.impl == "reference":
@@ -252,6 +253,38 @@ def main():
     e2e_ms_total = (time.perf_counter() - w0) * 1000.0
     clocks = sampler.stop() if rank == 0 else None
 
+    breakdown = None
+    if args.breakdown and rank == 0:
+        import dupl_b200.utils.cam_helper as ch_mod
+        import dupl_b200.model.model_dupl as md_mod
+        recs = []
+        names = ["gemm_bf16x3", "attention_fwd", "layernorm_split", "patchify", "cls_rows", "cam_contract", "mscam_post",
+                 "par_affinity", "par_propagate", "refine_prologue", "refine_epilogue", "split_bf16", "pos_embed_resize"]
+        saved = {n: getattr(ops, n) for n in names}
+
+        def wrap(n, fn):
+            def f(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                r = fn(*a, **k)
+                e1.record(stream)
+                recs.append((n, e0, e1))
+                return r
+            return f
+        for n in names:
+            setattr(ops, n, wrap(n, saved[n]))
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        device_step()
+        w1.record(stream)
+        torch.cuda.synchronize()
+        for n in names:
+            setattr(ops, n, saved[n])
+        breakdown = {"step_ms": w0.elapsed_time(w1)}
+        for n, e0, e1 in recs:
+            breakdown[n] = breakdown.get(n, 0.0) + e0.elapsed_time(e1)
+        breakdown = {k: round(v, 3) for k, v in breakdown.items()}
+
     t = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,6 +318,8 @@ def main():
                                  "MMAs per product (split operands), so the tensor pipe does 3x this figure",
                          "step_tflops": GFLOP_PER_IMAGE * 1e9 * BATCH / (ms_step * 1e-3) / 1e12},
         }
+        if breakdown is not None:
+            line["breakdown_ms"] = breakdown
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             secs = cpu_oracle_step(P, x, cls, box, thr, 1, students=(1,)) * 2.0

@@ -73,6 +73,15 @@ class RefineEpilogueArgs(C.Structure):
                 ("ignore_index", C.c_float), ("label", C.c_void_p), ("label_h", C.c_void_p), ("label_l", C.c_void_p)]
 
 
+class CrfArgs(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("C", C.c_int32),
+                ("pos_w", C.c_float), ("pos_xy_std", C.c_float), ("bi_w", C.c_float), ("bi_xy_std", C.c_float),
+                ("bi_rgb_std", C.c_float), ("iters", C.c_int32), ("input_is_energy", C.c_int32),
+                ("image", C.c_void_p), ("unary_or_probs", C.c_void_p), ("out", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("values", C.c_void_p), ("values_bytes", C.c_size_t), ("meta", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/dupl.h
 _PROTOTYPES = {
     "dupl_version": (C.c_int, []),
@@ -99,6 +108,10 @@ _PROTOTYPES = {
                                      C.c_int32, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_void_p]),
     "dupl_refine_prologue": (C.c_int, [C.POINTER(RefinePrologueArgs), C.c_void_p]),
     "dupl_refine_epilogue": (C.c_int, [C.POINTER(RefineEpilogueArgs), C.c_void_p]),
+    "dupl_crf_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dupl_crf_values_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dupl_crf_build": (C.c_int, [C.POINTER(CrfArgs), C.c_void_p]),
+    "dupl_crf_infer": (C.c_int, [C.POINTER(CrfArgs), C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -57,15 +57,16 @@ enum {  // mbarrier slots
   BAR_COUNT = BAR_O_FULL + 2
 };
 
-__device__ __forceinline__ void issue_split_mma(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                                uint32_t b_lo, uint32_t idesc, uint32_t b_kstep) {
+// 3-pass split product over a 64-deep contraction; warp-collective (leader elected inside tc_mma_f16).
+__device__ __forceinline__ void issue_split_mma(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                                uint64_t b_lo, uint32_t idesc, uint32_t b_kstep) {
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a = (pass == 2) ? a_lo : a_hi;
-    const uint32_t b = (pass == 1) ? b_lo : b_hi;
+    const uint64_t a = (pass == 2) ? a_lo : a_hi;
+    const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) = 64-deep contraction
-      tc_mma_f16(d_tmem, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
+    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16)
+      tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
   }
 }
 
@@ -140,22 +141,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       }
     }
   } else if (warp == 9) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================== MMA issuer (whole warp, leader elected per op)
+    {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BKV, 0, 0);  // A = Q (K-major), B = K (K-major), N = 64 keys
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_D, 0, 1);    // A = P (K-major), B = V (MN-major), N = 64 dims
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sQ = smem_u32(smem), sK = smem_u32(smem + ATT_OFF_K), sV = smem_u32(smem + ATT_OFF_V),
                      sP = smem_u32(smem + ATT_OFF_P);
-      auto qk = [&](int t, int j) {  // S_t = Q_t K(j)^T
-        const uint32_t k = sK + (j % ATT_STAGES) * 2 * ATT_KV_BYTES;
-        issue_split_mma(tmem_base + t * 64, sQ + (2 * t) * ATT_Q_BYTES, sQ + (2 * t + 1) * ATT_Q_BYTES, k,
-                        k + ATT_KV_BYTES, idesc_qk, 32);
+      uint64_t dQ[2][2], dP[2][2], dK[ATT_STAGES][2], dV[ATT_STAGES][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          dQ[t][pl] = umma_desc_sw128(sQ + (2 * t + pl) * ATT_Q_BYTES);
+          dP[t][pl] = umma_desc_sw128(sP + (2 * t + pl) * ATT_P_BYTES);
+        }
+#pragma unroll
+      for (int st = 0; st < ATT_STAGES; ++st)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          dK[st][pl] = umma_desc_sw128(sK + (2 * st + pl) * ATT_KV_BYTES);
+          dV[st][pl] = umma_desc_sw128(sV + (2 * st + pl) * ATT_KV_BYTES);
+        }
+      auto qk = [&](int t, int st) {  // S_t = Q_t K^T
+        issue_split_mma(tm + t * 64, dQ[t][0], dQ[t][1], dK[st][0], dK[st][1], idesc_qk, 32);
         tc_commit(&bars[BAR_S_FULL + t]);
       };
-      auto pv = [&](int t, int j) {  // O_t = P_t V(j)
-        const uint32_t v = sV + (j % ATT_STAGES) * 2 * ATT_KV_BYTES;
-        issue_split_mma(tmem_base + 128 + t * 64, sP + (2 * t) * ATT_P_BYTES, sP + (2 * t + 1) * ATT_P_BYTES, v,
-                        v + ATT_KV_BYTES, idesc_pv, 2048);
+      auto pv = [&](int t, int st) {  // O_t = P_t V
+        issue_split_mma(tm + 128 + t * 64, dP[t][0], dP[t][1], dV[st][0], dV[st][1], idesc_pv, 2048);
         tc_commit(&bars[BAR_O_FULL + t]);
       };
       mbar_wait(&bars[BAR_Q], 0);
@@ -164,33 +177,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       qk(0, 0);
       qk(1, 0);
       tc_commit(&bars[BAR_K_EMPTY + 0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = static_cast<uint32_t>(j & 1);
-        const int st = j % ATT_STAGES;
-        const uint32_t st_ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
-        const bool more = j + 1 < n_kv;
-        const int st1 = (j + 1) % ATT_STAGES;
-        const uint32_t st1_ph = static_cast<uint32_t>(((j + 1) / ATT_STAGES) & 1);
-        if (more) {
-          mbar_wait(&bars[BAR_K_FULL + st1], st1_ph);
-          mbar_wait(&bars[BAR_S_FREE + 0], ph);  // tile A has pulled S_A(j) into registers
-          tc_fence_after();
-          qk(0, j + 1);
+#pragma unroll 1
+      for (int j2 = 0; j2 < n_kv; j2 += ATT_STAGES) {
+#pragma unroll
+        for (int st = 0; st < ATT_STAGES; ++st) {  // stage index is a compile-time constant inside
+          const int j = j2 + st;
+          if (j < n_kv) {
+            const uint32_t ph = static_cast<uint32_t>(j & 1);
+            const uint32_t st_ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
+            const bool more = j + 1 < n_kv;
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int st1 = (st + 1) % ATT_STAGES;
+            const uint32_t st1_ph = static_cast<uint32_t>(((j + 1) / ATT_STAGES) & 1);
+            if (more) {
+              mbar_wait(&bars[BAR_K_FULL + st1], st1_ph);
+              mbar_wait(&bars[BAR_S_FREE + 0], ph);  // tile A has pulled S_A(j) into registers
+              tc_fence_after();
+              qk(0, st1);
+            }
+            mbar_wait(&bars[BAR_V_FULL + st], st_ph);
+            mbar_wait(&bars[BAR_P_READY + 0], ph);
+            tc_fence_after();
+            pv(0, st);
+            if (more) {
+              mbar_wait(&bars[BAR_S_FREE + 1], ph);
+              tc_fence_after();
+              qk(1, st1);
+              tc_commit(&bars[BAR_K_EMPTY + st1]);
+            }
+            mbar_wait(&bars[BAR_P_READY + 1], ph);
+            tc_fence_after();
+            pv(1, st);
+            tc_commit(&bars[BAR_V_EMPTY + st]);
+          }
         }
-        mbar_wait(&bars[BAR_V_FULL + st], st_ph);
-        mbar_wait(&bars[BAR_P_READY + 0], ph);
-        tc_fence_after();
-        pv(0, j);
-        if (more) {
-          mbar_wait(&bars[BAR_S_FREE + 1], ph);
-          tc_fence_after();
-          qk(1, j + 1);
-          tc_commit(&bars[BAR_K_EMPTY + st1]);
-        }
-        mbar_wait(&bars[BAR_P_READY + 1], ph);
-        tc_fence_after();
-        pv(1, j);
-        tc_commit(&bars[BAR_V_EMPTY + st]);
       }
     }
   } else {

@@ -127,9 +127,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, leader elected per op)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
+      const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -137,22 +138,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_acc + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t a_hi = s, a_lo = s + Cfg::A_BYTES;
-          const uint32_t b_hi = s + 2 * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(s), a_lo = umma_desc_sw128(s + Cfg::A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(s + 2 * Cfg::A_BYTES), b_lo = umma_desc_sw128(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a_lo : a_hi;
-            const uint32_t b = (pass == 1) ? b_lo : b_hi;
+            const uint64_t a = (pass == 2) ? a_lo : a_hi;
+            const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k) {
-              tc_mma_f16(d_tmem, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc,
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
                          (kb | pass | k) != 0 ? 1u : 0u);
-            }
           }
           tc_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
           if (++stage == Cfg::STAGES) {

@@ -78,18 +78,27 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// Arrive on an mbarrier once every tcgen05 op previously issued by THIS thread has completed.
+// Arrive on an mbarrier once every tcgen05 op previously issued by the elected thread has completed.
+// Warp-collective like tc_mma_f16 (same elected leader).
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16/fp16 inputs, fp32 accumulate. One thread issues.
+// D[tmem] (+)= A[smem] * B[smem], bf16/fp16 inputs, fp32 accumulate.
+// Called by ALL lanes of the issuing warp with warp-uniform operands: the leader is elected inside the
+// asm block, so the surrounding C++ stays convergent and descriptors live in uniform registers
+// (a divergent `if (lane == 0)` around the issue loop costs ~14 SASS instructions per MMA).
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -122,6 +131,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Descriptor of the same tile `bytes` further on (no carry out of the 14-bit address field within 227 KB).
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 // Instruction descriptor, kind::f16: bf16 x bf16 -> f32, M = 128.
 //   [4,6) c_format F32=1   [7,10) a_format BF16=1   [10,13) b_format BF16=1
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)   [17,23) N>>3   [24,29) M>>4

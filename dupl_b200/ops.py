@@ -261,3 +261,57 @@ def refine_epilogue(masks, cls, img_box, H, W, ignore_index, want_parts=False):
         a.label_h, a.label_l = lh.data_ptr(), ll.data_ptr()
     L.check(L.lib().dupl_refine_epilogue(C.byref(a), L.stream_ptr(dev)), "dupl_refine_epilogue")
     return (label, lh, ll) if want_parts else label
+
+
+# ------------------------------------------------------------------ DenseCRF
+class CrfWorkspace:
+    """Lattice workspace re-used across images of the same size (one allocation per (H, W))."""
+
+    def __init__(self):
+        self.key, self.buf, self.values, self.meta = None, None, None, None
+
+    def get(self, H, W, device):
+        if self.key != (H, W, device):
+            n = C.c_size_t(0)
+            L.check(L.lib().dupl_crf_workspace_bytes(W, H, C.byref(n)), "dupl_crf_workspace_bytes")
+            self.buf = torch.empty(n.value, dtype=torch.uint8, device=device)
+            self.meta = torch.zeros(4, dtype=torch.int32, device=device)
+            self.key = (H, W, device)
+        return self.buf, self.meta
+
+    def get_values(self, nbytes, device):
+        if self.values is None or self.values.numel() < nbytes or self.values.device != device:
+            self.values = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self.values
+
+
+def crf_inference(image_u8, unary_or_probs, iters, pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std, input_is_energy=False,
+                  ws=None):
+    """image_u8: uint8 [H,W,3] cuda; unary_or_probs: fp32 [C,H,W] cuda -> (Q fp32 [C,H,W] cuda, (M_gauss, M_bilateral))."""
+    L.require_cuda(image_u8, unary_or_probs)
+    ws = ws or CrfWorkspace()
+    x = L.f32c(unary_or_probs)
+    img = image_u8.contiguous()
+    Cn, H, W = x.shape
+    if img.dtype != torch.uint8 or tuple(img.shape) != (H, W, 3):
+        raise ValueError("image must be uint8 [H, W, 3] matching the probability map")
+    dev = x.device
+    buf, meta = ws.get(H, W, dev)
+    out = torch.empty_like(x)
+    a = L.CrfArgs()
+    a.W, a.H, a.C = W, H, Cn
+    a.pos_w, a.pos_xy_std, a.bi_w, a.bi_xy_std, a.bi_rgb_std = pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std
+    a.iters, a.input_is_energy = iters, 1 if input_is_energy else 0
+    a.image, a.unary_or_probs, a.out = img.data_ptr(), x.data_ptr(), out.data_ptr()
+    a.workspace, a.workspace_bytes, a.meta = buf.data_ptr(), buf.numel(), meta.data_ptr()
+    st = L.stream_ptr(dev)
+    L.check(L.lib().dupl_crf_build(C.byref(a), st), "dupl_crf_build")
+    m = meta.tolist()  # the one host sync of the CRF: vertex counts size the value arrays
+    if m[2]:
+        raise RuntimeError("DenseCRF: a lattice coordinate left the packed key range (features too large for this build)")
+    nv = C.c_size_t(0)
+    L.check(L.lib().dupl_crf_values_bytes(W, H, Cn, m[0], m[1], C.byref(nv)), "dupl_crf_values_bytes")
+    vals = ws.get_values(nv.value, dev)
+    a.values, a.values_bytes = vals.data_ptr(), vals.numel()
+    L.check(L.lib().dupl_crf_infer(C.byref(a), m[0], m[1], st), "dupl_crf_infer")
+    return out, (m[0], m[1])

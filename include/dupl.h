@@ -22,6 +22,7 @@
 #ifndef DUPL_H_
 #define DUPL_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -242,6 +243,40 @@ typedef struct {
 } dupl_refine_epilogue_args;
 
 int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DenseCRF mean-field inference (utils/dcrf.py:42-69 -> pydensecrf DenseCRF2D: setUnaryEnergy,
+ * addPairwiseGaussian(sxy=pos_xy_std, compat=pos_w), addPairwiseBilateral(sxy=bi_xy_std,
+ * srgb=bi_rgb_std, compat=bi_w), inference(iters)); also serves crf_inference / crf_inference_label
+ * (dcrf.py:7-40) through the same parameters.  Permutohedral-lattice filtering, symmetric
+ * normalisation, Potts compatibility.  Two phases so that the vertex arrays can be sized exactly:
+ *   dupl_crf_build  : builds both lattices for `image` into `workspace`, writes meta (device int32[4]:
+ *                     #vertices of the Gaussian lattice, #vertices of the bilateral lattice, key-range
+ *                     overflow flag, 0).  The caller reads meta (its only host sync) and then calls
+ *   dupl_crf_infer  : iters mean-field updates; `values` is a scratch of dupl_crf_values_bytes().
+ * image: uint8 [H][W][3]; unary_or_probs: fp32 [C][H][W] (probabilities -> -log(clip(p,1e-5,1)), or
+ * energies when input_is_energy != 0); out: fp32 Q [C][H][W].  C <= 96.  A pairwise term whose weight is
+ * 0 is skipped.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t W, H, C;
+  float pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std;
+  int32_t iters;
+  int32_t input_is_energy;
+  const uint8_t* image;
+  const float* unary_or_probs;
+  float* out;
+  void* workspace;
+  size_t workspace_bytes;
+  void* values;
+  size_t values_bytes;
+  int32_t* meta;
+} dupl_crf_args;
+
+int dupl_crf_workspace_bytes(int32_t W, int32_t H, size_t* bytes);
+int dupl_crf_values_bytes(int32_t W, int32_t H, int32_t C, int32_t M_gauss, int32_t M_bilateral, size_t* bytes);
+int dupl_crf_build(const dupl_crf_args* args, void* stream);
+int dupl_crf_infer(const dupl_crf_args* args, int32_t M_gauss, int32_t M_bilateral, void* stream);
 
 #ifdef __cplusplus
 }
