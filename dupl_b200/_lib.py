@@ -15,7 +15,7 @@ MAX_SEGMENTS = 8
 MAX_GROUPS = 2
 PAR_MAX_DIL = 8
 
-EPI_F32, EPI_SPLIT, EPI_GELU_SPLIT, EPI_RESID, EPI_PATCH = 0, 1, 2, 3, 4
+EPI_F32, EPI_SPLIT, EPI_GELU_SPLIT, EPI_RESID, EPI_PATCH, EPI_RELU_SPLIT = 0, 1, 2, 3, 4, 5
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)
@@ -89,8 +89,11 @@ _PROTOTYPES = {
     "dupl_launch_count": (C.c_int64, []),
     "dupl_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dupl_gemm_bf16x3": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
-    "dupl_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    "dupl_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "dupl_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
+    "dupl_rows_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
+    "dupl_gmp_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "dupl_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "dupl_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Segment), C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -6,14 +6,18 @@
 // S_B(j), P_A V, S_A(j+1) ... so neither pipe waits for the other in steady state.
 //   warps 0-3   softmax of tile A      thread t owns query row t end to end: tcgen05.ld hands it the
 //   warps 4-7   softmax of tile B      whole row of S -> running max / sum in registers, no shuffles;
-//                                      P is split to bf16 hi/lo and written to shared memory in the
-//                                      128-byte-swizzled K-major layout the tensor core reads;
+//                                      P is split to bf16 hi/lo and written back to TENSOR MEMORY
+//                                      (tcgen05.st), where the P V MMA reads it as its A operand;
 //                                      O = O*alpha + (P V) is accumulated in registers from the fresh
 //                                      per-tile product, so TMEM is never rescaled
-//   warp 8      TMA producer: Q_A, Q_B once, then K(j) / V(j) tiles, 2 stages each, straight out of
-//               the qkv GEMM's [M, 2304] split-bf16 planes (V is consumed in place as an MN-major operand)
-//   warp 9      MMA issuer (one lane): S = Q K^T and P V as 3-pass split-bf16 tcgen05.mma 128x64x16
-// TMEM: S_A | S_B | O_A | O_B, 64 fp32 columns each.  Shared memory 192 KB: one CTA per SM.
+//   warp 8      TMA producer: K(j) / V(j) tiles, 3 stages each, straight out of the qkv GEMM's
+//               [M, 2304] split-bf16 planes (V is consumed in place as an MN-major operand)
+//   warp 9      MMA issuer: S = Q K^T and P V as 3-pass split-bf16 tcgen05.mma 128x64x16 with the A
+//               operand (Q resp. P) in tensor memory.  With both operands in shared memory a
+//               128x64x16 MMA needs 192 B/clk of smem reads (the SM delivers 128): the first version
+//               of this kernel was shared-memory bound at 30 % tensor-pipe utilisation.
+// TMEM (512 columns): S_A S_B O_A O_B (64 fp32 columns each) | Q_A Q_B | P_A P_B (hi 32 + lo 32 columns
+// each, two bf16 per column).  Q is loaded once by the softmax threads (global -> registers -> TMEM).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -23,23 +27,27 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 64;
 constexpr int ATT_D = 64;
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // one plane of one query tile: 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;  // one plane of one K or V tile: 8 KB
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // one plane of one P tile: 16 KB
-constexpr int ATT_STAGES = 2;
-// Q: 2 tiles x 2 planes | K: stages x 2 planes | V: stages x 2 planes | P: 2 tiles x 2 planes
-constexpr int ATT_OFF_K = 4 * ATT_Q_BYTES;
+constexpr int ATT_STAGES = 3;
+// K: stages x 2 planes | V: stages x 2 planes
+constexpr int ATT_OFF_K = 0;
 constexpr int ATT_OFF_V = ATT_OFF_K + ATT_STAGES * 2 * ATT_KV_BYTES;
-constexpr int ATT_OFF_P = ATT_OFF_V + ATT_STAGES * 2 * ATT_KV_BYTES;
-constexpr int ATT_OFF_BAR = ATT_OFF_P + 4 * ATT_P_BYTES;
+constexpr int ATT_OFF_BAR = ATT_OFF_V + ATT_STAGES * 2 * ATT_KV_BYTES;
 constexpr int ATT_SMEM = ATT_OFF_BAR + 256 + 1024;
+// tensor-memory columns
+constexpr int TM_S = 0;      // + t*64
+constexpr int TM_O = 128;    // + t*64
+constexpr int TM_Q = 256;    // + t*64 : hi 32 columns, lo 32 columns
+constexpr int TM_P = 384;    // + t*64 : hi 32 columns, lo 32 columns
 
 struct AttnParamsDev {
-  CUtensorMap tm_q_hi, tm_q_lo, tm_kv_hi, tm_kv_lo;
+  CUtensorMap tm_kv_hi, tm_kv_lo;
   dupl_segment seg[DUPL_MAX_SEGMENTS];
   int cta_start[DUPL_MAX_SEGMENTS + 1];
-  int nseg, heads;
+  int nseg, heads, M;
   float scale_log2e;
+  const __nv_bfloat16* q_hi;  // the qkv planes (Q rows are read directly by the softmax threads)
+  const __nv_bfloat16* q_lo;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
 };
@@ -57,16 +65,17 @@ enum {  // mbarrier slots
   BAR_COUNT = BAR_O_FULL + 2
 };
 
-// 3-pass split product over a 64-deep contraction; warp-collective (leader elected inside tc_mma_f16).
-__device__ __forceinline__ void issue_split_mma(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
-                                                uint64_t b_lo, uint32_t idesc, uint32_t b_kstep) {
+// 3-pass split product over a 64-deep contraction, A operand in tensor memory (hi at a_tmem, lo 32 columns
+// further), B operand in shared memory; warp-collective (leader elected inside tc_mma_f16_ts).
+__device__ __forceinline__ void issue_split_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
+                                                   uint32_t idesc, uint32_t b_kstep) {
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
-    const uint64_t a = (pass == 2) ? a_lo : a_hi;
+    const uint32_t a = a_tmem + ((pass == 2) ? 32 : 0);
     const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16)
-      tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
+    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16): 8 TMEM columns of A per step
+      tc_mma_f16_ts(d_tmem, a + k * 8, umma_desc_advance(b, k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
   }
 }
 
@@ -98,12 +107,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   if (tid == 0) {
     for (int i = 0; i < BAR_COUNT; ++i) {
       const bool wg_arrives = (i >= BAR_S_FREE && i < BAR_O_FULL);  // s_free / p_ready: all 128 softmax threads
-      mbar_init(&bars[i], wg_arrives ? 128u : 1u);
+      mbar_init(&bars[i], i == BAR_Q ? 256u : (wg_arrives ? 128u : 1u));  // Q: both warpgroups store their tile
     }
     fence_mbar_init();
   }
   if (warp == 8) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -114,16 +123,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   if (warp == 8) {
     // =========================================================== TMA producer
     if (lane == 0) {
-      tma_prefetch_desc(&p.tm_q_hi);
-      tma_prefetch_desc(&p.tm_q_lo);
       tma_prefetch_desc(&p.tm_kv_hi);
       tma_prefetch_desc(&p.tm_kv_lo);
-      mbar_arrive_expect_tx(&bars[BAR_Q], 4 * ATT_Q_BYTES);
-      for (int t = 0; t < 2; ++t) {
-        const int row = img_row0 + (2 * qp + t) * ATT_BQ;
-        tma_load_2d(smem + (2 * t) * ATT_Q_BYTES, &p.tm_q_hi, &bars[BAR_Q], head * ATT_D, row);
-        tma_load_2d(smem + (2 * t + 1) * ATT_Q_BYTES, &p.tm_q_lo, &bars[BAR_Q], head * ATT_D, row);
-      }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ATT_STAGES;
         const uint32_t ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
@@ -146,16 +147,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BKV, 0, 0);  // A = Q (K-major), B = K (K-major), N = 64 keys
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_D, 0, 1);    // A = P (K-major), B = V (MN-major), N = 64 dims
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t sQ = smem_u32(smem), sK = smem_u32(smem + ATT_OFF_K), sV = smem_u32(smem + ATT_OFF_V),
-                     sP = smem_u32(smem + ATT_OFF_P);
-      uint64_t dQ[2][2], dP[2][2], dK[ATT_STAGES][2], dV[ATT_STAGES][2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          dQ[t][pl] = umma_desc_sw128(sQ + (2 * t + pl) * ATT_Q_BYTES);
-          dP[t][pl] = umma_desc_sw128(sP + (2 * t + pl) * ATT_P_BYTES);
-        }
+      const uint32_t sK = smem_u32(smem + ATT_OFF_K), sV = smem_u32(smem + ATT_OFF_V);
+      uint64_t dK[ATT_STAGES][2], dV[ATT_STAGES][2];
 #pragma unroll
       for (int st = 0; st < ATT_STAGES; ++st)
 #pragma unroll
@@ -164,11 +157,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
           dV[st][pl] = umma_desc_sw128(sV + (2 * st + pl) * ATT_KV_BYTES);
         }
       auto qk = [&](int t, int st) {  // S_t = Q_t K^T
-        issue_split_mma(tm + t * 64, dQ[t][0], dQ[t][1], dK[st][0], dK[st][1], idesc_qk, 32);
+        issue_split_mma_ts(tm + TM_S + t * 64, tm + TM_Q + t * 64, dK[st][0], dK[st][1], idesc_qk, 32);
         tc_commit(&bars[BAR_S_FULL + t]);
       };
       auto pv = [&](int t, int st) {  // O_t = P_t V
-        issue_split_mma(tm + 128 + t * 64, dP[t][0], dP[t][1], dV[st][0], dV[st][1], idesc_pv, 2048);
+        issue_split_mma_ts(tm + TM_O + t * 64, tm + TM_P + t * 64, dV[st][0], dV[st][1], idesc_pv, 2048);
         tc_commit(&bars[BAR_O_FULL + t]);
       };
       mbar_wait(&bars[BAR_Q], 0);
@@ -186,8 +179,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
             const uint32_t ph = static_cast<uint32_t>(j & 1);
             const uint32_t st_ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
             const bool more = j + 1 < n_kv;
-            constexpr int dummy = 0;
-            (void)dummy;
             const int st1 = (st + 1) % ATT_STAGES;
             const uint32_t st1_ph = static_cast<uint32_t>(((j + 1) / ATT_STAGES) & 1);
             if (more) {
@@ -219,11 +210,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     const int t = warp >> 2;
     const int r = tid & 127;  // query row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tmem_s = tmem_base + t * 64 + lane_base;
-    const uint32_t tmem_o = tmem_base + 128 + t * 64 + lane_base;
-    uint8_t* p_row_hi = smem + ATT_OFF_P + (2 * t) * ATT_P_BYTES + r * 128;
-    uint8_t* p_row_lo = p_row_hi + ATT_P_BYTES;
-    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t tmem_s = tmem_base + TM_S + t * 64 + lane_base;
+    const uint32_t tmem_o = tmem_base + TM_O + t * 64 + lane_base;
+    const uint32_t tmem_q = tmem_base + TM_Q + t * 64 + lane_base;
+    const uint32_t tmem_p = tmem_base + TM_P + t * 64 + lane_base;
+
+    // ---- this thread's query row: global -> registers -> tensor memory (hi 32 columns | lo 32 columns)
+    {
+      const long grow = static_cast<long>(img_row0) + (2 * qp + t) * ATT_BQ + r;
+      uint32_t qh[32], ql[32];
+      if (grow < p.M) {
+        const uint4* gh = reinterpret_cast<const uint4*>(p.q_hi + grow * 3 * hd + head * ATT_D);
+        const uint4* gl = reinterpret_cast<const uint4*>(p.q_lo + grow * 3 * hd + head * ATT_D);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 a = __ldg(gh + i), b = __ldg(gl + i);
+          qh[4 * i] = a.x; qh[4 * i + 1] = a.y; qh[4 * i + 2] = a.z; qh[4 * i + 3] = a.w;
+          ql[4 * i] = b.x; ql[4 * i + 1] = b.y; ql[4 * i + 2] = b.z; ql[4 * i + 3] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) qh[i] = ql[i] = 0u;
+      }
+      tmem_st_32x32(tmem_q, qh);
+      tmem_st_32x32(tmem_q + 32, ql);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars[BAR_Q]);
+    }
 
     float o[ATT_D];
 #pragma unroll
@@ -286,15 +300,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       }
       alpha_prev = alpha;
 
-      // ---- publish P(j) in the swizzled K-major layout: 16-byte chunk index ^= row % 8
-#pragma unroll
-      for (int c8 = 0; c8 < ATT_BKV / 8; ++c8) {
-        const uint32_t off = (static_cast<uint32_t>(c8) ^ sw) * 16;
-        *reinterpret_cast<uint4*>(p_row_hi + off) = make_uint4(phi[4 * c8], phi[4 * c8 + 1], phi[4 * c8 + 2], phi[4 * c8 + 3]);
-        *reinterpret_cast<uint4*>(p_row_lo + off) = make_uint4(plo[4 * c8], plo[4 * c8 + 1], plo[4 * c8 + 2], plo[4 * c8 + 3]);
-      }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-      tc_fence_before();         // orders the O-tile TMEM reads above before the next P V is issued
+      // ---- publish P(j): tensor memory, two bf16 per column (the A operand of the P V MMA)
+      tmem_st_32x32(tmem_p, phi);
+      tmem_st_32x32(tmem_p + 32, plo);
+      tc_wait_st();
+      tc_fence_before();  // also orders the O-tile TMEM reads above before the next P V is issued
       mbar_arrive(&bars[BAR_P_READY + t]);
     }
 
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -346,8 +356,6 @@ extern "C" int dupl_attention_fwd(const dupl_attention_args* a, void* stream) {
   memset(&P, 0, sizeof(P));
   const int hd = a->heads * ATT_D;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&P.tm_q_hi, a->qkv_hi, a->M, 3 * hd, 3 * hd, ATT_BQ))) return rc;
-  if ((rc = make_tmap_bf16_2d(&P.tm_q_lo, a->qkv_lo, a->M, 3 * hd, 3 * hd, ATT_BQ))) return rc;
   if ((rc = make_tmap_bf16_2d(&P.tm_kv_hi, a->qkv_hi, a->M, 3 * hd, 3 * hd, ATT_BKV))) return rc;
   if ((rc = make_tmap_bf16_2d(&P.tm_kv_lo, a->qkv_lo, a->M, 3 * hd, 3 * hd, ATT_BKV))) return rc;
   // Longest sequences first so the tail of the grid is made of short CTAs.
@@ -372,6 +380,9 @@ extern "C" int dupl_attention_fwd(const dupl_attention_args* a, void* stream) {
   P.nseg = a->nseg;
   P.heads = a->heads;
   P.scale_log2e = a->scale * 1.44269504088896340736f;
+  P.M = a->M;
+  P.q_hi = static_cast<const __nv_bfloat16*>(a->qkv_hi);
+  P.q_lo = static_cast<const __nv_bfloat16*>(a->qkv_lo);
   P.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   P.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
   static bool attr_set = false;

@@ -40,7 +40,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows) {
+                      uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -53,10 +53,11 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu box_rows %u)",

@@ -40,11 +40,11 @@ void set_error(const char* fmt, ...);
 // Number of kernels this library has launched in the process (dupl_launch_count()).
 void count_launch();
 
-// 2-D bf16 tensor map: `rows` x `cols` elements, row stride `ld` elements, box = box_rows x 64
-// columns (128 bytes) with the 128-byte swizzle; out-of-bounds elements read as zero.
+// 2-D bf16 tensor map: `rows` x `cols` elements, row stride `ld` elements, box = box_rows x box_cols
+// columns (64 -> 128-byte rows with the 128-byte swizzle, 32 -> 64-byte rows with the 64-byte swizzle); out-of-bounds elements read as zero.
 // Returns 0 on success (DUPL_ERR_* otherwise).
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows);
+                      uint32_t box_rows, uint32_t box_cols = 64);
 
 int sm_count();
 

@@ -624,7 +624,7 @@ static int infer_impl(const dupl_crf_args* a, const CrfLayout& L, const int* M, 
   float* U = static_cast<float*>(a->values);
   float* Q = U + nc;
   float* msg = Q + nc;
-  size_t off = 3 * nc * sizeof(float);
+  size_t off = align_up(3 * nc * sizeof(float));
   const bool use[2] = {a->pos_w != 0.0f, a->bi_w != 0.0f};
   const float weight[2] = {a->pos_w, a->bi_w};
   long long* acc[2];
@@ -689,7 +689,7 @@ extern "C" int dupl_crf_workspace_bytes(int32_t W, int32_t H, size_t* bytes) {
 extern "C" int dupl_crf_values_bytes(int32_t W, int32_t H, int32_t C, int32_t M_gauss, int32_t M_bilateral, size_t* bytes) {
   DUPL_CHECK_ARG(W > 0 && H > 0 && C > 0 && M_gauss >= 0 && M_bilateral >= 0 && bytes != nullptr,
                  "dupl_crf_values_bytes: bad arguments");
-  size_t off = 3 * static_cast<size_t>(W) * H * C * sizeof(float);
+  size_t off = align_up(3 * static_cast<size_t>(W) * H * C * sizeof(float));
   const int M[2] = {M_gauss, M_bilateral};
   for (int k = 0; k < 2; ++k) {
     const size_t mc = static_cast<size_t>(M[k]) * C;

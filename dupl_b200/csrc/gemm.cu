@@ -6,21 +6,26 @@
 // bf16/fp16/tf32 pass moves the normalised CAMs by 2e-3 (tools/precision_study.py), above the 1e-3
 // parity bar of the path; the split keeps the error at ~2e-5 for 3 MMAs per k-step.
 //
-// Structure (one CTA per SM, 192 threads):
-//   warp 0     TMA producer: A_hi/A_lo [128 x 64] and W_hi/W_lo [BN x 64] tiles, 128-byte swizzle
+// Structure (one CTA per SM, 192 threads, clusters of 2 CTAs):
+//   warp 0     TMA producer: A_hi/A_lo [128 x 64] and W_hi/W_lo [BN x 64] tiles, 128-byte swizzle.
+//              The two CTAs of a cluster work on vertically adjacent output tiles (same W tile): each
+//              loads HALF of the W tile and multicasts it to both, so a k-block costs 64 KB of L2->SM
+//              traffic per CTA instead of 96 KB (the single-CTA version was L2-bandwidth bound at
+//              ~60 % tensor-pipe utilisation, profiles/r01_summary.md)
 //   warp 1     MMA issuer (one lane): 3 x 4 tcgen05.mma (128 x BN x 16) per k-block, accumulators
 //              double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), bias / GELU /
 //              residual / split / patch-embed row remap, 128-bit global stores
 // The M dimension concatenates every image of every scale (and the grid covers both students), so
 // tile-quantisation loss stays below 1 % although 148 is an awkward SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace dupl {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;
 
 struct GemmGroupDev {
@@ -41,19 +46,21 @@ struct GemmParamsDev {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+// BK = k-block depth in bf16 elements: 64 (128-byte swizzled rows) or 32 (64-byte rows, twice the stages).
+template <int BN, int BK>
 struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // one plane
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int A_BYTES = GEMM_BM * BK * 2;  // one plane
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParamsDev p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], 2);  // both CTAs of the cluster must have drained a stage before it is refilled
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full[a], 1);
@@ -91,34 +98,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Work item = (group, pair of M tiles, N tile); CTA `rank` of the cluster takes M tile 2*pair + rank.
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_pairs = (m_tiles + 1) >> 1;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int tiles_per_group = m_tiles * n_tiles;
+  const int tiles_per_group = m_pairs * n_tiles;
   const int total_tiles = tiles_per_group * p.groups;
-  const int k_blocks = p.K / GEMM_BK;
+  const int k_blocks = p.K / BK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int g = t / tiles_per_group;
         const int r = t - g * tiles_per_group;
-        const int m0 = (r / n_tiles) * GEMM_BM;
+        const int m0 = (2 * (r / n_tiles) + rank) * GEMM_BM;
         const int n0 = (r % n_tiles) * BN;
         const GemmGroupDev& G = p.g[g];
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(s, &G.tm_a_hi, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d(s + Cfg::A_BYTES, &G.tm_a_lo, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d(s + 2 * Cfg::A_BYTES, &G.tm_b_hi, &full_bar[stage], kb * GEMM_BK, n0);
-          tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &G.tm_b_lo, &full_bar[stage], kb * GEMM_BK, n0);
+          tma_load_2d(s, &G.tm_a_hi, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(s + Cfg::A_BYTES, &G.tm_a_lo, &full_bar[stage], kb * BK, m0);
+          // this CTA's half of the W tile (rows [rank*BN/2, +BN/2)) goes to both CTAs
+          uint8_t* sb = s + 2 * Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2);
+          tma_load_2d_multicast(sb, &G.tm_b_hi, &full_bar[stage], kb * BK, n0 + rank * (BN / 2), 3);
+          tma_load_2d_multicast(sb + Cfg::B_BYTES, &G.tm_b_lo, &full_bar[stage], kb * BK, n0 + rank * (BN / 2), 3);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + acc * BN;
@@ -143,18 +157,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t a_hi = umma_desc_sw128(s), a_lo = umma_desc_sw128(s + Cfg::A_BYTES);
-          const uint64_t b_hi = umma_desc_sw128(s + 2 * Cfg::A_BYTES), b_lo = umma_desc_sw128(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+          auto desc = [](uint32_t addr) { return BK == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr); };
+          const uint64_t a_hi = desc(s), a_lo = desc(s + Cfg::A_BYTES);
+          const uint64_t b_hi = desc(s + 2 * Cfg::A_BYTES), b_lo = desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint64_t a = (pass == 2) ? a_lo : a_hi;
             const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
+            for (int k = 0; k < BK / 16; ++k)
               tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
                          (kb | pass | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs have read it
+          tc_commit_multicast(&empty_bar[stage], 3);  // stage drained here: tell both producers of the cluster
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -170,10 +185,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int g = t / tiles_per_group;
       const int r = t - g * tiles_per_group;
-      const int m0 = (r / n_tiles) * GEMM_BM;
+      const int m0 = (2 * (r / n_tiles) + rank) * GEMM_BM;
       const int n0 = (r % n_tiles) * BN;
       const GemmGroupDev& G = p.g[g];
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -235,6 +250,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
             }
+            if (p.epilogue == DUPL_EPI_RELU_SPLIT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
             __nv_bfloat16* oh = G.out_hi + static_cast<long>(row) * p.ldo + col0;
             __nv_bfloat16* ol = G.out_lo + static_cast<long>(row) * p.ldo + col0;
 #pragma unroll
@@ -259,26 +278,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN>
+template <int BN, int BK>
 static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BK>;
   static bool attr_set = false;
   if (!attr_set) {
-    DUPL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUPL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_tiles = cdiv(P.M, GEMM_BM), n_tiles = cdiv(P.N, BN);
-  const int total = m_tiles * n_tiles * P.groups;
-  const int grid = total < sm_count() ? total : sm_count();
-  gemm_bf16x3_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(P);
-  DUPL_LAUNCH_OK();
+  const int m_pairs = cdiv(cdiv(P.M, GEMM_BM), 2), n_tiles = cdiv(P.N, BN);
+  const int total = m_pairs * n_tiles * P.groups;  // work items, one per cluster of 2 CTAs
+  const int clusters = total < sm_count() / 2 ? total : sm_count() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DUPL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<BN, BK>, P));
+  count_launch();
   return DUPL_OK;
 }
 
@@ -289,11 +322,15 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   DUPL_CHECK_ARG(a != nullptr, "dupl_gemm_bf16x3: args is NULL");
   DUPL_CHECK_ARG(a->groups >= 1 && a->groups <= DUPL_MAX_GROUPS, "dupl_gemm_bf16x3: groups=%d", a->groups);
   DUPL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "dupl_gemm_bf16x3: empty problem %dx%dx%d", a->M, a->N, a->K);
-  DUPL_CHECK_ARG(a->K % GEMM_BK == 0, "dupl_gemm_bf16x3: K=%d must be a multiple of 64", a->K);
+  DUPL_CHECK_ARG(a->K % 64 == 0, "dupl_gemm_bf16x3: K=%d must be a multiple of 64", a->K);
+  static const int bk = [] {
+    const char* e = getenv("DUPL_GEMM_BK");
+    return (e != nullptr && atoi(e) == 64) ? 64 : 32;
+  }();
   DUPL_CHECK_ARG(a->N % 16 == 0, "dupl_gemm_bf16x3: N=%d must be a multiple of 16", a->N);
   DUPL_CHECK_ARG(a->lda % 8 == 0 && a->lda >= a->K, "dupl_gemm_bf16x3: lda=%d", a->lda);
   DUPL_CHECK_ARG(a->ldo % 8 == 0 && a->ldo >= a->N, "dupl_gemm_bf16x3: ldo=%d", a->ldo);
-  DUPL_CHECK_ARG(a->epilogue >= DUPL_EPI_F32 && a->epilogue <= DUPL_EPI_PATCH, "dupl_gemm_bf16x3: epilogue=%d",
+  DUPL_CHECK_ARG(a->epilogue >= DUPL_EPI_F32 && a->epilogue <= DUPL_EPI_RELU_SPLIT, "dupl_gemm_bf16x3: epilogue=%d",
                  a->epilogue);
   GemmParamsDev P;
   memset(&P, 0, sizeof(P));
@@ -314,10 +351,10 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     DUPL_CHECK_ARG(f32_out || (G.out_hi && G.out_lo), "dupl_gemm_bf16x3: out_hi/out_lo is NULL in group %d", g);
     DUPL_CHECK_ARG(a->epilogue != DUPL_EPI_RESID || G.resid, "dupl_gemm_bf16x3: resid is NULL in group %d", g);
     int rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->M, a->K, a->lda, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->M, a->K, a->lda, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, a->K, bn))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, a->K, bn))) return rc;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, a->K, bn / 2, bk))) return rc;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, a->K, bn / 2, bk))) return rc;
     P.g[g].bias = G.bias; P.g[g].resid = G.resid; P.g[g].out_f32 = G.out_f32;
     P.g[g].out_hi = static_cast<__nv_bfloat16*>(G.out_hi);
     P.g[g].out_lo = static_cast<__nv_bfloat16*>(G.out_lo);
@@ -327,7 +364,12 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
         DUPL_CHECK_ARG(G.pos[s] != nullptr, "dupl_gemm_bf16x3: pos[%d] is NULL in group %d", s, g);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256>(P, st);
-  if (bn == 128) return launch_gemm<128>(P, st);
-  return launch_gemm<64>(P, st);
+  if (bk == 64) {
+    if (bn == 256) return launch_gemm<256, 64>(P, st);
+    if (bn == 128) return launch_gemm<128, 64>(P, st);
+    return launch_gemm<64, 64>(P, st);
+  }
+  if (bn == 256) return launch_gemm<256, 32>(P, st);
+  if (bn == 128) return launch_gemm<128, 32>(P, st);
+  return launch_gemm<64, 32>(P, st);
 }

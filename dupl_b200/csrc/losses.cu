@@ -1,0 +1,340 @@
+// Losses of model/losses.py with fused forward and backward kernels:
+//   get_seg_loss         (losses.py:24-39)  background / foreground balanced cross-entropy
+//   get_masked_ptc_loss  (losses.py:6-21)   abs-cosine Gram of the feature map against the affinity mask
+// Reductions are two-stage (per-block partials, then one block in a fixed order) so results are
+// bit-reproducible.  The Gram is computed in fp32 on the CUDA cores (0.94 GFLOP per image): exact
+// rather than fast; it is < 1 % of the step.
+#include "common.cuh"
+
+namespace dupl {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.0f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) r += sh[w];
+  return r;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg loss
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seg_ce_fwd_kernel(const float* __restrict__ pred, const long long* __restrict__ label,
+                                                         int C, long hw, long total, long long ignore,
+                                                         float* __restrict__ lse_out, float* __restrict__ partials) {
+  __shared__ float sh[8];
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  float bg_loss = 0.0f, fg_loss = 0.0f, bg_cnt = 0.0f, fg_cnt = 0.0f;
+  if (i < total) {
+    const long b = i / hw, p = i % hw;
+    const float* x = pred + b * C * hw + p;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(x + c * hw));
+    float s = 0.0f;
+    for (int c = 0; c < C; ++c) s += expf(__ldg(x + c * hw) - mx);
+    const float lse = mx + logf(s);
+    lse_out[i] = lse;
+    const long long lab = label[i];
+    if (lab != ignore && lab >= 0 && lab < C) {
+      const float nll = lse - __ldg(x + lab * hw);
+      if (lab == 0) {
+        bg_loss = nll;
+        bg_cnt = 1.0f;
+      } else {
+        fg_loss = nll;
+        fg_cnt = 1.0f;
+      }
+    }
+  }
+  float r;
+  r = block_sum(bg_loss, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 0] = r;
+  r = block_sum(fg_loss, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 1] = r;
+  r = block_sum(bg_cnt, sh);  if (threadIdx.x == 0) partials[4 * blockIdx.x + 2] = r;
+  r = block_sum(fg_cnt, sh);  if (threadIdx.x == 0) partials[4 * blockIdx.x + 3] = r;
+}
+
+// stats[0..3] = sums; stats[4] = loss
+__global__ void __launch_bounds__(256) seg_ce_finish_kernel(const float* __restrict__ partials, int nblocks,
+                                                            float* __restrict__ stats) {
+  __shared__ double sh[4][256];
+  double a[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+    for (int k = 0; k < 4; ++k) a[k] += partials[4 * i + k];
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = a[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 256; ++i)
+      for (int k = 0; k < 4; ++k) t[k] += sh[k][i];
+    for (int k = 0; k < 4; ++k) stats[k] = static_cast<float>(t[k]);
+    const float bg = stats[0] / (stats[2] + 1e-6f), fg = stats[1] / (stats[3] + 1e-6f);
+    stats[4] = (bg + fg) * 0.5f;
+  }
+}
+
+__global__ void __launch_bounds__(256) seg_ce_bwd_kernel(const float* __restrict__ pred, const long long* __restrict__ label,
+                                                         const float* __restrict__ lse, const float* __restrict__ stats,
+                                                         const float* __restrict__ grad_out, int C, long hw, long total,
+                                                         long long ignore, float* __restrict__ dpred) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const long b = i / hw, p = i % hw;
+  const long long lab = label[i];
+  float w = 0.0f;
+  if (lab != ignore && lab >= 0 && lab < C) w = 0.5f / ((lab == 0 ? stats[2] : stats[3]) + 1e-6f) * grad_out[0];
+  const float* x = pred + b * C * hw + p;
+  float* d = dpred + b * C * hw + p;
+  const float l = lse[i];
+  for (int c = 0; c < C; ++c) {
+    float g = 0.0f;
+    if (w != 0.0f) g = w * (expf(__ldg(x + c * hw) - l) - (c == lab ? 1.0f : 0.0f));
+    d[c * hw] = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTC loss.  x: [b][C][n] (n = h*w), mask: int64 [b][n][n]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ptc_invnorm_kernel(const float* __restrict__ x, int C, int n, int total,
+                                                          float* __restrict__ inv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / n, p = i % n;
+  const float* col = x + static_cast<long>(b) * C * n + p;
+  float s = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(col + static_cast<long>(c) * n);
+    s = fmaf(v, v, s);
+  }
+  inv[i] = 1.0f / fmaxf(sqrtf(s), 1e-8f);  // F.normalize(eps=1e-8): x / max(||x||, eps)
+}
+
+constexpr int PT = 64;  // Gram tile
+constexpr int PK = 16;  // channel chunk
+
+// Gs[b][p][q] = cos(x_p, x_q); partial masked sums of |Gs|.
+__global__ void __launch_bounds__(256) ptc_gram_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                       const long long* __restrict__ mask, int C, int n,
+                                                       float* __restrict__ Gs, float* __restrict__ partials) {
+  __shared__ float sa[PK][PT + 1], sb[PK][PT + 1];
+  __shared__ float sh[8];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * PT, q0 = blockIdx.x * PT;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 x 16 threads, 4 x 4 outputs each
+  const float* xb = x + static_cast<long>(b) * C * n;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int c0 = 0; c0 < C; c0 += PK) {
+    for (int e = threadIdx.x; e < PK * PT; e += 256) {
+      const int cc = e / PT, pp = e % PT;
+      const int c = c0 + cc;
+      sa[cc][pp] = (c < C && p0 + pp < n) ? __ldg(xb + static_cast<long>(c) * n + p0 + pp) : 0.0f;
+      sb[cc][pp] = (c < C && q0 + pp < n) ? __ldg(xb + static_cast<long>(c) * n + q0 + pp) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < PK; ++cc) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[cc][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = sb[cc][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float pos_sum = 0.0f, neg_sum = 0.0f, pos_cnt = 0.0f, neg_cnt = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty * 4 + i;
+    if (p >= n) continue;
+    const float ip = inv[b * n + p];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + tx * 4 + j;
+      if (q >= n) continue;
+      const float g = acc[i][j] * ip * inv[b * n + q];
+      const long o = (static_cast<long>(b) * n + p) * n + q;
+      Gs[o] = g;
+      const long long m = mask[o];
+      if (m == 1) {
+        pos_sum += fabsf(g);
+        pos_cnt += 1.0f;
+      } else if (m == 0) {
+        neg_sum += fabsf(g);
+        neg_cnt += 1.0f;
+      }
+    }
+  }
+  const int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  float r;
+  r = block_sum(pos_sum, sh); if (threadIdx.x == 0) partials[4 * blk + 0] = r;
+  r = block_sum(neg_sum, sh); if (threadIdx.x == 0) partials[4 * blk + 1] = r;
+  r = block_sum(pos_cnt, sh); if (threadIdx.x == 0) partials[4 * blk + 2] = r;
+  r = block_sum(neg_cnt, sh); if (threadIdx.x == 0) partials[4 * blk + 3] = r;
+}
+
+__global__ void __launch_bounds__(256) ptc_finish_kernel(const float* __restrict__ partials, int nblocks,
+                                                         float* __restrict__ stats) {
+  __shared__ double sh[4][256];
+  double a[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+    for (int k = 0; k < 4; ++k) a[k] += partials[4 * i + k];
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = a[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 256; ++i)
+      for (int k = 0; k < 4; ++k) t[k] += sh[k][i];
+    for (int k = 0; k < 4; ++k) stats[k] = static_cast<float>(t[k]);
+    // 0.5 (1 - sum_pos / (n_pos + 1)) + 0.5 sum_neg / (n_neg + 1)
+    stats[4] = 0.5f * (1.0f - stats[0] / (stats[2] + 1.0f)) + 0.5f * stats[1] / (stats[3] + 1.0f);
+  }
+}
+
+// dXh[b][c][p] = sum_q T[p][q] xh[c][q],  T[p][q] = S[p][q] + S[q][p],
+// S[p][q] = g * sign(Gs[p][q]) * (mask==1 ? -0.5/(n_pos+1) : mask==0 ? 0.5/(n_neg+1) : 0)
+__global__ void __launch_bounds__(256) ptc_bwd_gemm_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                           const long long* __restrict__ mask, const float* __restrict__ Gs,
+                                                           const float* __restrict__ stats, const float* __restrict__ grad_out,
+                                                           int C, int n, float* __restrict__ dxh) {
+  __shared__ float st[PK][PT + 1];   // T[q chunk][p tile]
+  __shared__ float sx[PK][PT + 1];   // xh[q chunk][c tile]
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * PT, c0 = blockIdx.y * PT;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // outputs: c = c0 + ty*4 + i, p = p0 + tx*4 + j
+  const float g = grad_out[0];
+  const float wpos = -0.5f / (stats[2] + 1.0f) * g, wneg = 0.5f / (stats[3] + 1.0f) * g;
+  const float* xb = x + static_cast<long>(b) * C * n;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  auto sfun = [&](int p, int q) -> float {
+    const long o = (static_cast<long>(b) * n + p) * n + q;
+    const long long m = mask[o];
+    if (m != 0 && m != 1) return 0.0f;
+    const float gs = Gs[o];
+    const float sg = gs > 0.0f ? 1.0f : (gs < 0.0f ? -1.0f : 0.0f);
+    return sg * (m == 1 ? wpos : wneg);
+  };
+  for (int q0 = 0; q0 < n; q0 += PK) {
+    for (int e = threadIdx.x; e < PK * PT; e += 256) {
+      const int qq = e / PT, pp = e % PT;
+      const int q = q0 + qq, p = p0 + pp;
+      st[qq][pp] = (q < n && p < n) ? sfun(p, q) + sfun(q, p) : 0.0f;
+      const int c = c0 + pp;
+      sx[qq][pp] = (q < n && c < C) ? __ldg(xb + static_cast<long>(c) * n + q) * inv[b * n + q] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qq = 0; qq < PK; ++qq) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sx[qq][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = st[qq][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty * 4 + i;
+    if (c >= C) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = p0 + tx * 4 + j;
+      if (p < n) dxh[(static_cast<long>(b) * C + c) * n + p] = acc[i][j];
+    }
+  }
+}
+
+// x_hat = x * inv  =>  dx = inv * (dxh - x_hat * <x_hat, dxh>)   (columns whose norm was clamped: dx = inv * dxh)
+__global__ void __launch_bounds__(256) ptc_bwd_norm_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                           const float* __restrict__ dxh, int C, int n, int total,
+                                                           float* __restrict__ dx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / n, p = i % n;
+  const long base = static_cast<long>(b) * C * n + p;
+  const float iv = inv[i];
+  float dot = 0.0f;
+  for (int c = 0; c < C; ++c) dot = fmaf(__ldg(x + base + static_cast<long>(c) * n) * iv, __ldg(dxh + base + static_cast<long>(c) * n), dot);
+  const bool clamped = iv >= 1e8f;  // ||x|| <= eps
+  for (int c = 0; c < C; ++c) {
+    const long o = base + static_cast<long>(c) * n;
+    const float xh = __ldg(x + o) * iv;
+    dx[o] = iv * (dxh[o] - (clamped ? 0.0f : xh * dot));
+  }
+}
+
+}  // namespace dupl
+
+using namespace dupl;
+
+extern "C" int dupl_seg_loss_fwd(const float* pred, const int64_t* label, int32_t b, int32_t C, int32_t H, int32_t W,
+                                 int64_t ignore_index, float* lse, float* partials, float* stats, void* stream) {
+  DUPL_CHECK_ARG(pred && label && lse && partials && stats && b > 0 && C > 0 && H > 0 && W > 0, "dupl_seg_loss_fwd: bad arguments");
+  const long hw = static_cast<long>(H) * W, total = hw * b;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  seg_ce_fwd_kernel<<<blocks, 256, 0, st>>>(pred, reinterpret_cast<const long long*>(label), C, hw, total, ignore_index, lse, partials);
+  DUPL_LAUNCH_OK();
+  seg_ce_finish_kernel<<<1, 256, 0, st>>>(partials, blocks, stats);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_seg_loss_bwd(const float* pred, const int64_t* label, const float* lse, const float* stats,
+                                 const float* grad_out, int32_t b, int32_t C, int32_t H, int32_t W, int64_t ignore_index,
+                                 float* dpred, void* stream) {
+  DUPL_CHECK_ARG(pred && label && lse && stats && grad_out && dpred, "dupl_seg_loss_bwd: NULL pointer");
+  const long hw = static_cast<long>(H) * W, total = hw * b;
+  seg_ce_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, reinterpret_cast<const long long*>(label), lse, stats, grad_out, C, hw, total, ignore_index, dpred);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_loss_fwd(const float* x, const int64_t* mask, int32_t b, int32_t C, int32_t n, float* inv,
+                                 float* Gs, float* partials, float* stats, void* stream) {
+  DUPL_CHECK_ARG(x && mask && inv && Gs && partials && stats && b > 0 && C > 0 && n > 0, "dupl_ptc_loss_fwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ptc_invnorm_kernel<<<cdiv(b * n, 256), 256, 0, st>>>(x, C, n, b * n, inv);
+  DUPL_LAUNCH_OK();
+  dim3 grid(cdiv(n, PT), cdiv(n, PT), b);
+  ptc_gram_kernel<<<grid, 256, 0, st>>>(x, inv, reinterpret_cast<const long long*>(mask), C, n, Gs, partials);
+  DUPL_LAUNCH_OK();
+  ptc_finish_kernel<<<1, 256, 0, st>>>(partials, static_cast<int>(grid.x * grid.y * grid.z), stats);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_loss_bwd(const float* x, const int64_t* mask, const float* inv, const float* Gs, const float* stats,
+                                 const float* grad_out, int32_t b, int32_t C, int32_t n, float* dxh_scratch, float* dx,
+                                 void* stream) {
+  DUPL_CHECK_ARG(x && mask && inv && Gs && stats && grad_out && dxh_scratch && dx, "dupl_ptc_loss_bwd: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(cdiv(n, PT), cdiv(C, PT), b);
+  ptc_bwd_gemm_kernel<<<grid, 256, 0, st>>>(x, inv, reinterpret_cast<const long long*>(mask), Gs, stats, grad_out, C, n, dxh_scratch);
+  DUPL_LAUNCH_OK();
+  ptc_bwd_norm_kernel<<<cdiv(b * n, 256), 256, 0, st>>>(x, inv, dxh_scratch, C, n, b * n, dx);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}

@@ -42,7 +42,8 @@ template <int V>
 __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ hi,
-                                                              __nv_bfloat16* __restrict__ lo, int rows, float eps) {
+                                                              __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32,
+                                                              int rows, float eps) {
   constexpr int COLS = V * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -69,8 +70,10 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
     const long o = static_cast<long>(row) * COLS + c;
-    store_split4(hi + o, lo + o, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                 (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    const float4 y = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                 (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    if (hi != nullptr) store_split4(hi + o, lo + o, y.x, y.y, y.z, y.w);
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + o) = y;
   }
 }
 
@@ -270,8 +273,9 @@ extern "C" int dupl_split_bf16(const float* x, void* hi, void* lo, int64_t n, vo
 }
 
 extern "C" int dupl_layernorm_split(const float* x, const float* gamma, const float* beta, void* out_hi, void* out_lo,
-                                    int32_t rows, int32_t cols, float eps, void* stream) {
-  DUPL_CHECK_ARG(x && gamma && beta && out_hi && out_lo, "dupl_layernorm_split: NULL pointer");
+                                    float* out_f32, int32_t rows, int32_t cols, float eps, void* stream) {
+  DUPL_CHECK_ARG(x && gamma && beta && ((out_hi && out_lo) || out_f32) && ((out_hi == nullptr) == (out_lo == nullptr)),
+                 "dupl_layernorm_split: NULL pointer");
   DUPL_CHECK_ARG(rows > 0 && cols % 128 == 0 && cols >= 128 && cols <= 1024, "dupl_layernorm_split: rows=%d cols=%d",
                  rows, cols);
   const int grid = cdiv(rows, 8);
@@ -279,7 +283,7 @@ extern "C" int dupl_layernorm_split(const float* x, const float* gamma, const fl
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(out_lo);
   switch (cols / 128) {
-#define LN_CASE(V) case V: layernorm_split_kernel<V><<<grid, 256, 0, st>>>(x, gamma, beta, hi, lo, rows, eps); break;
+#define LN_CASE(V) case V: layernorm_split_kernel<V><<<grid, 256, 0, st>>>(x, gamma, beta, hi, lo, out_f32, rows, eps); break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
   }

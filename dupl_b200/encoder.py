@@ -27,9 +27,14 @@ class StudentPlanes:
         self.encoder = encoder
         self._planes = {}
         self._pos = {}
+        self._pdict = None
 
     def _params(self):
-        return dict(self.encoder.named_parameters())
+        # nn.Module keeps the same Parameter objects across .to()/.cuda()/optimizer steps (only .data moves),
+        # so the name -> Parameter map is built once; walking named_parameters() per lookup cost ~10 ms per pass.
+        if self._pdict is None:
+            self._pdict = dict(self.encoder.named_parameters())
+        return self._pdict
 
     def plane(self, name):
         p = self._params()[name]

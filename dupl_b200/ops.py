@@ -65,10 +65,35 @@ def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None):
     L.check(L.lib().dupl_gemm_bf16x3(C.byref(a), L.stream_ptr(dev)), "dupl_gemm_bf16x3")
 
 
-def layernorm_split(x, gamma, beta, out_hi, out_lo, eps=1e-6):
+def layernorm_split(x, gamma, beta, out_hi, out_lo, eps=1e-6, out_f32=None):
     rows, cols = x.shape
-    L.check(L.lib().dupl_layernorm_split(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(out_hi), L.ptr(out_lo),
+    L.check(L.lib().dupl_layernorm_split(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(out_hi), L.ptr(out_lo), L.ptr(out_f32),
                                          rows, cols, eps, L.stream_ptr(x.device)), "dupl_layernorm_split")
+
+
+def im2col3x3(in_hi, in_lo, B, gh, gw, dilation, row_offset, row_stride, first):
+    cin = in_hi.shape[1]
+    out_hi = torch.empty(B * gh * gw, 9 * cin, dtype=torch.bfloat16, device=in_hi.device)
+    out_lo = torch.empty_like(out_hi)
+    L.check(L.lib().dupl_im2col3x3(L.ptr(in_hi), L.ptr(in_lo), L.ptr(out_hi), L.ptr(out_lo), B, gh, gw, cin, dilation,
+                                   row_offset, row_stride, first, L.stream_ptr(in_hi.device)), "dupl_im2col3x3")
+    return out_hi, out_lo
+
+
+def rows_to_nchw(src, B, gh, gw, Cc, row_offset, row_stride, first):
+    out = torch.empty(B, Cc, gh, gw, dtype=torch.float32, device=src.device)
+    L.check(L.lib().dupl_rows_to_nchw(L.ptr(src), L.ptr(out), B, gh * gw, Cc, src.shape[1], row_offset, row_stride, first,
+                                      L.stream_ptr(src.device)), "dupl_rows_to_nchw")
+    return out
+
+
+def gmp_classify(x, w, B, np_, row_offset, row_stride, first, want_argmax=False):
+    K, D = w.shape
+    logits = torch.empty(B, K, dtype=torch.float32, device=x.device)
+    arg = torch.empty(B, D, dtype=torch.int32, device=x.device) if want_argmax else None
+    L.check(L.lib().dupl_gmp_classify(L.ptr(x), L.ptr(w), L.ptr(logits), L.ptr(arg), B, np_, D, K, row_offset, row_stride,
+                                      first, L.stream_ptr(x.device)), "dupl_gmp_classify")
+    return (logits, arg) if want_argmax else logits
 
 
 def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale):

@@ -71,6 +71,7 @@ int dupl_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
 #define DUPL_EPI_GELU_SPLIT 2 /* out_hi/lo = split(gelu_erf(acc + bias))  (fc1+act: vit.py:98-99) */
 #define DUPL_EPI_RESID 3      /* out_f32 = resid + acc + bias  (proj / fc2 + residual: vit.py:158-159) */
 #define DUPL_EPI_PATCH 4      /* out_f32[token row] = acc + bias + pos_embed (vit.py:292-304)  */
+#define DUPL_EPI_RELU_SPLIT 5 /* out_hi/lo = split(relu(acc + bias))   (conv6/conv7 + ReLU: conv_head.py:34-38) */
 
 typedef struct {
   const void* a_hi;
@@ -100,9 +101,10 @@ typedef struct {
 int dupl_gemm_bf16x3(const dupl_gemm_args* args, void* stream);
 
 /* LayerNorm over the last dim (biased variance, eps inside the sqrt; vit.py:146,152,256 with
- * eps=1e-6 from deit.py:100) of x[rows, cols] -> split bf16 planes (cols % 128 == 0, <= 1024). */
+ * eps=1e-6 from deit.py:100) of x[rows, cols] -> split bf16 planes and/or fp32 (either output may be
+ * NULL; cols % 128 == 0, <= 1024). */
 int dupl_layernorm_split(const float* x, const float* gamma, const float* beta, void* out_hi, void* out_lo,
-                         int32_t rows, int32_t cols, float eps, void* stream);
+                         float* out_f32, int32_t rows, int32_t cols, float eps, void* stream);
 
 /* softmax(Q K^T * scale) V per (image, head)  (vit.py:120-135), fused flash-style.
  * qkv planes: [M, 3*heads*64] split bf16 as produced by the qkv GEMM (q | k | v, head-major);
@@ -147,6 +149,23 @@ int dupl_cls_rows(float* tok, const float* cls_token, const float* const* pos, c
 int dupl_cam_contract(const float* tok, const float* gamma, const float* beta, float eps, const float* w,
                       int32_t K, int32_t D, const dupl_segment* seg, int32_t nseg, float* out,
                       const int64_t* out_offset_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder and classification heads (model/decoder/conv_head.py:33-41, model_dupl.py:86-95).
+ * Rows of a token-major matrix are addressed as row(b, p) = row_offset + b*row_stride + first + p
+ * (first = 1 skips the cls token of each image).
+ * ---------------------------------------------------------------------------------------- */
+/* im2col of a 3x3 / dilation d / zero-padding d convolution on token-major split-bf16 planes [*, Cin]:
+ * out[(b*gh*gw + y*gw + x)][tap*Cin + c], tap = ky*3 + kx; the conv is then dupl_gemm_bf16x3 against
+ * the weight re-laid out as [Cout][tap][Cin]. */
+int dupl_im2col3x3(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int32_t B, int32_t gh, int32_t gw,
+                   int32_t Cin, int32_t dilation, int32_t row_offset, int32_t row_stride, int32_t first, void* stream);
+/* out[b][c][p] = src[row(b,p)][c], c < C (src row stride ld): token-major -> NCHW (to_2D, model_dupl.py:64-67). */
+int dupl_rows_to_nchw(const float* src, float* out, int32_t B, int32_t np, int32_t C, int32_t ld, int32_t row_offset,
+                      int32_t row_stride, int32_t first, void* stream);
+/* logits[b][k] = sum_d (max_p x[row(b,p)][d]) w[k][d]; argmax (optional, int32 [B][D]) keeps the pooled rows. */
+int dupl_gmp_classify(const float* x, const float* w, float* logits, int32_t* argmax, int32_t B, int32_t np, int32_t D,
+                      int32_t K, int32_t row_offset, int32_t row_stride, int32_t first, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * multi_scale_cam2_siamese post-processing (utils/cam_helper.py:173-202): per scale bilinear

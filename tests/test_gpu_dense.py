@@ -143,3 +143,29 @@ def test_multi_scale_cam_matches_oracle():
     assert torch.equal(c1, cam) and torch.equal(a1, aux)
     ocam2, _, osum2, _ = O.multi_scale_cam(P, 2, x, (1.0, 0.5, 1.5), return_sums=True)
     assert mscam_err(c2, ocam2, osum2) < 1e-3
+
+
+def test_val_forward_matches_oracle():
+    """siamese_network.forward(val=True) (model_dupl.py:160-168, 86-98): cls logits, seg logits, feature map and
+    aux cls logits within 1e-3 relative of the fp32 oracle; also the single-branch call."""
+    from oracle import dupl_oracle as O
+    m, P = _load_model()
+    x = synth_images(2, 96, 64, seed=5)
+    with torch.no_grad():
+        res = m(x.cuda(), val=True)
+        for br in (1, 2):
+            want = O.network_forward(P, br, x)
+            got = res[f"branch{br}"]
+            assert len(got) == 4
+            for g, w in zip(got, want):
+                assert g.shape == w.shape
+                assert rel_err(g, w) < 1e-3
+        one = m(x.cuda(), val=True, branch=2)
+        assert torch.equal(one[1], res["branch2"][1])
+
+
+def test_training_mode_forward_fails_loudly_until_built():
+    m, _ = _load_model()
+    m.train()
+    with pytest.raises(NotImplementedError, match="no PyTorch fallback"):
+        m(synth_images(1, 32, 32).cuda())

@@ -70,3 +70,20 @@ def test_model_golden():
     _, _, osum, oaux_sum = O.multi_scale_cam(P, 2, d["x"], (1.0, 0.5, 1.5), return_sums=True)
     assert mscam_err(cam, d["mscam_2"], osum) < 1e-3
     assert mscam_err(aux, d["mscam_aux_2"], oaux_sum) < 1e-3
+
+
+def test_val_forward_golden():
+    """model(x) outputs of the reference (cls, seg, fmap, cls_aux) — model_dupl.py:86-106."""
+    from dupl_b200.model.model_dupl import siamese_network
+    d = load("model.npz")
+    P = init_state_dict(21)
+    m = siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
+    m.load_state_dict(P, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        res = m(d["x"].cuda(), val=True)
+    cls1, seg1, fmap1, aux1 = res["branch1"]
+    for got, want in ((cls1, d["cls_1"]), (seg1, d["seg_1"]), (fmap1, d["fmap_1"]), (aux1, d["cls_aux_1"]),
+                      (res["branch2"][0], d["cls_2"]), (res["branch2"][1], d["seg_2"]), (res["branch2"][3], d["cls_aux_2"])):
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 1e-3
