@@ -6,14 +6,18 @@
 // bf16/fp16/tf32 pass moves the normalised CAMs by 2e-3 (tools/precision_study.py), above the 1e-3
 // parity bar of the path; the split keeps the error at ~2e-5 for 3 MMAs per k-step.
 //
-// Structure (one CTA per SM, 192 threads, clusters of 2 CTAs):
-//   warp 0     TMA producer: A_hi/A_lo [128 x 64] and W_hi/W_lo [BN x 64] tiles, 128-byte swizzle.
-//              The two CTAs of a cluster work on vertically adjacent output tiles (same W tile): each
-//              loads HALF of the W tile and multicasts it to both, so a k-block costs 64 KB of L2->SM
-//              traffic per CTA instead of 96 KB (the single-CTA version was L2-bandwidth bound at
-//              ~60 % tensor-pipe utilisation, profiles/r01_summary.md)
-//   warp 1     MMA issuer (one lane): 3 x 4 tcgen05.mma (128 x BN x 16) per k-block, accumulators
-//              double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+// Structure (one CTA per SM, 192 threads, CTA PAIRS = clusters of 2, tcgen05 cta_group::2):
+//   a pair computes a 256 x BN output tile; each CTA stages its 128 rows of A and HALF of the W tile
+//   (BN/2 rows) in its own shared memory, and owns 128 rows of the accumulator in its own TMEM.  With
+//   both operands in shared memory a single-CTA 128 x 256 x 16 MMA reads 12 KB of shared memory per
+//   128 clocks (94 B/clk with the 3 passes) while TMA writes another 64 B/clk: the single-CTA version
+//   sat at ~60 % tensor-pipe utilisation on the 128 B/clk shared-memory port.  The pair halves the W
+//   reads per SM (62 B/clk) and the smaller stage leaves room for 3 pipeline stages.
+//   warp 0     TMA producer (both CTAs): A_hi/A_lo [128 x BK], W_hi/W_lo [BN/2 x BK]; the bytes of both
+//              CTAs are accounted on the leader's full barrier
+//   warp 1     MMA issuer (leader CTA only): 3 x BK/16 tcgen05.mma.cta_group::2 (256 x BN x 16) per
+//              k-block; commits are multicast to both CTAs; accumulators double-buffered in TMEM so
+//              the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), bias / GELU /
 //              residual / split / patch-embed row remap, 128-bit global stores
 // The M dimension concatenates every image of every scale (and the grid covers both students), so
@@ -50,7 +54,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN, int BK>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * BK * 2;  // one plane
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the W tile, one plane
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
@@ -83,22 +87,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) {
-        mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 2);  // both CTAs of the cluster must have drained a stage before it is refilled
+        mbar_init(&full_bar[s], 1);   // used in the leader CTA only (its producer's arrive.expect_tx)
+        mbar_init(&empty_bar[s], 1);  // one multicast commit per k-block
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 128);
+        mbar_init(&tmem_empty[a], 256);  // leader's copy collects the epilogue threads of BOTH CTAs
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
+  cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -126,13 +130,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(s, &G.tm_a_hi, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(s + Cfg::A_BYTES, &G.tm_a_lo, &full_bar[stage], kb * BK, m0);
-          // this CTA's half of the W tile (rows [rank*BN/2, +BN/2)) goes to both CTAs
-          uint8_t* sb = s + 2 * Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2);
-          tma_load_2d_multicast(sb, &G.tm_b_hi, &full_bar[stage], kb * BK, n0 + rank * (BN / 2), 3);
-          tma_load_2d_multicast(sb + Cfg::B_BYTES, &G.tm_b_lo, &full_bar[stage], kb * BK, n0 + rank * (BN / 2), 3);
+          const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
+          tma_load_2d_pair(s, &G.tm_a_hi, lead_full, kb * BK, m0);
+          tma_load_2d_pair(s + Cfg::A_BYTES, &G.tm_a_lo, lead_full, kb * BK, m0);
+          tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &G.tm_b_hi, lead_full, kb * BK, n0 + rank * (BN / 2));
+          tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &G.tm_b_lo, lead_full, kb * BK, n0 + rank * (BN / 2));
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -141,9 +144,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp, leader elected per op)
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, lane elected per op)
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, 0, 0, 256);
       const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -166,16 +169,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
-                         (kb | pass | k) != 0 ? 1u : 0u);
+              tc_mma_f16_pair(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
+                              (kb | pass | k) != 0 ? 1u : 0u);
           }
-          tc_commit_multicast(&empty_bar[stage], 3);  // stage drained here: tell both producers of the cluster
+          tc_commit_pair(&empty_bar[stage]);  // stage drained in both CTAs: tell both producers
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete
+        tc_commit_pair(&tmem_full[acc]);  // accumulator complete in both CTAs
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));  // the leader's MMA warp waits for both CTAs' epilogues
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -278,10 +281,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  cluster_sync();  // no CTA leaves while its peer may still read its shared memory or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -323,9 +326,11 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   DUPL_CHECK_ARG(a->groups >= 1 && a->groups <= DUPL_MAX_GROUPS, "dupl_gemm_bf16x3: groups=%d", a->groups);
   DUPL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "dupl_gemm_bf16x3: empty problem %dx%dx%d", a->M, a->N, a->K);
   DUPL_CHECK_ARG(a->K % 64 == 0, "dupl_gemm_bf16x3: K=%d must be a multiple of 64", a->K);
+  // k-block depth: 64 (128-byte swizzle, 3 stages) and 32 (64-byte swizzle, 7 stages) measure the same on
+  // B200 (the kernel is not latency bound); DUPL_GEMM_BK=32 selects the deeper pipeline for experiments.
   static const int bk = [] {
     const char* e = getenv("DUPL_GEMM_BK");
-    return (e != nullptr && atoi(e) == 64) ? 64 : 32;
+    return (e != nullptr && atoi(e) == 32) ? 32 : 64;
   }();
   DUPL_CHECK_ARG(a->N % 16 == 0, "dupl_gemm_bf16x3: N=%d must be a multiple of 16", a->N);
   DUPL_CHECK_ARG(a->lda % 8 == 0 && a->lda >= a->K, "dupl_gemm_bf16x3: lda=%d", a->lda);

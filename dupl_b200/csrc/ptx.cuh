@@ -55,13 +55,54 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// Same, delivered to the same shared-memory offset (and mbarrier offset) of every CTA in `cta_mask`.
-__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
-                                                      uint16_t cta_mask) {
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// shared::cluster address of `p` (a shared-memory location of the calling CTA) in CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA of a pair: data lands in this CTA's shared memory, the bytes are accounted on the
+// mbarrier at shared::cluster address `bar_cluster_addr` (the leader CTA's barrier).
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 256 x N x 16 MMA executed by the two SMs of a CTA pair (each holds 128 rows of A and N/2 rows of B in
+// its own shared memory, and 128 rows of the accumulator in its own TMEM).  Issued by the leader CTA only.
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Commit of the pair's MMAs, arriving on the barrier at this offset in both CTAs.
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(bar))
       : "memory");
 }
 // ---------------------------------------------------------------- clusters
@@ -104,15 +145,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
       ::"r"(smem_u32(bar))
-      : "memory");
-}
-// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (cluster multicast).
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16/fp16 inputs, fp32 accumulate.
@@ -193,9 +225,10 @@ __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t by
 // Instruction descriptor, kind::f16: bf16 x bf16 -> f32, M = 128.
 //   [4,6) c_format F32=1   [7,10) a_format BF16=1   [10,13) b_format BF16=1
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, int b_mn_major, int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (8u << 24);
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- split-bf16 helpers

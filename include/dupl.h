@@ -264,6 +264,27 @@ typedef struct {
 int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Losses (model/losses.py) with fused forward + backward.
+ * ---------------------------------------------------------------------------------------- */
+/* get_seg_loss (losses.py:24-39): 0.5 * [ sum CE over label==0 / (n_bg + 1e-6) + sum CE over label not in
+ * {0, ignore} / (n_fg + 1e-6) ].  pred fp32 [b,C,H,W]; label int64 [b,H,W].
+ * lse: [b,H,W] scratch kept for backward; partials: 4*ceil(b*H*W/256) floats; stats: 5 floats
+ * (sum_bg, sum_fg, n_bg, n_fg, loss). */
+int dupl_seg_loss_fwd(const float* pred, const int64_t* label, int32_t b, int32_t C, int32_t H, int32_t W,
+                      int64_t ignore_index, float* lse, float* partials, float* stats, void* stream);
+/* dpred = grad_out[0] * d loss / d pred. */
+int dupl_seg_loss_bwd(const float* pred, const int64_t* label, const float* lse, const float* stats,
+                      const float* grad_out, int32_t b, int32_t C, int32_t H, int32_t W, int64_t ignore_index,
+                      float* dpred, void* stream);
+/* get_masked_ptc_loss (losses.py:6-21): x fp32 [b,C,n] (n = h*w), mask int64 [b,n,n] with values {0,1,other};
+ * inv: [b,n]; Gs: [b,n,n] signed cosine matrix kept for backward; partials: 4*b*ceil(n/64)^2 floats;
+ * stats: 5 floats (sum_pos, sum_neg, n_pos, n_neg, loss). */
+int dupl_ptc_loss_fwd(const float* x, const int64_t* mask, int32_t b, int32_t C, int32_t n, float* inv, float* Gs,
+                      float* partials, float* stats, void* stream);
+int dupl_ptc_loss_bwd(const float* x, const int64_t* mask, const float* inv, const float* Gs, const float* stats,
+                      const float* grad_out, int32_t b, int32_t C, int32_t n, float* dxh_scratch, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DenseCRF mean-field inference (utils/dcrf.py:42-69 -> pydensecrf DenseCRF2D: setUnaryEnergy,
  * addPairwiseGaussian(sxy=pos_xy_std, compat=pos_w), addPairwiseBilateral(sxy=bi_xy_std,
  * srgb=bi_rgb_std, compat=bi_w), inference(iters)); also serves crf_inference / crf_inference_label

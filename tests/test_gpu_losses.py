@@ -1,0 +1,74 @@
+"""GPU: fused loss kernels (dupl_b200.model.losses) vs the oracle's autograd on CPU — values and gradients."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _labels(b, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(0, 6, (b, H, W), generator=g)
+    lab[lab == 5] = 255
+    lab[lab == 4] = 0
+    return lab
+
+
+@pytest.mark.parametrize("b,C,H,W", [(2, 21, 32, 48), (1, 81, 17, 23), (3, 5, 64, 64)])
+def test_seg_loss_value_and_gradient(b, C, H, W):
+    from dupl_b200.model.losses import get_seg_loss
+    from oracle import dupl_oracle as O
+    g = torch.Generator().manual_seed(b * C)
+    pred = torch.randn(b, C, H, W, generator=g) * 2
+    lab = _labels(b, H, W, seed=H)
+    p_ref = pred.clone().requires_grad_(True)
+    want = O.seg_loss(p_ref, lab)
+    (want * 1.7).backward()
+    p_gpu = pred.cuda().requires_grad_(True)
+    got = get_seg_loss(p_gpu, lab.cuda(), ignore_index=255)
+    (got * 1.7).backward()
+    assert abs(got.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    assert rel_err(p_gpu.grad, p_ref.grad) < 1e-4
+
+
+def test_seg_loss_without_foreground_or_background_is_finite():
+    from dupl_b200.model.losses import get_seg_loss
+    pred = torch.randn(1, 4, 8, 8).cuda().requires_grad_(True)
+    lab = torch.full((1, 8, 8), 255, dtype=torch.long).cuda()
+    loss = get_seg_loss(pred, lab)
+    loss.backward()
+    assert loss.item() == 0.0 and torch.count_nonzero(pred.grad) == 0
+
+
+@pytest.mark.parametrize("b,C,h,w", [(2, 768, 7, 9), (1, 96, 12, 11), (3, 768, 28, 28)])
+def test_ptc_loss_value_and_gradient(b, C, h, w):
+    from dupl_b200.model.losses import get_masked_ptc_loss
+    from dupl_b200.utils import cam_helper
+    from oracle import dupl_oracle as O
+    g = torch.Generator().manual_seed(C + h)
+    fmap = torch.randn(b, C, h, w, generator=g)
+    lab = torch.randint(0, 4, (b, h, w), generator=g)
+    lab[lab == 3] = 255
+    aff = O.label_to_aff_mask(lab)
+    f_ref = fmap.clone().requires_grad_(True)
+    want = O.masked_ptc_loss(f_ref, aff)
+    (want * 0.5).backward()
+    f_gpu = fmap.cuda().requires_grad_(True)
+    got = get_masked_ptc_loss(f_gpu, cam_helper.label_to_aff_mask(lab.cuda()))
+    (got * 0.5).backward()
+    assert abs(got.item() - want.item()) < 1e-5
+    assert rel_err(f_gpu.grad, f_ref.grad) < 1e-3
+
+
+def test_losses_match_reference_golden_values():
+    from dupl_b200.model.losses import get_masked_ptc_loss, get_seg_loss
+    d = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "losses.npz")).items()}
+    ptc = get_masked_ptc_loss(d["fmap"].cuda(), d["aff"].cuda())
+    assert abs(ptc.item() - float(d["ptc"])) < 1e-5
+    seg = get_seg_loss(d["pred"].float().cuda(), d["label"].long().cuda(), ignore_index=255)
+    assert abs(seg.item() - float(d["seg"])) < 1e-4
