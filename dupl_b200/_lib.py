@@ -42,7 +42,14 @@ class GemmArgs(C.Structure):
 class AttentionArgs(C.Structure):
     _fields_ = [("nseg", C.c_int32), ("seg", Segment * MAX_SEGMENTS), ("M", C.c_int32), ("heads", C.c_int32),
                 ("scale", C.c_float), ("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p),
-                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p)]
+                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("lse", C.c_void_p)]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p), ("o_hi", C.c_void_p), ("o_lo", C.c_void_p),
+                ("dO", C.c_void_p), ("lse", C.c_void_p), ("Dvec", C.c_void_p), ("dqkv", C.c_void_p),
+                ("batch", C.c_int32), ("tokens", C.c_int32), ("row_offset", C.c_int32), ("heads", C.c_int32),
+                ("scale", C.c_float)]
 
 
 class MscamArgs(C.Structure):
@@ -111,6 +118,16 @@ _PROTOTYPES = {
                                      C.c_int32, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_void_p]),
     "dupl_refine_prologue": (C.c_int, [C.POINTER(RefinePrologueArgs), C.c_void_p]),
     "dupl_refine_epilogue": (C.c_int, [C.POINTER(RefineEpilogueArgs), C.c_void_p]),
+    "dupl_split_transpose": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    "dupl_transpose_plane": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dupl_colsum": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
+    "dupl_layernorm_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "dupl_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dupl_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dupl_col2im3x3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p]),
+    "dupl_nchw_to_rows_add": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    "dupl_gmp_classify_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32] * 7 + [C.c_void_p]),
+    "dupl_attention_bwd": (C.c_int, [C.POINTER(AttentionBwdArgs), C.c_void_p]),
     "dupl_seg_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dupl_seg_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]),

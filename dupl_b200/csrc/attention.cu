@@ -50,6 +50,7 @@ struct AttnParamsDev {
   const __nv_bfloat16* q_lo;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  float* lse;  // optional [M, heads]: ln sum_j exp(scale * s_ij), kept for the backward pass
 };
 
 enum {  // mbarrier slots
@@ -321,6 +322,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     }
     const int qrow = (2 * qp + t) * ATT_BQ + r;
     if (qrow < sg.tokens) {
+      if (p.lse != nullptr)
+        p.lse[static_cast<long>(img_row0 + qrow) * p.heads + head] =
+            (m_run * p.scale_log2e + log2f(l_run)) * 0.69314718055994530942f;
       const float inv = 1.0f / l_run;
       const long off = static_cast<long>(img_row0 + qrow) * hd + head * ATT_D;
       __nv_bfloat16* oh = p.out_hi + off;
@@ -385,6 +389,7 @@ extern "C" int dupl_attention_fwd(const dupl_attention_args* a, void* stream) {
   P.q_lo = static_cast<const __nv_bfloat16*>(a->qkv_lo);
   P.out_hi = static_cast<__nv_bfloat16*>(a->out_hi);
   P.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
+  P.lse = a->lse;
   static bool attr_set = false;
   if (!attr_set) {
     DUPL_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));

@@ -250,6 +250,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             }
           } else {
             if (p.epilogue == DUPL_EPI_GELU_SPLIT) {
+              if (G.out_f32 != nullptr) {  // training: keep the pre-activation for the GELU backward
+                float* o = G.out_f32 + static_cast<long>(row) * p.ldo + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
             }

@@ -1,0 +1,653 @@
+// Backward-pass kernels of the training step: everything around the tcgen05 GEMMs that
+// compute dgrad / wgrad (dupl_gemm_bf16x3 on transposed operand planes).
+//   split_transpose   fp32 rows -> split-bf16 planes and/or their transpose (zero-padded contraction dim)
+//   transpose_u16     transpose of one bf16 plane (saved activations / weights -> wgrad / dgrad operands)
+//   colsum            bias gradients
+//   layernorm_bwd     dx accumulated into the residual-stream gradient, dgamma/dbeta via block partials
+//   gelu_bwd, relu_bwd
+//   col2im3x3         gradient of the dilated im2col (gather form, deterministic)
+//   gmp_classify_bwd  global-max-pool + 1x1 classifier
+//   attention backward (attn_bwd_d / attn_bwd_dkv / attn_bwd_dq): fp32 on the CUDA cores from the saved
+//                     split-bf16 Q, K, V, O and the log-sum-exp rows — exact, and the known slow spot of
+//                     the training step (tensor-core version: next round).
+// All reductions have a fixed order: results are bit-reproducible.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dupl {
+
+// ------------------------------------------------------------------------------------------------
+// split + transpose.  src row r (r < R) lives at src + row_map(r) * ld, row_map(r) = r when tokens == 0,
+// else (r / np) * tokens + first + r % np  (skips cls rows).
+// ------------------------------------------------------------------------------------------------
+struct RowMap {
+  int tokens, np, first;
+  __device__ __forceinline__ long operator()(int r) const {
+    return tokens == 0 ? r : static_cast<long>(r / np) * tokens + first + r % np;
+  }
+};
+
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, int R, int Cc, int ld, RowMap map,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                              __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
+                                                              int Rpad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.0f;
+    if (r < R && c < Cc) v = src[map(r) * ld + c];
+    tile[i][threadIdx.x] = v;
+    if (hi != nullptr && r < R && c < Cc) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[static_cast<long>(r) * Cc + c] = h;
+      lo[static_cast<long>(r) * Cc + c] = l;
+    }
+  }
+  __syncthreads();
+  if (t_hi != nullptr) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (c < Cc && r < Rpad) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[threadIdx.x][i], h, l);  // rows >= R were loaded as 0 -> zero padding
+        t_hi[static_cast<long>(c) * Rpad + r] = h;
+        t_lo[static_cast<long>(c) * Rpad + r] = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) transpose_u16_kernel(const unsigned short* __restrict__ in, int R, int Cc, int ld,
+                                                            RowMap map, unsigned short* __restrict__ out, int Rpad) {
+  __shared__ unsigned short tile[32][34];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[map(r) * ld + c] : static_cast<unsigned short>(0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < Rpad) out[static_cast<long>(c) * Rpad + r] = tile[threadIdx.x][i];
+  }
+}
+
+// out[c] = sum_r x[map(r)][c]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int Cc, int ld, RowMap map,
+                                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  float s = 0.0f;
+  for (int r = 0; r < R; ++r) s += x[map(r) * ld + c];
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: y = (x - mean) * rstd * gamma + beta.
+// dres[row] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// partial[blk][0][c] = sum_rows dy * xhat, partial[blk][1][c] = sum_rows dy   (rows of this block)
+// ------------------------------------------------------------------------------------------------
+constexpr int LNB_ROWS = 32;
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, float* __restrict__ dres,
+                                                            float* __restrict__ partial, int rows, float eps) {
+  constexpr int COLS = V * 128;
+  __shared__ float sbuf[8][COLS];  // cross-warp reduction buffer, used twice (dgamma then dbeta partials)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int rr = warp; rr < LNB_ROWS; rr += 8) {
+    const int row = blockIdx.x * LNB_ROWS + rr;
+    if (row >= rows) break;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long>(row) * COLS);
+    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long>(row) * COLS);
+    float4 v[V], d[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = xr[lane + 32 * i];
+      d[i] = dr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / COLS);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / COLS) + eps);
+    float s1 = 0.0f, s2 = 0.0f;  // sum g, sum g * xhat
+    float4 g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+      g[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+      ag[i].x += d[i].x * v[i].x; ag[i].y += d[i].y * v[i].y; ag[i].z += d[i].z * v[i].z; ag[i].w += d[i].w * v[i].w;
+      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * (1.0f / COLS), m2 = s2 * (1.0f / COLS);
+    float4* out = reinterpret_cast<float4*>(dres + static_cast<long>(row) * COLS);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o4 = out[lane + 32 * i];
+      o4.x += rstd * (g[i].x - m1 - v[i].x * m2);
+      o4.y += rstd * (g[i].y - m1 - v[i].y * m2);
+      o4.z += rstd * (g[i].z - m1 - v[i].z * m2);
+      o4.w += rstd * (g[i].w - m1 - v[i].w * m2);
+      out[lane + 32 * i] = o4;
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 t = which == 0 ? ag[i] : ab[i];
+      sbuf[warp][c] = t.x; sbuf[warp][c + 1] = t.y; sbuf[warp][c + 2] = t.z; sbuf[warp][c + 3] = t.w;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < COLS; c += 256) {
+      float a = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += sbuf[w][c];
+      partial[(static_cast<long>(blockIdx.x) * 2 + which) * COLS + c] = a;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int cols,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.0f, b = 0.0f;
+  for (int k = 0; k < nblocks; ++k) {
+    a += partial[(static_cast<long>(k) * 2 + 0) * cols + c];
+    b += partial[(static_cast<long>(k) * 2 + 1) * cols + c];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise backward of the fused activations
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(float* __restrict__ d, const float* __restrict__ pre, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  d[i] *= cdf + x * pdf;
+}
+
+// d *= (act_hi > 0 || act_lo > 0): the saved split planes of relu(y)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(float* __restrict__ d, const __nv_bfloat16* __restrict__ act_hi,
+                                                       const __nv_bfloat16* __restrict__ act_lo, long n) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float a = __bfloat162float(act_hi[i]) + __bfloat162float(act_lo[i]);
+  if (!(a > 0.0f)) d[i] = 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// col2im of the dilated 3x3 im2col: din[row(b,y,x)][c] += sum_tap dcol[(b, y - dy, x - dx)][tap*Cin + c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col2im3x3_kernel(const float* __restrict__ dcol, float* __restrict__ din, int B, int gh,
+                                                        int gw, int Cin, int dil, int ld_in, RowMap map, int accumulate) {
+  const long total = static_cast<long>(B) * gh * gw * Cin;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cin);
+  long t = idx / Cin;
+  const int x = static_cast<int>(t % gw);
+  t /= gw;
+  const int y = static_cast<int>(t % gh);
+  const int b = static_cast<int>(t / gh);
+  float s = 0.0f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    // output position (yo, xo) read input (yo + dy, xo + dx): this input pixel feeds yo = y - dy
+    const int yo = y - (tap / 3 - 1) * dil, xo = x - (tap % 3 - 1) * dil;
+    if (yo >= 0 && yo < gh && xo >= 0 && xo < gw)
+      s += dcol[(static_cast<long>(b) * gh * gw + yo * gw + xo) * (9L * Cin) + tap * Cin + c];
+  }
+  float* o = din + map(static_cast<int>(static_cast<long>(b) * gh * gw + y * gw + x)) * ld_in + c;
+  *o = accumulate ? *o + s : s;
+}
+
+// dst[map(b*np + p)][c] += src[b][c][p]
+__global__ void __launch_bounds__(256) nchw_to_rows_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int np,
+                                                               int Cc, int ld, RowMap map) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < Cc && p < np) ? src[(static_cast<long>(b) * Cc + c) * np + p] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < np && c < Cc) dst[map(b * np + p) * ld + c] += tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// global max pool + classifier backward.  One block per image.
+// dx[row(b, argmax[b][d])][d] += sum_k dlogits[b][k] w[k][d];  dw_partial[b][k][d] = dlogits[b][k] * pooled[b][d]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gmp_classify_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ dlogits, const int* __restrict__ argmax,
+                                                               float* __restrict__ dx, float* __restrict__ dw_partial, int np,
+                                                               int D, int K, int ld, RowMap map) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int p = argmax[static_cast<long>(b) * D + d];
+    const long row = map(b * np + p);
+    const float pooled = x[row * ld + d];
+    float g = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      const float dl = dlogits[b * K + k];
+      g = fmaf(dl, __ldg(w + static_cast<long>(k) * D + d), g);
+      dw_partial[(static_cast<long>(b) * K + k) * D + d] = dl * pooled;
+    }
+    dx[row * ld + d] += g;  // one (row, d) per thread within the image: no race
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_over_first_kernel(const float* __restrict__ in, int n_first, long inner,
+                                                             float* __restrict__ out) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= inner) return;
+  float s = 0.0f;
+  for (int b = 0; b < n_first; ++b) s += in[b * inner + i];
+  out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention backward (fp32, CUDA cores).  Per (image, head): Q,K,V,O [N,64] from split planes,
+// dO fp32 [M, heads*64], lse [M, heads] (natural log of sum_j exp(scale * s_ij)).
+//   D_i   = sum_d dO_id O_id
+//   P_ij  = exp(scale * s_ij - lse_i),  dP_ij = sum_d dO_id V_jd,  dS_ij = scale * P_ij (dP_ij - D_i)
+//   dV_j += sum_i P_ij dO_i,  dK_j += sum_i dS_ij Q_i,  dQ_i += sum_j dS_ij K_j
+// dqkv: fp32 [M, 3*heads*64] (q | k | v like the forward planes).
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  const __nv_bfloat16* qkv_hi;
+  const __nv_bfloat16* qkv_lo;
+  const __nv_bfloat16* o_hi;
+  const __nv_bfloat16* o_lo;
+  const float* dO;
+  const float* lse;
+  float* Dvec;   // [M, heads]
+  float* dqkv;
+  int tokens, row_offset, heads;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) attn_bwd_d_kernel(AttnBwdParams p, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);  // (row, head)
+  if (item >= rows * p.heads) return;
+  const int row = p.row_offset + item / p.heads, h = item % p.heads;
+  const int hd = p.heads * 64;
+  const long o = static_cast<long>(row) * hd + h * 64;
+  float s = 0.0f;
+  for (int d = lane; d < 64; d += 32)
+    s += p.dO[o + d] * (__bfloat162float(p.o_hi[o + d]) + __bfloat162float(p.o_lo[o + d]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) p.Dvec[static_cast<long>(row) * p.heads + h] = s;
+}
+
+constexpr int AB = 64;  // tile edge
+// loads a [64 rows x 64] tile of a split-bf16 matrix (row stride ld) as fp32 into smem, rows >= valid -> 0
+__device__ __forceinline__ void load_tile_split(float (*dst)[AB + 1], const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+                                                long row0, int valid, int ld, int col0) {
+  for (int e = threadIdx.x; e < AB * AB; e += 256) {
+    const int r = e / AB, c = e % AB;
+    float v = 0.0f;
+    if (r < valid) {
+      const long o = (row0 + r) * ld + col0 + c;
+      v = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+    }
+    dst[r][c] = v;
+  }
+}
+__device__ __forceinline__ void load_tile_f32(float (*dst)[AB + 1], const float* src, long row0, int valid, int ld, int col0) {
+  for (int e = threadIdx.x; e < AB * AB; e += 256) {
+    const int r = e / AB, c = e % AB;
+    dst[r][c] = r < valid ? src[(row0 + r) * ld + col0 + c] : 0.0f;
+  }
+}
+// acc[i][j] += sum_k A[ty*4+i][k] * B[tx*4+j][k]      (A, B row-major tiles, "NT")
+__device__ __forceinline__ void mm_nt(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
+#pragma unroll 8
+  for (int k = 0; k < AB; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[ty * 4 + i][k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = B[tx * 4 + j][k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+// acc[i][j] += sum_k A[k][ty*4+i] * B[k][tx*4+j]      ("TN": contraction over tile rows)
+__device__ __forceinline__ void mm_tn(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
+#pragma unroll 8
+  for (int k = 0; k < AB; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[k][ty * 4 + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = B[k][tx * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+// acc[i][j] += sum_k A[ty*4+i][k] * B[k][tx*4+j]      ("NN")
+__device__ __forceinline__ void mm_nn(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
+#pragma unroll 8
+  for (int k = 0; k < AB; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[ty * 4 + i][k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = B[k][tx * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// Computes, for query tile i and key tile j (already in smem), P into sP and dS into sS (both [q][key]).
+__device__ __forceinline__ void attn_tile_p_ds(float (*sQ)[AB + 1], float (*sK)[AB + 1], float (*sV)[AB + 1],
+                                               float (*sdO)[AB + 1], float (*sP)[AB + 1], float (*sS)[AB + 1],
+                                               const float* s_lse, const float* s_D, int q_valid, int k_valid, float scale,
+                                               int ty, int tx) {
+  float s[4][4], dp[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.0f;
+  mm_nt(s, sQ, sK, ty, tx);     // S = Q K^T
+  mm_nt(dp, sdO, sV, ty, tx);   // dP = dO V^T
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = tx * 4 + j;
+      float pv = 0.0f, ds = 0.0f;
+      if (q < q_valid && k < k_valid) {
+        pv = expf(s[i][j] * scale - s_lse[q]);
+        ds = scale * pv * (dp[i][j] - s_D[q]);
+      }
+      sP[q][k] = pv;
+      sS[q][k] = ds;
+    }
+  }
+}
+
+constexpr int ATTN_BWD_SMEM = (6 * AB * (AB + 1) + 2 * AB) * sizeof(float);
+
+// grid (kv tiles, heads, images): dK_j, dV_j
+__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnBwdParams p) {
+  extern __shared__ float smf[];
+  float (*sQ)[AB + 1] = reinterpret_cast<float (*)[AB + 1]>(smf);
+  float (*sK)[AB + 1] = sQ + AB;
+  float (*sV)[AB + 1] = sK + AB;
+  float (*sdO)[AB + 1] = sV + AB;
+  float (*sP)[AB + 1] = sdO + AB;
+  float (*sS)[AB + 1] = sP + AB;
+  float* s_lse = reinterpret_cast<float*>(sS + AB);
+  float* s_D = s_lse + AB;
+  const int j = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int hd = p.heads * 64, ld3 = 3 * hd;
+  const long row0 = p.row_offset + static_cast<long>(img) * p.tokens;
+  const int k_valid = min(AB, p.tokens - j * AB);
+  load_tile_split(sK, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, hd + h * 64);
+  load_tile_split(sV, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, 2 * hd + h * 64);
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dk[a][b] = dv[a][b] = 0.0f;
+  const int q_tiles = (p.tokens + AB - 1) / AB;
+  for (int i = 0; i < q_tiles; ++i) {
+    const int q_valid = min(AB, p.tokens - i * AB);
+    __syncthreads();
+    load_tile_split(sQ, p.qkv_hi, p.qkv_lo, row0 + i * AB, q_valid, ld3, h * 64);
+    load_tile_f32(sdO, p.dO, row0 + i * AB, q_valid, hd, h * 64);
+    if (threadIdx.x < AB) {
+      const int q = threadIdx.x;
+      const long r = row0 + i * AB + q;
+      s_lse[q] = q < q_valid ? p.lse[r * p.heads + h] : 0.0f;
+      s_D[q] = q < q_valid ? p.Dvec[r * p.heads + h] : 0.0f;
+    }
+    __syncthreads();
+    attn_tile_p_ds(sQ, sK, sV, sdO, sP, sS, s_lse, s_D, q_valid, k_valid, p.scale, ty, tx);
+    __syncthreads();
+    mm_tn(dv, sP, sdO, ty, tx);  // dV[key][d] += sum_q P[q][key] dO[q][d]
+    mm_tn(dk, sS, sQ, ty, tx);   // dK[key][d] += sum_q dS[q][key] Q[q][d]
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int key = ty * 4 + a;
+    if (key >= k_valid) continue;
+    const long r = row0 + j * AB + key;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      p.dqkv[r * ld3 + hd + h * 64 + tx * 4 + b] = dk[a][b];
+      p.dqkv[r * ld3 + 2 * hd + h * 64 + tx * 4 + b] = dv[a][b];
+    }
+  }
+}
+
+// grid (q tiles, heads, images): dQ_i
+__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnBwdParams p) {
+  extern __shared__ float smf[];
+  float (*sQ)[AB + 1] = reinterpret_cast<float (*)[AB + 1]>(smf);
+  float (*sK)[AB + 1] = sQ + AB;
+  float (*sV)[AB + 1] = sK + AB;
+  float (*sdO)[AB + 1] = sV + AB;
+  float (*sP)[AB + 1] = sdO + AB;
+  float (*sS)[AB + 1] = sP + AB;
+  float* s_lse = reinterpret_cast<float*>(sS + AB);
+  float* s_D = s_lse + AB;
+  const int i = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int hd = p.heads * 64, ld3 = 3 * hd;
+  const long row0 = p.row_offset + static_cast<long>(img) * p.tokens;
+  const int q_valid = min(AB, p.tokens - i * AB);
+  load_tile_split(sQ, p.qkv_hi, p.qkv_lo, row0 + i * AB, q_valid, ld3, h * 64);
+  load_tile_f32(sdO, p.dO, row0 + i * AB, q_valid, hd, h * 64);
+  if (threadIdx.x < AB) {
+    const int q = threadIdx.x;
+    const long r = row0 + i * AB + q;
+    s_lse[q] = q < q_valid ? p.lse[r * p.heads + h] : 0.0f;
+    s_D[q] = q < q_valid ? p.Dvec[r * p.heads + h] : 0.0f;
+  }
+  float dq[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dq[a][b] = 0.0f;
+  const int k_tiles = (p.tokens + AB - 1) / AB;
+  for (int j = 0; j < k_tiles; ++j) {
+    const int k_valid = min(AB, p.tokens - j * AB);
+    __syncthreads();
+    load_tile_split(sK, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, hd + h * 64);
+    load_tile_split(sV, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, 2 * hd + h * 64);
+    __syncthreads();
+    attn_tile_p_ds(sQ, sK, sV, sdO, sP, sS, s_lse, s_D, q_valid, k_valid, p.scale, ty, tx);
+    __syncthreads();
+    mm_nn(dq, sS, sK, ty, tx);  // dQ[q][d] += sum_key dS[q][key] K[key][d]
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int q = ty * 4 + a;
+    if (q >= q_valid) continue;
+    const long r = row0 + i * AB + q;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) p.dqkv[r * ld3 + h * 64 + tx * 4 + b] = dq[a][b];
+  }
+}
+
+static RowMap make_map(int tokens, int np, int first) {
+  RowMap m;
+  m.tokens = tokens; m.np = np > 0 ? np : 1; m.first = first;
+  return m;
+}
+
+}  // namespace dupl
+
+using namespace dupl;
+
+extern "C" int dupl_split_transpose(const float* src, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np,
+                                    int32_t first, void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, void* stream) {
+  DUPL_CHECK_ARG(src && R > 0 && Cc > 0 && ld >= Cc, "dupl_split_transpose: bad arguments");
+  DUPL_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (t_hi == nullptr) == (t_lo == nullptr) && (hi || t_hi),
+                 "dupl_split_transpose: planes must come in hi/lo pairs");
+  DUPL_CHECK_ARG(t_hi == nullptr || Rpad >= R, "dupl_split_transpose: Rpad=%d < R=%d", Rpad, R);
+  const int rows = t_hi ? Rpad : R;
+  dim3 grid(cdiv(rows, 32), cdiv(Cc, 32)), block(32, 8);
+  split_transpose_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, R, Cc, ld, make_map(tokens, np, first), static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo),
+      static_cast<__nv_bfloat16*>(t_hi), static_cast<__nv_bfloat16*>(t_lo), Rpad);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_transpose_plane(const void* in, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np,
+                                    int32_t first, void* out, int32_t Rpad, void* stream) {
+  DUPL_CHECK_ARG(in && out && R > 0 && Cc > 0 && ld >= Cc && Rpad >= R, "dupl_transpose_plane: bad arguments");
+  dim3 grid(cdiv(Rpad, 32), cdiv(Cc, 32)), block(32, 8);
+  transpose_u16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned short*>(in), R, Cc, ld, make_map(tokens, np, first), static_cast<unsigned short*>(out), Rpad);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
+                           float* out, void* stream) {
+  DUPL_CHECK_ARG(x && out && R > 0 && Cc > 0, "dupl_colsum: bad arguments");
+  colsum_kernel<<<cdiv(Cc, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, Cc, ld, make_map(tokens, np, first), out);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dres, float* partial,
+                                  float* dgamma, float* dbeta, int32_t rows, int32_t cols, float eps, void* stream) {
+  DUPL_CHECK_ARG(dy && x && gamma && dres && partial && dgamma && dbeta, "dupl_layernorm_bwd: NULL pointer");
+  DUPL_CHECK_ARG(rows > 0 && cols == 768, "dupl_layernorm_bwd: rows=%d cols=%d (768 columns are built)", rows, cols);
+  const int nb = cdiv(rows, LNB_ROWS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  layernorm_bwd_kernel<6><<<nb, 256, 0, st>>>(dy, x, gamma, dres, partial, rows, eps);
+  DUPL_LAUNCH_OK();
+  layernorm_bwd_finish_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, nb, cols, dgamma, dbeta);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_gelu_bwd(float* d, const float* pre, int64_t n, void* stream) {
+  DUPL_CHECK_ARG(d && pre && n > 0, "dupl_gelu_bwd: bad arguments");
+  gelu_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, pre, n);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_relu_bwd(float* d, const void* act_hi, const void* act_lo, int64_t n, void* stream) {
+  DUPL_CHECK_ARG(d && act_hi && act_lo && n > 0, "dupl_relu_bwd: bad arguments");
+  relu_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d, static_cast<const __nv_bfloat16*>(act_hi), static_cast<const __nv_bfloat16*>(act_lo), n);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_col2im3x3(const float* dcol, float* din, int32_t B, int32_t gh, int32_t gw, int32_t Cin, int32_t dilation,
+                              int32_t ld_in, int32_t tokens, int32_t first, int32_t accumulate, void* stream) {
+  DUPL_CHECK_ARG(dcol && din && B > 0 && gh > 0 && gw > 0 && Cin > 0, "dupl_col2im3x3: bad arguments");
+  const long total = static_cast<long>(B) * gh * gw * Cin;
+  col2im3x3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dcol, din, B, gh, gw, Cin, dilation, ld_in, make_map(tokens, gh * gw, first), accumulate);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_nchw_to_rows_add(const float* src, float* dst, int32_t B, int32_t np, int32_t Cc, int32_t ld,
+                                     int32_t tokens, int32_t first, void* stream) {
+  DUPL_CHECK_ARG(src && dst && B > 0 && np > 0 && Cc > 0, "dupl_nchw_to_rows_add: bad arguments");
+  dim3 grid(cdiv(np, 32), cdiv(Cc, 32), B), block(32, 8);
+  nchw_to_rows_add_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, np, Cc, ld, make_map(tokens, np, first));
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_gmp_classify_bwd(const float* x, const float* w, const float* dlogits, const int32_t* argmax, float* dx,
+                                     float* dw_partial, float* dw, int32_t B, int32_t np, int32_t D, int32_t K, int32_t ld,
+                                     int32_t tokens, int32_t first, void* stream) {
+  DUPL_CHECK_ARG(x && w && dlogits && argmax && dx && dw_partial && dw, "dupl_gmp_classify_bwd: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gmp_classify_bwd_kernel<<<B, 256, 0, st>>>(x, w, dlogits, argmax, dx, dw_partial, np, D, K, ld, make_map(tokens, np, first));
+  DUPL_LAUNCH_OK();
+  const long inner = static_cast<long>(K) * D;
+  sum_over_first_kernel<<<static_cast<int>((inner + 255) / 256), 256, 0, st>>>(dw_partial, B, inner, dw);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_attention_bwd(const dupl_attention_bwd_args* a, void* stream) {
+  DUPL_CHECK_ARG(a != nullptr, "dupl_attention_bwd: args is NULL");
+  DUPL_CHECK_ARG(a->qkv_hi && a->qkv_lo && a->o_hi && a->o_lo && a->dO && a->lse && a->Dvec && a->dqkv,
+                 "dupl_attention_bwd: NULL pointer");
+  DUPL_CHECK_ARG(a->batch > 0 && a->tokens > 0 && a->heads > 0, "dupl_attention_bwd: bad shape");
+  AttnBwdParams p;
+  p.qkv_hi = static_cast<const __nv_bfloat16*>(a->qkv_hi);
+  p.qkv_lo = static_cast<const __nv_bfloat16*>(a->qkv_lo);
+  p.o_hi = static_cast<const __nv_bfloat16*>(a->o_hi);
+  p.o_lo = static_cast<const __nv_bfloat16*>(a->o_lo);
+  p.dO = a->dO; p.lse = a->lse; p.Dvec = a->Dvec; p.dqkv = a->dqkv;
+  p.tokens = a->tokens; p.row_offset = a->row_offset; p.heads = a->heads; p.scale = a->scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
+    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
+    attr_set = true;
+  }
+  const int rows = a->batch * a->tokens;
+  attn_bwd_d_kernel<<<cdiv(rows * a->heads, 8), 256, 0, st>>>(p, rows);
+  DUPL_LAUNCH_OK();
+  dim3 grid(cdiv(a->tokens, AB), a->heads, a->batch);
+  attn_bwd_dkv_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(p);
+  DUPL_LAUNCH_OK();
+  attn_bwd_dq_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(p);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}

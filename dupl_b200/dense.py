@@ -1,9 +1,9 @@
 """Decoder + classification heads on top of the encoder (reference: model/model_dupl.py:86-106,
 model/decoder/conv_head.py:33-41): the non-`cam_only` outputs `(cls_x4, seg, _x4, cls_aux)`.
 
-Inference (no-grad) execution only for now: every op is a libdupl.so kernel.  Calling the model in
-training mode with gradients enabled raises — the backward kernels of the training step are not built
-yet; there is deliberately no PyTorch fallback.
+No-grad calls run the inference kernels below; with gradients enabled the call is routed to
+dupl_b200.train (one autograd.Function per student with CUDA forward and backward).  There is no
+PyTorch fallback on either path.
 """
 import torch
 
@@ -39,17 +39,30 @@ class DecoderPlanes:
         return hit[1]
 
 
+def _get_t(self, name):
+    """Transposed implicit-GEMM weight planes [9*Cin, Cout] (B operand of the conv dgrad GEMM)."""
+    conv = getattr(self.net.decoder, name)
+    p = conv.weight
+    key = (p.data_ptr(), p._version)
+    hit = self._cache.get(name + "^T")
+    if hit is None or hit[0] != key:
+        w = self.get(name)
+        hit = (key, E.transpose_planes(w, w[0].shape[0], w[0].shape[1]))
+        self._cache[name + "^T"] = hit
+    return hit[1]
+
+
+DecoderPlanes.get_t = _get_t
+
+
 def _decoder_planes(net):
     if getattr(net, "_dec_planes", None) is None:
         net._dec_planes = DecoderPlanes(net)
     return net._dec_planes
 
 
-def _require_no_grad(nets):
-    if torch.is_grad_enabled() and any(p.requires_grad for n in nets for p in n.parameters()):
-        raise NotImplementedError(
-            "dupl_b200: the training-mode forward/backward (autograd) of siamese_network is not built yet — only the "
-            "no-grad paths (cam_only, val, torch.no_grad()) run on the CUDA kernels. There is no PyTorch fallback.")
+def _wants_grad(nets):
+    return torch.is_grad_enabled() and any(p.requires_grad for n in nets for p in n.parameters())
 
 
 @torch.no_grad()
@@ -110,18 +123,29 @@ def _heads(nets, x, aux_seg_only=False):
 def network_forward(net, x, val=False, cam_with_grad=False):
     if cam_with_grad:
         raise NotImplementedError("cam_with_grad is never used by the reference scripts (model_dupl.py:100-104)")
-    _require_no_grad([net])
+    if _wants_grad([net]):
+        from . import train
+        return train.student_forward(net, x)
     return _heads([net], x)[0]
 
 
 def pair_forward(net1, net2, x, val=False, cam_with_grad=False):
     if cam_with_grad:
         raise NotImplementedError("cam_with_grad is never used by the reference scripts (model_dupl.py:100-104)")
-    _require_no_grad([net1, net2])
+    if _wants_grad([net1, net2]):
+        from . import train
+        return train.student_forward(net1, x), train.student_forward(net2, x)
     r1, r2 = _heads([net1, net2], x)
     return r1, r2
 
 
 def pair_forward_aug(net1, net2, x_aug, scale=0.75):
-    """seg logits of the strongly-augmented view at `scale` (model_dupl.py:195-205)."""
-    raise NotImplementedError("need_sp=True belongs to the training step, which is not built yet (DESIGN.md §1)")
+    """seg logits of the strongly-augmented view resized by `scale` (model_dupl.py:195-205: F.interpolate with
+    scale_factor=0.75, bilinear, then both students; only the seg output reaches the caller)."""
+    from . import train
+    H, W = x_aug.shape[-2:]
+    size = (int(H * scale), int(W * scale))
+    if _wants_grad([net1, net2]):
+        return train.student_forward(net1, x_aug, size)[1], train.student_forward(net2, x_aug, size)[1]
+    with torch.no_grad():
+        return train._forward(net1, x_aug, size)[0][1], train._forward(net2, x_aug, size)[0][1]

@@ -16,6 +16,18 @@ DEPTH = 12
 LN_EPS = 1e-6  # deit.py:100
 
 
+def transpose_planes(planes, R, Cc):
+    """(hi, lo) [R, Cc] bf16 -> (hi^T, lo^T) [Cc, pad64(R)] (zero padded): pure data movement."""
+    Rpad = (R + 63) // 64 * 64
+    out = []
+    for p in planes:
+        o = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=p.device)
+        L.check(L.lib().dupl_transpose_plane(L.ptr(p), R, Cc, p.shape[1], 0, 0, 0, L.ptr(o), Rpad, L.stream_ptr(p.device)),
+                "dupl_transpose_plane")
+        out.append(o)
+    return tuple(out)
+
+
 class StudentPlanes:
     """split-bf16 planes of one student's encoder weights, refreshed lazily when a parameter changes
     (torch bumps `_version` on every in-place update, e.g. by the optimizer)."""
@@ -45,6 +57,16 @@ class StudentPlanes:
             w = p.detach().reshape(p.shape[0], -1)
             hit = (key, ops.split_bf16(w))
             self._planes[name] = hit
+        return hit[1]
+
+    def plane_t(self, name):
+        """Transposed planes [K, N] of a Linear weight [N, K] (B operand of the dgrad GEMM), cached like plane()."""
+        p = self._params()[name]
+        key = (p.data_ptr(), p._version)
+        hit = self._planes.get(name + "^T")
+        if hit is None or hit[0] != key:
+            hit = (key, transpose_planes(self.plane(name), p.shape[0], p[0].numel()))
+            self._planes[name + "^T"] = hit
         return hit[1]
 
     def vec(self, name):

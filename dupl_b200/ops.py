@@ -96,7 +96,7 @@ def gmp_classify(x, w, B, np_, row_offset, row_stride, first, want_argmax=False)
     return (logits, arg) if want_argmax else logits
 
 
-def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale):
+def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale, lse=None):
     a = L.AttentionArgs()
     a.nseg = len(segs)
     for i, s in enumerate(segs):
@@ -104,6 +104,7 @@ def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale):
     a.M, a.heads, a.scale = qkv_hi.shape[0], heads, scale
     a.qkv_hi, a.qkv_lo = qkv_hi.data_ptr(), qkv_lo.data_ptr()
     a.out_hi, a.out_lo = out_hi.data_ptr(), out_lo.data_ptr()
+    a.lse = lse.data_ptr() if lse is not None else None
     L.check(L.lib().dupl_attention_fwd(C.byref(a), L.stream_ptr(qkv_hi.device)), "dupl_attention_fwd")
 
 

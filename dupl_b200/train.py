@@ -1,0 +1,321 @@
+"""Training-mode forward + backward of one student (`network.forward`, model/model_dupl.py:69-106 and
+everything below it: vit.py:289-326, conv_head.py:33-41) as ONE torch.autograd.Function.
+
+The Function takes the student's parameters as inputs and returns (cls_x4, seg, _x4, cls_aux); its
+backward returns one gradient per parameter, so the reference script's `loss.backward()` and
+DistributedDataParallel's reducer hooks work unchanged (unused `head.*` parameters stay unused, as in the
+reference).  Every arithmetic step is a libdupl.so kernel: tcgen05 split-bf16 GEMMs for all forward,
+dgrad and wgrad contractions, plus the HBM-bound kernels of train_kernels.cu.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import encoder as E
+from . import ops
+from .dense import DECODER_DIL, _decoder_planes
+
+D = E.EMBED
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+# ------------------------------------------------------------------ thin wrappers of the backward kernels
+def _st(dev):
+    return L.stream_ptr(dev)
+
+
+def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0):
+    dev = src.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    Rpad = _pad64(R)
+    hi = lo = thi = tlo = None
+    if want_planes:
+        hi, lo = torch.empty(R, Cc, **bf), torch.empty(R, Cc, **bf)
+    if want_t:
+        thi, tlo = torch.empty(Cc, Rpad, **bf), torch.empty(Cc, Rpad, **bf)
+    L.check(L.lib().dupl_split_transpose(L.ptr(src), R, Cc, src.shape[1], tokens, np_, first, L.ptr(hi), L.ptr(lo),
+                                         L.ptr(thi), L.ptr(tlo), Rpad, _st(dev)), "dupl_split_transpose")
+    return (hi, lo), (thi, tlo)
+
+
+def transpose_planes(planes, R, Cc, tokens=0, np_=0, first=0):
+    """(hi, lo) [*, Cc] -> (hi^T, lo^T) [Cc, pad64(R)]"""
+    dev = planes[0].device
+    Rpad = _pad64(R)
+    out = []
+    for p in planes:
+        o = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=dev)
+        L.check(L.lib().dupl_transpose_plane(L.ptr(p), R, Cc, p.shape[1], tokens, np_, first, L.ptr(o), Rpad, _st(dev)),
+                "dupl_transpose_plane")
+        out.append(o)
+    return tuple(out)
+
+
+def colsum(x, R, Cc, tokens=0, np_=0, first=0):
+    out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dupl_colsum(L.ptr(x), R, Cc, x.shape[1], tokens, np_, first, L.ptr(out), _st(x.device)), "dupl_colsum")
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, dres):
+    rows, cols = x.shape
+    dev = x.device
+    partial = torch.empty(2 * cols * ((rows + 31) // 32), dtype=torch.float32, device=dev)
+    dg, db = torch.empty(cols, dtype=torch.float32, device=dev), torch.empty(cols, dtype=torch.float32, device=dev)
+    L.check(L.lib().dupl_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(dres), L.ptr(partial), L.ptr(dg), L.ptr(db),
+                                       rows, cols, E.LN_EPS, _st(dev)), "dupl_layernorm_bwd")
+    return dg, db
+
+
+def dgrad(dy_planes, wt_planes, M, n_out, k_contr):
+    """dX[M, n_out] = dY[M, k_contr] @ W, with W^T given as planes [n_out, k_contr]."""
+    out = torch.empty(M, n_out, dtype=torch.float32, device=dy_planes[0].device)
+    ops.gemm_bf16x3([dict(a=dy_planes, w=wt_planes, out_f32=out)], M, n_out, k_contr, L.EPI_F32)
+    return out
+
+
+def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr):
+    """dW[n_rows, n_cols] = dY^T @ X, operands as transposed planes [n_rows, k_contr], [n_cols, k_contr]."""
+    out = torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt_planes[0].device)
+    ops.gemm_bf16x3([dict(a=dyt_planes, w=xt_planes, out_f32=out)], n_rows, n_cols, k_contr, L.EPI_F32)
+    return out
+
+
+class _Saved:
+    pass
+
+
+# ------------------------------------------------------------------ forward with saved activations
+def _forward(net, x, size=None):
+    """size: (hs, ws) to resize the input to first (bilinear, align_corners=False) — the 0.75x view of need_sp."""
+    L.require_cuda(x)
+    x = L.f32c(x)
+    B, _, H, W = x.shape
+    hs, ws = size if size is not None else (H, W)
+    pl = net.planes()
+    dp = _decoder_planes(net)
+    segs, M, Mp = ops.make_segments([(B, hs // 16, ws // 16)])
+    sg = segs[0]
+    gh, gw, np_, N = sg.gh, sg.gw, sg.gh * sg.gw, sg.tokens
+    dev = x.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    S = _Saved()
+    S.B, S.gh, S.gw, S.np, S.N, S.M, S.Mp, S.sg = B, gh, gw, np_, N, M, Mp, sg
+
+    S.patch = (torch.empty(Mp, D, **bf), torch.empty(Mp, D, **bf))
+    ops.patchify(x, sg, (hs, ws), False, *S.patch)
+    pos = [pl.pos(gh, gw)]
+    tok = torch.empty(M, D, **f32)
+    ops.gemm_bf16x3([dict(a=S.patch, w=pl.plane("patch_embed.proj.weight"), bias=pl.vec("patch_embed.proj.bias"),
+                          out_f32=tok, pos=pos)], Mp, D, D, L.EPI_PATCH, segs=segs)
+    ops.cls_rows(tok, pl.vec("cls_token").reshape(-1), pos, segs)
+
+    scale = (D // E.HEADS) ** -0.5
+    S.blocks = []
+    aux_idx = net.encoder.aux_block_index()
+    for i in range(E.DEPTH):
+        bp = f"blocks.{i}."
+        b = _Saved()
+        b.x_in = tok
+        b.xn1 = (torch.empty(M, D, **bf), torch.empty(M, D, **bf))
+        ops.layernorm_split(tok, pl.vec(bp + "norm1.weight"), pl.vec(bp + "norm1.bias"), *b.xn1, eps=E.LN_EPS)
+        b.qkv = (torch.empty(M, 3 * D, **bf), torch.empty(M, 3 * D, **bf))
+        ops.gemm_bf16x3([dict(a=b.xn1, w=pl.plane(bp + "attn.qkv.weight"), bias=pl.vec(bp + "attn.qkv.bias"), out=b.qkv)],
+                        M, 3 * D, D, L.EPI_SPLIT)
+        b.att = (torch.empty(M, D, **bf), torch.empty(M, D, **bf))
+        b.lse = torch.empty(M, E.HEADS, **f32)
+        ops.attention_fwd(b.qkv[0], b.qkv[1], b.att[0], b.att[1], segs, E.HEADS, scale, lse=b.lse)
+        b.x_mid = torch.empty(M, D, **f32)
+        ops.gemm_bf16x3([dict(a=b.att, w=pl.plane(bp + "attn.proj.weight"), bias=pl.vec(bp + "attn.proj.bias"),
+                              resid=tok, out_f32=b.x_mid)], M, D, D, L.EPI_RESID)
+        b.xn2 = (torch.empty(M, D, **bf), torch.empty(M, D, **bf))
+        ops.layernorm_split(b.x_mid, pl.vec(bp + "norm2.weight"), pl.vec(bp + "norm2.bias"), *b.xn2, eps=E.LN_EPS)
+        b.hid = (torch.empty(M, 4 * D, **bf), torch.empty(M, 4 * D, **bf))
+        b.h_pre = torch.empty(M, 4 * D, **f32)
+        ops.gemm_bf16x3([dict(a=b.xn2, w=pl.plane(bp + "mlp.fc1.weight"), bias=pl.vec(bp + "mlp.fc1.bias"), out=b.hid,
+                              out_f32=b.h_pre)], M, 4 * D, D, L.EPI_GELU_SPLIT, ldo=4 * D)
+        tok = torch.empty(M, D, **f32)
+        ops.gemm_bf16x3([dict(a=b.hid, w=pl.plane(bp + "mlp.fc2.weight"), bias=pl.vec(bp + "mlp.fc2.bias"),
+                              resid=b.x_mid, out_f32=tok)], M, D, 4 * D, L.EPI_RESID)
+        S.blocks.append(b)
+    S.tok_final = tok
+    S.aux_is_final = aux_idx == E.DEPTH - 1
+    S.aux_idx = aux_idx
+
+    # final norm, heads
+    S.xn_planes = (torch.empty(M, D, **bf), torch.empty(M, D, **bf))
+    S.xn = torch.empty(M, D, **f32)
+    ops.layernorm_split(tok, pl.vec("norm.weight"), pl.vec("norm.bias"), *S.xn_planes, eps=E.LN_EPS, out_f32=S.xn)
+    S.col6 = ops.im2col3x3(S.xn_planes[0], S.xn_planes[1], B, gh, gw, DECODER_DIL, 0, N, 1)
+    S.h6 = (torch.empty(Mp, 512, **bf), torch.empty(Mp, 512, **bf))
+    ops.gemm_bf16x3([dict(a=S.col6, w=dp.get("conv6"), out=S.h6)], Mp, 512, 9 * D, L.EPI_RELU_SPLIT)
+    S.col7 = ops.im2col3x3(S.h6[0], S.h6[1], B, gh, gw, DECODER_DIL, 0, np_, 0)
+    S.h7 = (torch.empty(Mp, 512, **bf), torch.empty(Mp, 512, **bf))
+    ops.gemm_bf16x3([dict(a=S.col7, w=dp.get("conv7"), out=S.h7)], Mp, 512, 9 * 512, L.EPI_RELU_SPLIT)
+    w8 = dp.get("conv8")
+    S.n8 = w8[0].shape[0]
+    seg_rows = torch.empty(Mp, S.n8, **f32)
+    ops.gemm_bf16x3([dict(a=S.h7, w=w8, out_f32=seg_rows)], Mp, S.n8, 512, L.EPI_F32)
+    seg = ops.rows_to_nchw(seg_rows, B, gh, gw, net.num_classes, 0, np_, 0)
+    x4 = ops.rows_to_nchw(S.xn, B, gh, gw, D, 0, N, 1)
+    K = net.num_classes - 1
+    S.wc = L.f32c(net.classifier.weight.detach().reshape(K, -1))
+    S.wa = L.f32c(net.aux_classifier.weight.detach().reshape(K, -1))
+    cls_x4, S.arg_c = ops.gmp_classify(S.xn, S.wc, B, np_, 0, N, 1, want_argmax=True)
+    S.aux_src = S.xn if S.aux_is_final else S.blocks[aux_idx + 1].x_in  # output of block aux_idx (un-normed)
+    cls_aux, S.arg_a = ops.gmp_classify(S.aux_src, S.wa, B, np_, 0, N, 1, want_argmax=True)
+    return (cls_x4, seg, x4, cls_aux), S
+
+
+# ------------------------------------------------------------------ backward
+def _gmp_bwd(x_rows, w, dlogits, argmax, dx, S):
+    B, K = dlogits.shape
+    dev = dx.device
+    dwp = torch.empty(B, K, D, dtype=torch.float32, device=dev)
+    dw = torch.empty(K, D, dtype=torch.float32, device=dev)
+    L.check(L.lib().dupl_gmp_classify_bwd(L.ptr(x_rows), L.ptr(w), L.ptr(L.f32c(dlogits)), L.ptr(argmax), L.ptr(dx), L.ptr(dwp),
+                                          L.ptr(dw), B, S.np, D, K, D, S.N, 1, _st(dev)), "dupl_gmp_classify_bwd")
+    return dw
+
+
+def _conv_bwd(d_out, act_planes, col_planes, wmat_t, S, cin, d_in, in_tokens, in_first, accumulate):
+    """Backward of relu(conv3x3_d5(in)): d_out fp32 [Mp, 512] (grad wrt the relu output) ->
+    d_in (+)=, returns dWmat [512, 9*cin]."""
+    dev = d_out.device
+    Mp = S.Mp
+    L.check(L.lib().dupl_relu_bwd(L.ptr(d_out), L.ptr(act_planes[0]), L.ptr(act_planes[1]), d_out.numel(), _st(dev)), "dupl_relu_bwd")
+    dpl, dt = split_transpose(d_out, Mp, 512)
+    dcol = dgrad(dpl, wmat_t, Mp, 9 * cin, 512)
+    L.check(L.lib().dupl_col2im3x3(L.ptr(dcol), L.ptr(d_in), S.B, S.gh, S.gw, cin, DECODER_DIL, d_in.shape[1], in_tokens, in_first,
+                                   1 if accumulate else 0, _st(dev)), "dupl_col2im3x3")
+    col_t = transpose_planes(col_planes, Mp, 9 * cin)
+    return wgrad(dt, col_t, 512, 9 * cin, _pad64(Mp))
+
+
+def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
+    pl = net.planes()
+    dp = _decoder_planes(net)
+    dev = S.xn.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    M, Mp, N, B, np_ = S.M, S.Mp, S.N, S.B, S.np
+    Mpad = _pad64(M)
+    grads = {}
+    K = net.num_classes - 1
+
+    d_xn = torch.zeros(M, D, **f32)          # grad wrt the final-normed tokens
+    if g_x4 is not None:
+        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_x4)), L.ptr(d_xn), B, np_, D, D, N, 1, _st(dev)), "dupl_nchw_to_rows_add")
+    if g_cls is not None:
+        grads["classifier.weight"] = _gmp_bwd(S.xn, S.wc, g_cls, S.arg_c, d_xn, S).reshape(K, D, 1, 1)
+    if g_aux is not None and S.aux_is_final:
+        grads["aux_classifier.weight"] = _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_xn, S).reshape(K, D, 1, 1)
+    if g_seg is not None:
+        # conv8 (1x1): seg_rows = h7 @ W8^T
+        Cn = net.num_classes
+        d_seg_rows = torch.zeros(Mp, 64, **f32)  # contraction dim of the dgrad padded to 64
+        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_seg)), L.ptr(d_seg_rows), B, np_, Cn, 64, 0, 0, _st(dev)), "dupl_nchw_to_rows_add")
+        dsp, dst = split_transpose(d_seg_rows, Mp, 64)
+        w8 = dp.get("conv8")
+        w8t = transpose_planes(w8, S.n8, 512)                       # [512, 64]
+        d_h7 = dgrad(dsp, w8t, Mp, 512, 64)
+        h7t = transpose_planes(S.h7, Mp, 512)
+        dw8 = wgrad(dst, h7t, 64, 512, _pad64(Mp))
+        grads["decoder.conv8.weight"] = dw8[:Cn].reshape(Cn, 512, 1, 1).contiguous()
+        # conv7 + relu, conv6 + relu
+        d_h6 = torch.empty(Mp, 512, **f32)
+        dw7 = _conv_bwd(d_h7, S.h7, S.col7, dp.get_t("conv7"), S, 512, d_h6, 0, 0, False)
+        grads["decoder.conv7.weight"] = dw7.reshape(512, 3, 3, 512).permute(0, 3, 1, 2).contiguous()
+        dw6 = _conv_bwd(d_h6, S.h6, S.col6, dp.get_t("conv6"), S, D, d_xn, N, 1, True)
+        grads["decoder.conv6.weight"] = dw6.reshape(512, 3, 3, D).permute(0, 3, 1, 2).contiguous()
+
+    # final LayerNorm
+    d_tok = torch.zeros(M, D, **f32)
+    dg, db = layernorm_bwd(d_xn, S.tok_final, pl.vec("norm.weight"), d_tok)
+    grads["encoder.norm.weight"], grads["encoder.norm.bias"] = dg, db
+
+    scale = (D // E.HEADS) ** -0.5
+    for i in reversed(range(E.DEPTH)):
+        bp = f"blocks.{i}."
+        b = S.blocks[i]
+        if g_aux is not None and not S.aux_is_final and i == S.aux_idx:
+            # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
+            grads["aux_classifier.weight"] = _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_tok, S).reshape(K, D, 1, 1)
+        # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+        dpl, dt = split_transpose(d_tok, M, D)
+        grads["encoder." + bp + "mlp.fc2.bias"] = colsum(d_tok, M, D)
+        grads["encoder." + bp + "mlp.fc2.weight"] = wgrad(dt, transpose_planes(b.hid, M, 4 * D), D, 4 * D, Mpad)
+        d_hid = dgrad(dpl, pl.plane_t(bp + "mlp.fc2.weight"), M, 4 * D, D)
+        L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid), L.ptr(b.h_pre), d_hid.numel(), _st(dev)), "dupl_gelu_bwd")
+        dpl, dt = split_transpose(d_hid, M, 4 * D)
+        grads["encoder." + bp + "mlp.fc1.bias"] = colsum(d_hid, M, 4 * D)
+        grads["encoder." + bp + "mlp.fc1.weight"] = wgrad(dt, transpose_planes(b.xn2, M, D), 4 * D, D, Mpad)
+        d_xn2 = dgrad(dpl, pl.plane_t(bp + "mlp.fc1.weight"), M, D, 4 * D)
+        dg, db = layernorm_bwd(d_xn2, b.x_mid, pl.vec(bp + "norm2.weight"), d_tok)
+        grads["encoder." + bp + "norm2.weight"], grads["encoder." + bp + "norm2.bias"] = dg, db
+        # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
+        dpl, dt = split_transpose(d_tok, M, D)
+        grads["encoder." + bp + "attn.proj.bias"] = colsum(d_tok, M, D)
+        grads["encoder." + bp + "attn.proj.weight"] = wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad)
+        d_att = dgrad(dpl, pl.plane_t(bp + "attn.proj.weight"), M, D, D)
+        d_qkv = torch.empty(M, 3 * D, **f32)
+        a = L.AttentionBwdArgs()
+        a.qkv_hi, a.qkv_lo, a.o_hi, a.o_lo = b.qkv[0].data_ptr(), b.qkv[1].data_ptr(), b.att[0].data_ptr(), b.att[1].data_ptr()
+        dvec = torch.empty(M, E.HEADS, **f32)
+        a.dO, a.lse, a.Dvec, a.dqkv = d_att.data_ptr(), b.lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
+        a.batch, a.tokens, a.row_offset, a.heads, a.scale = B, N, 0, E.HEADS, scale
+        L.check(L.lib().dupl_attention_bwd(C.byref(a), _st(dev)), "dupl_attention_bwd")
+        dpl, dt = split_transpose(d_qkv, M, 3 * D)
+        grads["encoder." + bp + "attn.qkv.bias"] = colsum(d_qkv, M, 3 * D)
+        grads["encoder." + bp + "attn.qkv.weight"] = wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad)
+        d_xn1 = dgrad(dpl, pl.plane_t(bp + "attn.qkv.weight"), M, D, 3 * D)
+        dg, db = layernorm_bwd(d_xn1, b.x_in, pl.vec(bp + "norm1.weight"), d_tok)
+        grads["encoder." + bp + "norm1.weight"], grads["encoder." + bp + "norm1.bias"] = dg, db
+
+    # ---- patch embedding (pos_embed is frozen, vit.py:243)
+    _, dt = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1)
+    grads["encoder.patch_embed.proj.bias"] = colsum(d_tok, Mp, D, tokens=N, np_=np_, first=1)
+    dwpe = wgrad(dt, transpose_planes(S.patch, Mp, D), D, D, _pad64(Mp))
+    grads["encoder.patch_embed.proj.weight"] = dwpe.reshape(D, 3, 16, 16)
+    grads["encoder.cls_token"] = colsum(d_tok, B, D, tokens=N, np_=1, first=0).reshape(1, 1, D)
+    return grads
+
+
+def trainable_parameters(net):
+    """(name, parameter) pairs that take part in the forward pass, in a fixed order."""
+    out = []
+    for name, p in net.named_parameters():
+        if name.startswith("encoder.head.") or not p.requires_grad:
+            continue
+        out.append((name, p))
+    return out
+
+
+class StudentFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, size, *params):
+        ctx.set_materialize_grads(False)
+        outs, S = _forward(net, x, size)
+        ctx.net, ctx.S = net, S
+        ctx.names = [(n, tuple(p.shape)) for n, p in trainable_parameters(net)]
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_cls, g_seg, g_x4, g_aux):
+        with torch.no_grad():
+            grads = _backward(ctx.net, ctx.S, g_cls, g_seg, g_x4, g_aux)
+        ctx.S = None
+        out = []
+        for n, shape in ctx.names:
+            g = grads.get(n)
+            out.append(None if g is None else g.reshape(shape))
+        return (None, None, None, *out)
+
+
+def student_forward(net, x, size=None):
+    params = [p for _, p in trainable_parameters(net)]
+    return StudentFunction.apply(net, x, size, *params)

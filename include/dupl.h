@@ -68,7 +68,7 @@ int dupl_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
 /* Epilogues of dupl_gemm_bf16x3 */
 #define DUPL_EPI_F32 0        /* out_f32 = acc + bias                                         */
 #define DUPL_EPI_SPLIT 1      /* out_hi/lo = split(acc + bias)            (qkv: vit.py:122)     */
-#define DUPL_EPI_GELU_SPLIT 2 /* out_hi/lo = split(gelu_erf(acc + bias))  (fc1+act: vit.py:98-99) */
+#define DUPL_EPI_GELU_SPLIT 2 /* out_hi/lo = split(gelu_erf(acc + bias))  (fc1+act: vit.py:98-99); out_f32 (optional) = acc + bias */
 #define DUPL_EPI_RESID 3      /* out_f32 = resid + acc + bias  (proj / fc2 + residual: vit.py:158-159) */
 #define DUPL_EPI_PATCH 4      /* out_f32[token row] = acc + bias + pos_embed (vit.py:292-304)  */
 #define DUPL_EPI_RELU_SPLIT 5 /* out_hi/lo = split(relu(acc + bias))   (conv6/conv7 + ReLU: conv_head.py:34-38) */
@@ -119,6 +119,7 @@ typedef struct {
   const void* qkv_lo;
   void* out_hi;
   void* out_lo;
+  float* lse; /* optional [M, heads]: ln sum_j exp(scale * s_ij) per row and head (for dupl_attention_bwd) */
 } dupl_attention_args;
 
 int dupl_attention_fwd(const dupl_attention_args* args, void* stream);
@@ -262,6 +263,58 @@ typedef struct {
 } dupl_refine_epilogue_args;
 
 int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward pass of the training step (train_final_voc.py:470-471 `loss.backward()` through
+ * model/model_dupl.py, vit.py, conv_head.py).  dgrad and wgrad of every Linear / conv are
+ * dupl_gemm_bf16x3 calls on transposed operand planes; the kernels below provide the operands and the
+ * non-GEMM gradients.  Row addressing: row(r) = r when tokens == 0, else (r / np)*tokens + first + r % np.
+ * ---------------------------------------------------------------------------------------- */
+/* src fp32 [R rows (mapped), Cc] (row stride ld) -> planes hi/lo [R, Cc] (optional) and transposed planes
+ * t_hi/t_lo [Cc, Rpad] (optional; columns R..Rpad-1 zero so that Rpad % 64 == 0 can be a GEMM contraction). */
+int dupl_split_transpose(const float* src, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
+                         void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, void* stream);
+/* one bf16 plane [R (mapped), Cc] (row stride ld) -> its transpose [Cc, Rpad], zero padded. */
+int dupl_transpose_plane(const void* in, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
+                         void* out, int32_t Rpad, void* stream);
+/* out[c] = sum_r x[row(r)][c]  (bias gradients) */
+int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first, float* out,
+                void* stream);
+/* LayerNorm backward (vit.py:146,152,256): dres[rows, cols] += dL/dx; dgamma, dbeta [cols];
+ * partial: scratch of 2*cols*ceil(rows/32) floats.  cols == 768. */
+int dupl_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dres, float* partial, float* dgamma,
+                       float* dbeta, int32_t rows, int32_t cols, float eps, void* stream);
+/* d[i] *= gelu'(pre[i]) (exact erf form) */
+int dupl_gelu_bwd(float* d, const float* pre, int64_t n, void* stream);
+/* d[i] = 0 where the saved relu output (split planes) is 0 */
+int dupl_relu_bwd(float* d, const void* act_hi, const void* act_lo, int64_t n, void* stream);
+/* gradient of dupl_im2col3x3: din[row(b,y,x)][c] (+)= sum_tap dcol[(b, y-dy, x-dx)][tap*Cin + c] */
+int dupl_col2im3x3(const float* dcol, float* din, int32_t B, int32_t gh, int32_t gw, int32_t Cin, int32_t dilation,
+                   int32_t ld_in, int32_t tokens, int32_t first, int32_t accumulate, void* stream);
+/* dst[row(b*np + p)][c] += src[b][c][p]  (gradient of dupl_rows_to_nchw) */
+int dupl_nchw_to_rows_add(const float* src, float* dst, int32_t B, int32_t np, int32_t Cc, int32_t ld, int32_t tokens,
+                          int32_t first, void* stream);
+/* gradient of dupl_gmp_classify: dx[row(b, argmax[b][d])][d] += sum_k dlogits[b][k] w[k][d];
+ * dw[k][d] = sum_b dlogits[b][k] * pooled[b][d]; dw_partial: scratch [B, K, D]. */
+int dupl_gmp_classify_bwd(const float* x, const float* w, const float* dlogits, const int32_t* argmax, float* dx,
+                          float* dw_partial, float* dw, int32_t B, int32_t np, int32_t D, int32_t K, int32_t ld,
+                          int32_t tokens, int32_t first, void* stream);
+/* Attention backward for one segment (vit.py:120-135): from the forward's qkv / output planes, lse and the
+ * gradient dO fp32 [M, heads*64] -> dqkv fp32 [M, 3*heads*64].  Dvec: scratch [M, heads]. */
+typedef struct {
+  const void* qkv_hi;
+  const void* qkv_lo;
+  const void* o_hi;
+  const void* o_lo;
+  const float* dO;
+  const float* lse;
+  float* Dvec;
+  float* dqkv;
+  int32_t batch, tokens, row_offset, heads;
+  float scale;
+} dupl_attention_bwd_args;
+
+int dupl_attention_bwd(const dupl_attention_bwd_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Losses (model/losses.py) with fused forward + backward.

@@ -162,10 +162,3 @@ def test_val_forward_matches_oracle():
                 assert rel_err(g, w) < 1e-3
         one = m(x.cuda(), val=True, branch=2)
         assert torch.equal(one[1], res["branch2"][1])
-
-
-def test_training_mode_forward_fails_loudly_until_built():
-    m, _ = _load_model()
-    m.train()
-    with pytest.raises(NotImplementedError, match="no PyTorch fallback"):
-        m(synth_images(1, 32, 32).cuda())

@@ -1,0 +1,114 @@
+"""GPU: training-mode forward + backward of the students (dupl_b200.train, autograd.Function over CUDA kernels)
+against the oracle's CPU autograd: every parameter gradient within 1e-3 (norm-relative) of fp32."""
+import pytest
+import torch
+
+from helpers import init_state_dict, rel_err, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(num_classes=21):
+    from dupl_b200.model.model_dupl import siamese_network
+    P = init_state_dict(num_classes)
+    m = siamese_network("deit_base_patch16_224", num_classes=num_classes, pretrained=False, aux_layer=-3)
+    m.load_state_dict(P, strict=True)
+    return m.cuda().train(), P
+
+
+def _probe_weights(outs, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(o.shape, generator=g) for o in outs]
+
+
+def _nrel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("H,W", [(32, 48), (64, 64)])
+def test_student_forward_backward_matches_oracle_autograd(H, W):
+    from oracle import dupl_oracle as O
+    m, P = _models()
+    x = synth_images(2, H, W, seed=7)
+    # ---- oracle (CPU autograd) for student 2
+    Pg = {k: v.clone().requires_grad_(k.startswith("branch2.") and "pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+    want = O.network_forward(Pg, 2, x)
+    probes = _probe_weights(want, seed=H)
+    sum(( o * w).sum() for o, w in zip(want, probes)).backward()
+    # ---- CUDA
+    got = m(x.cuda(), branch=2)
+    assert len(got) == 4
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and rel_err(g, w) < 1e-3
+    sum((o * w.cuda()).sum() for o, w in zip(got, probes)).backward()
+    checked = 0
+    worst = (0.0, "")
+    bad = []
+    for name, p in m.branch2.named_parameters():
+        ref = Pg["branch2." + name].grad
+        if name.startswith("encoder.head.") or name == "encoder.pos_embed":
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        assert torch.isfinite(p.grad).all(), name
+        e = _nrel(p.grad, ref)
+        worst = max(worst, (e, name))
+        if e >= 1e-3:
+            bad.append((name, round(e, 5)))
+        checked += 1
+    assert checked == 154
+    assert not bad, bad
+    assert all(p.grad is None for p in m.branch1.parameters())  # the other student was not touched
+
+
+def test_both_students_dict_output_and_need_sp_view():
+    """model(x) -> {'branch1': 4-tuple, 'branch2': 4-tuple}; need_sp adds the 0.75x aug-view seg logits (model_dupl.py:190-205)."""
+    from oracle import dupl_oracle as O
+    m, P = _models()
+    x = synth_images(2, 64, 64, seed=8)
+    x_aug = synth_images(2, 64, 64, seed=9)
+    res = m(torch.cat([x, x_aug]).cuda(), need_sp=True)
+    assert set(res) == {"branch1", "branch2", "branch1_aug", "branch2_aug"}
+    with torch.no_grad():
+        want1 = O.network_forward(P, 1, x)
+        small = O.bilinear(x_aug, 48, 48)
+        want_aug = O.network_forward(P, 2, small)[1]
+    for g, w in zip(res["branch1"], want1):
+        assert rel_err(g, w) < 1e-3
+    assert res["branch2_aug"].shape == want_aug.shape == (2, 21, 3, 3)
+    assert rel_err(res["branch2_aug"], want_aug) < 1e-3
+    (res["branch1"][1].sum() + res["branch2_aug"].sum()).backward()
+    assert m.branch1.decoder.conv8.weight.grad is not None and m.branch2.decoder.conv8.weight.grad is not None
+
+
+def test_phase_b_step_losses_and_gradients_match_oracle_loop():
+    """dupl_b200.train_step.PhaseBStep (restatement of train_final_voc.py:260-356,438-456) vs the oracle's CPU loop:
+    every loss part within 1e-3, refined labels (near-)identical, gradient of the total loss within 1e-3."""
+    from dupl_b200.train_step import PhaseBStep, VOC_HIGH_THRES_TARGET
+    from helpers import synth_boxes, synth_cls_labels
+    from oracle import dupl_oracle as O
+    m, P = _models()
+    b, S = 2, 64
+    x = synth_images(b, S, S, seed=11)
+    cls = synth_cls_labels(b, 20, seed=12)
+    box = synth_boxes(b, S, S, seed=13)
+    Pg = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+    want, wparts, wlabels = O.phase_b_losses(Pg, x, cls, box, 3000, thres_target=VOC_HIGH_THRES_TARGET)
+    want.backward()
+    step = PhaseBStep(m, None)
+    got, parts, labels = step.losses(x.cuda(), cls.cuda(), box, 3000)
+    got.backward()
+    for k in wparts:
+        assert abs(parts[k].item() - wparts[k].item()) < 1e-3 * max(1.0, abs(wparts[k].item())), (k, parts[k].item(), wparts[k].item())
+    for a, w in zip(labels, wlabels):
+        assert (a.cpu() != w).float().mean().item() < 1e-3
+    bad = []
+    for name, p in m.named_parameters():
+        ref = Pg[name].grad
+        if ".head." in name or "pos_embed" in name:
+            continue
+        e = _nrel(p.grad, ref)
+        if e >= 2e-3:
+            bad.append((name, round(e, 5)))
+    assert not bad, bad[:10]
