@@ -38,3 +38,64 @@ def test_refine_matches_reference_bit_exact():
     box = torch.tensor([[0, 64, 0, 64], [5, 60, 3, 50]], dtype=torch.int16)
     want = ref.cam_helper.refine_cams_with_bkg_v2(par, imgs, cams, cls, high_thre=0.65, low_thre=0.25, ignore_index=255, img_box=box)
     assert torch.equal(O.refine_cams(imgs, cams, cls, 0.65, 0.25, 255, box), want)
+
+
+def test_phase_b_loop_matches_the_reference_functions_composed_like_the_script():
+    """The loop body train_final_voc.py:260-356,438-456 re-executed with the reference's OWN modules (model, cam_helper,
+    PAR, losses) vs oracle.phase_b_losses on the same inputs."""
+    import numpy as np
+    import torch.nn.functional as F
+    from helpers import init_state_dict, synth_boxes, synth_cls_labels, synth_images
+    ref = ref_import.load()
+    P = init_state_dict(21)
+    model = ref.model_dupl.siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
+    model.load_state_dict(P, strict=True)
+    model.train()
+    par = ref.PAR.PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24])
+    b, S = 2, 64
+    inputs = synth_images(b, S, S, seed=11)
+    cls_label = synth_cls_labels(b, 20, seed=12)
+    img_box = synth_boxes(b, S, S, seed=13)
+    n_iter, cam_iters, max_iters = 3000, 2000, 20000
+    target = torch.tensor([0.70, 0.70, 0.70, 0.70, 0.55, 0.55, 0.55, 0.55, 0.70, 0.55, 0.55, 0.55, 0.55, 0.55, 0.55, 0.55, 0.55,
+                           0.55, 0.70, 0.55])
+    start = torch.ones(20) * 0.7
+    f = (n_iter - cam_iters) / (max_iters - cam_iters - 1)
+    high_thres = start + (target - start) * (1 - np.cos(np.pi * f)) / 2                       # train_helper.cosine_descent
+    inputs_denorm = ref.imutils.denormalize_img2(inputs.clone())
+    hl, ml = [], []
+    for i in range(b):                                                                          # :268-275
+        t = torch.max(high_thres[torch.nonzero(cls_label[i]).squeeze(-1)])
+        hl.append(t)
+        ml.append(torch.ones((S, S)) * t)
+    high, high_mask = torch.stack(hl), torch.stack(ml).unsqueeze(1)
+    cams_1, aux_1 = ref.cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=(1.0, 0.5, 1.5), branch=1)
+    cams_2, aux_2 = ref.cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=(1.0, 0.5, 1.5), branch=2)
+    res = model(inputs)
+    cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
+    cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
+    cls_loss = sum(F.multilabel_soft_margin_loss(t, cls_label) for t in (cls_1, cls_aux_1, cls_2, cls_aux_2))
+    ptc = 0
+    for aux, fmap in ((aux_1, fmap_1), (aux_2, fmap_2)):
+        r = F.interpolate(aux, size=fmap.shape[2:], mode="bilinear", align_corners=False)
+        _, pl = ref.cam_helper.cam_to_label_dynamic_cls(r.detach(), cls_label=cls_label, img_box=img_box, ignore_mid=True,
+                                                        bkg_thre=0.5, high_thre=high, low_thre=0.25, ignore_index=255)
+        ptc = ptc + ref.losses.get_masked_ptc_loss(fmap, ref.cam_helper.label_to_aff_mask(pl))
+    rep = cls_label.unsqueeze(-1).unsqueeze(-1).repeat([1, 1, S, S])
+    lab_1 = ref.cam_helper.refine_cams_with_dynamic_thres(par, inputs_denorm, cams=cams_1.detach() * rep, cls_labels=cls_label,
+                                                          high_thre_map=high_mask, low_thre=0.25, ignore_index=255, img_box=img_box)
+    lab_2 = ref.cam_helper.refine_cams_with_dynamic_thres(par, inputs_denorm, cams=cams_2.detach() * rep, cls_labels=cls_label,
+                                                          high_thre_map=high_mask, low_thre=0.25, ignore_index=255, img_box=img_box)
+    s1 = F.interpolate(segs_1, size=lab_1.shape[1:], mode="bilinear", align_corners=False)
+    s2 = F.interpolate(segs_2, size=lab_2.shape[1:], mode="bilinear", align_corners=False)
+    seg = ref.losses.get_seg_loss(s1, lab_2.type(torch.long)) + ref.losses.get_seg_loss(s2, lab_1.type(torch.long))
+    f1, f2 = fmap_1.view(b, 768, -1), fmap_2.view(b, 768, -1)
+    cos = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
+    sim = (1 + cos(f1.detach(), f2).mean()) + (1 + cos(f2.detach(), f1).mean())
+    loss = 1.0 * cls_loss + 0.2 * ptc + 0.2 * seg + 0.1 * sim
+    want = dict(cls_loss=cls_loss, ptc_loss=ptc, seg_loss=seg, sim_loss=sim)
+    got_loss, got, labels = O.phase_b_losses(P, inputs, cls_label, img_box, n_iter, thres_target=target.tolist())
+    for k in want:
+        assert abs(got[k].item() - want[k].item()) < 1e-5 * max(1.0, abs(want[k].item())), k
+    assert abs(got_loss.item() - loss.item()) < 1e-5
+    assert torch.equal(labels[0], lab_1) and torch.equal(labels[1], lab_2)
