@@ -133,6 +133,8 @@ _PROTOTYPES = {
     "dupl_seg_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]),
     "dupl_ptc_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "dupl_ptc_loss_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3),
+    "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
+                                  C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "dupl_crf_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dupl_crf_values_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dupl_crf_build": (C.c_int, [C.POINTER(CrfArgs), C.c_void_p]),
@@ -169,7 +171,9 @@ def check(rc, what):
 
 
 def stream_ptr(device=None):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw cudaStream_t of torch's current stream on `device` (fast path: no Stream object is built)."""
+    idx = device.index if isinstance(device, torch.device) and device.index is not None else torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
 
 
 def ptr(t):

@@ -74,14 +74,22 @@ __global__ void __launch_bounds__(256) transpose_u16_kernel(const unsigned short
   }
 }
 
-// out[c] = sum_r x[map(r)][c]
+// out[c] = sum_r x[map(r)][c].  Block = 32 columns x 8 row lanes; fixed summation order.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int Cc, int ld, RowMap map,
                                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cc) return;
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.0f;
-  for (int r = 0; r < R; ++r) s += x[map(r) * ld + c];
-  out[c] = s;
+  if (c < Cc)
+    for (int r = threadIdx.y; r < R; r += 8) s += x[map(r) * ld + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < Cc) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    out[c] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -557,7 +565,7 @@ extern "C" int dupl_transpose_plane(const void* in, int32_t R, int32_t Cc, int32
 extern "C" int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
                            float* out, void* stream) {
   DUPL_CHECK_ARG(x && out && R > 0 && Cc > 0, "dupl_colsum: bad arguments");
-  colsum_kernel<<<cdiv(Cc, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, Cc, ld, make_map(tokens, np, first), out);
+  colsum_kernel<<<cdiv(Cc, 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, R, Cc, ld, make_map(tokens, np, first), out);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -337,6 +337,15 @@ int dupl_ptc_loss_fwd(const float* x, const int64_t* mask, int32_t b, int32_t C,
 int dupl_ptc_loss_bwd(const float* x, const int64_t* mask, const float* inv, const float* Gs, const float* stats,
                       const float* grad_out, int32_t b, int32_t C, int32_t n, float* dxh_scratch, float* dx, void* stream);
 
+/* GMM noise filter of the training loop (train_final_voc.py:358-394, sklearn GaussianMixture in the
+ * reference): per image, 2-component 1-D mixture on loss[label not in {0, ignore} and loss > loss_min]; when more
+ * than min_count samples exist and the means differ by more than valid_gap, every pixel whose posterior under
+ * the high-mean component exceeds gamma and whose label != 0 gets label = ignore_index.
+ * loss fp32 [b, n]; label fp32 [b, n] (in place); info int32 [b, 4] = samples, filtered?, EM iterations, #flipped. */
+int dupl_gmm_filter(const float* loss, float* label, int32_t b, int32_t n, float ignore_index, float loss_min,
+                    int32_t min_count, float valid_gap, float gamma, float reg_covar, int32_t max_iter, float tol,
+                    int32_t* info, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * DenseCRF mean-field inference (utils/dcrf.py:42-69 -> pydensecrf DenseCRF2D: setUnaryEnergy,
  * addPairwiseGaussian(sxy=pos_xy_std, compat=pos_w), addPairwiseBilateral(sxy=bi_xy_std,

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=448)
+    ap.add_argument("--profile", action="store_true", help="after timing, one extra step under torch.profiler (kernel table to stderr)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -78,6 +79,12 @@ def main():
                           "loss_first_warmup": losses[0] if losses else None, "loss_last": loss.item(),
                           "parts": {k: float(v) for k, v in parts.items()}, "finite": bool(torch.isfinite(loss).item()),
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step(x, cls, box, 4000)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60), file=sys.stderr)
     if dist is not None:
         dist.destroy_process_group()
 
