@@ -47,8 +47,8 @@ class AttentionArgs(C.Structure):
 
 class AttentionBwdArgs(C.Structure):
     _fields_ = [("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p), ("o_hi", C.c_void_p), ("o_lo", C.c_void_p),
-                ("dO", C.c_void_p), ("lse", C.c_void_p), ("Dvec", C.c_void_p), ("dqkv", C.c_void_p),
-                ("batch", C.c_int32), ("tokens", C.c_int32), ("row_offset", C.c_int32), ("heads", C.c_int32),
+                ("do_hi", C.c_void_p), ("do_lo", C.c_void_p), ("lse", C.c_void_p), ("Dvec", C.c_void_p), ("dqkv", C.c_void_p),
+                ("M", C.c_int32), ("batch", C.c_int32), ("tokens", C.c_int32), ("row_offset", C.c_int32), ("heads", C.c_int32),
                 ("scale", C.c_float)]
 
 

@@ -1,0 +1,392 @@
+// Attention backward on tcgen05 (SURVEY A14 / G5 "bwd kernel for training path"; reference: autograd
+// through vit.py:120-135).  Per (image, head), with S = Q K^T, P = exp(scale S - lse), D_i = sum_d dO_id O_id:
+//   dP = dO V^T,  dS = scale * P o (dP - D),  dV = P^T dO,  dK = dS^T Q,  dQ = dS K
+// Two kernels, each shaped so that every operand is either K-major in shared memory, a 64-wide MN-major
+// tile in shared memory, or rows held by the owning thread in tensor memory (the operand modes the
+// forward kernel uses):
+//   attn_bwd_dq_kernel   CTA = 128 queries.  Per 64-key tile: S = Q K^T and dP = dO V^T (A, B from smem),
+//                        thread i turns its rows into dS_i (registers) and stores it split-bf16 to TMEM,
+//                        dQ += dS K (A from TMEM, K consumed in place as an MN-major operand).
+//   attn_bwd_dkv_kernel  CTA = 128 keys, works on TRANSPOSED tiles so that a thread owns a key row:
+//                        S^T = K Q^T, dP^T = V dO^T per 64-query tile, thread j forms P^T_j and dS^T_j,
+//                        dV += P^T dO and dK += dS^T Q (A from TMEM, dO / Q tiles as MN-major operands).
+// All products are 3-pass split-bf16 with fp32 accumulation in TMEM; dQ, dK, dV accumulate in TMEM over
+// the whole loop (the backward needs no rescaling) and are written once as fp32.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dupl {
+
+constexpr int AB_THREADS = 128;
+constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
+constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
+constexpr int AB_SMEM = 4 * AB_T128 + 8 * AB_T64 + 1024 + 256;  // 128 KB + barriers
+
+struct AttnBwdTcParams {
+  CUtensorMap tm_qkv128_hi, tm_qkv128_lo, tm_qkv64_hi, tm_qkv64_lo;  // [M, 3*heads*64] planes, boxes of 128 / 64 rows
+  CUtensorMap tm_do128_hi, tm_do128_lo, tm_do64_hi, tm_do64_lo;      // [M, heads*64] planes
+  const float* lse;   // [M, heads]
+  const float* Dvec;  // [M, heads]
+  float* dqkv;        // [M, 3*heads*64]
+  int tokens, row_offset, heads;
+  float scale;
+};
+
+// D[tmem] (+)= A[smem] B[smem]^T, 3-pass split, 64-deep contraction; b_kstep = 32 (K-major B) or 2048 (MN-major B)
+__device__ __forceinline__ void mma_ss_split(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, uint32_t b_kstep, bool accumulate) {
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t a = (pass == 2) ? a_lo : a_hi;
+    const uint64_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * b_kstep), idesc,
+                 (accumulate || (pass | k) != 0) ? 1u : 0u);
+  }
+}
+// same with A in tensor memory (hi at a_tmem, lo 32 columns further)
+__device__ __forceinline__ void mma_ts_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                             uint32_t b_kstep, bool accumulate) {
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = a_tmem + ((pass == 2) ? 32 : 0);
+    const uint64_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      tc_mma_f16_ts(d_tmem, a + k * 8, umma_desc_advance(b, k * b_kstep), idesc, (accumulate || (pass | k) != 0) ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ void store_split_row(uint32_t taddr, const float (&v)[64]) {
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int c = 0; c < 64; c += 2) split2_bf16(v[c], v[c + 1], hi[c >> 1], lo[c >> 1]);
+  tmem_st_32x32(taddr, hi);
+  tmem_st_32x32(taddr + 32, lo);
+}
+
+__device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
+  uint32_t a[32], b[32];
+  tmem_ld_32x32(taddr, a);
+  tmem_ld_32x32(taddr + 32, b);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    v[c] = __uint_as_float(a[c]);
+    v[32 + c] = __uint_as_float(b[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dQ
+// grid (q tiles of 128, heads, images)
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                     // hi | lo, 128 rows
+  uint8_t* sdO = sQ + 2 * AB_T128;        // hi | lo, 128 rows
+  uint8_t* sK = sdO + 2 * AB_T128;        // [2 stages][hi | lo], 64 rows
+  uint8_t* sV = sK + 4 * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 4 * AB_T64);
+  uint64_t* bar_q = bars;          // Q, dO landed
+  uint64_t* bar_kv = bars + 1;     // [2]
+  uint64_t* bar_s = bars + 3;      // S, dP complete
+  uint64_t* bar_d = bars + 4;      // dQ MMAs of this tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int hd = p.heads * 64;
+  const int row0 = p.row_offset + img * p.tokens;
+  const int n_kv = (p.tokens + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  constexpr int TM_S = 0, TM_DP = 64, TM_DQ = 128, TM_DS = 192;
+
+  auto load_kv = [&](int j) {
+    const int st = j & 1;
+    mbar_arrive_expect_tx(&bar_kv[st], 4 * AB_T64);
+    tma_load_2d(sK + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], hd + head * 64, row0 + j * 64);
+    tma_load_2d(sK + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], hd + head * 64, row0 + j * 64);
+    tma_load_2d(sV + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
+    tma_load_2d(sV + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
+  };
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 4 * AB_T128);
+    tma_load_2d(sQ, &p.tm_qkv128_hi, bar_q, head * 64, row0 + qt * 128);
+    tma_load_2d(sQ + AB_T128, &p.tm_qkv128_lo, bar_q, head * 64, row0 + qt * 128);
+    tma_load_2d(sdO, &p.tm_do128_hi, bar_q, head * 64, row0 + qt * 128);
+    tma_load_2d(sdO + AB_T128, &p.tm_do128_lo, bar_q, head * 64, row0 + qt * 128);
+    load_kv(0);
+    if (n_kv > 1) load_kv(1);
+  }
+
+  const int qrow = qt * 128 + tid;
+  const bool q_ok = qrow < p.tokens;
+  const long grow = static_cast<long>(row0) + qrow;
+  const float lse2 = q_ok ? p.lse[grow * p.heads + head] * 1.44269504088896340736f : 0.0f;
+  const float Di = q_ok ? p.Dvec[grow * p.heads + head] : 0.0f;
+  const float c2 = p.scale * 1.44269504088896340736f;
+
+  constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);  // B K-major
+  constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);  // B MN-major
+  const uint64_t dQh = umma_desc_sw128(smem_u32(sQ)), dQl = umma_desc_sw128(smem_u32(sQ + AB_T128));
+  const uint64_t dOh = umma_desc_sw128(smem_u32(sdO)), dOl = umma_desc_sw128(smem_u32(sdO + AB_T128));
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int st = j & 1;
+    const uint32_t ph = static_cast<uint32_t>(j & 1), kv_ph = static_cast<uint32_t>((j >> 1) & 1);
+    const uint64_t dKh = umma_desc_sw128(smem_u32(sK + st * 2 * AB_T64)), dKl = umma_desc_sw128(smem_u32(sK + st * 2 * AB_T64 + AB_T64));
+    const uint64_t dVh = umma_desc_sw128(smem_u32(sV + st * 2 * AB_T64)), dVl = umma_desc_sw128(smem_u32(sV + st * 2 * AB_T64 + AB_T64));
+    if (warp == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[st], kv_ph);
+      tc_fence_after();
+      mma_ss_split(tm + TM_S, dQh, dQl, dKh, dKl, idesc_kk, 32, false);   // S  = Q K^T
+      mma_ss_split(tm + TM_DP, dOh, dOl, dVh, dVl, idesc_kk, 32, false);  // dP = dO V^T
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    float s[64], dp[64];
+    load_row64(tm + TM_S + lane_base, s);
+    load_row64(tm + TM_DP + lane_base, dp);
+    const int kv_valid = p.tokens - j * 64;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      const float pv = (q_ok && c < kv_valid) ? fast_exp2(fmaf(s[c], c2, -lse2)) : 0.0f;
+      s[c] = p.scale * pv * (dp[c] - Di);  // dS
+    }
+    store_split_row(tm + TM_DS + lane_base, s);
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      mma_ts_split(tm + TM_DQ, tm + TM_DS, dKh, dKl, idesc_mn, 2048, j > 0);  // dQ += dS K
+      tc_commit(bar_d);
+    }
+    mbar_wait(bar_d, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 2 < n_kv) load_kv(j + 2);
+  }
+
+  float dq[64];
+  load_row64(tm + TM_DQ + lane_base, dq);
+  if (q_ok) {
+    float4* o = reinterpret_cast<float4*>(p.dqkv + grow * 3 * hd + head * 64);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tm, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dK, dV
+// grid (kv tiles of 128, heads, images)
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                   // hi | lo, 128 rows
+  uint8_t* sV = sK + 2 * AB_T128;
+  uint8_t* sQ = sV + 2 * AB_T128;       // [2 stages][hi | lo], 64 rows
+  uint8_t* sdO = sQ + 4 * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + 4 * AB_T64);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_q = bars + 1;  // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_d = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int hd = p.heads * 64;
+  const int row0 = p.row_offset + img * p.tokens;
+  const int n_q = (p.tokens + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  constexpr int TM_ST = 0, TM_DPT = 64, TM_DV = 128, TM_DK = 192, TM_PT = 256, TM_DST = 320;
+
+  auto load_q = [&](int i) {
+    const int st = i & 1;
+    mbar_arrive_expect_tx(&bar_q[st], 4 * AB_T64);
+    tma_load_2d(sQ + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_q[st], head * 64, row0 + i * 64);
+    tma_load_2d(sQ + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_q[st], head * 64, row0 + i * 64);
+    tma_load_2d(sdO + st * 2 * AB_T64, &p.tm_do64_hi, &bar_q[st], head * 64, row0 + i * 64);
+    tma_load_2d(sdO + st * 2 * AB_T64 + AB_T64, &p.tm_do64_lo, &bar_q[st], head * 64, row0 + i * 64);
+  };
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 4 * AB_T128);
+    tma_load_2d(sK, &p.tm_qkv128_hi, bar_kv, hd + head * 64, row0 + kt * 128);
+    tma_load_2d(sK + AB_T128, &p.tm_qkv128_lo, bar_kv, hd + head * 64, row0 + kt * 128);
+    tma_load_2d(sV, &p.tm_qkv128_hi, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
+    tma_load_2d(sV + AB_T128, &p.tm_qkv128_lo, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
+    load_q(0);
+    if (n_q > 1) load_q(1);
+  }
+
+  const int key = kt * 128 + tid;
+  const bool k_ok = key < p.tokens;
+  const float c2 = p.scale * 1.44269504088896340736f;
+  constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);
+  constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);
+  const uint64_t dKh = umma_desc_sw128(smem_u32(sK)), dKl = umma_desc_sw128(smem_u32(sK + AB_T128));
+  const uint64_t dVh = umma_desc_sw128(smem_u32(sV)), dVl = umma_desc_sw128(smem_u32(sV + AB_T128));
+
+  for (int i = 0; i < n_q; ++i) {
+    const int st = i & 1;
+    const uint32_t ph = static_cast<uint32_t>(i & 1), q_ph = static_cast<uint32_t>((i >> 1) & 1);
+    const uint64_t dQh = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64)), dQl = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64 + AB_T64));
+    const uint64_t dOh = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64)), dOl = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64 + AB_T64));
+    if (warp == 0) {
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(&bar_q[st], q_ph);
+      tc_fence_after();
+      mma_ss_split(tm + TM_ST, dKh, dKl, dQh, dQl, idesc_kk, 32, false);   // S^T  = K Q^T
+      mma_ss_split(tm + TM_DPT, dVh, dVl, dOh, dOl, idesc_kk, 32, false);  // dP^T = V dO^T
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    float s[64], dp[64];
+    load_row64(tm + TM_ST + lane_base, s);
+    load_row64(tm + TM_DPT + lane_base, dp);
+    const int q_valid = p.tokens - i * 64;
+    const float* lse_t = p.lse + (static_cast<long>(row0) + i * 64) * p.heads + head;
+    const float* D_t = p.Dvec + (static_cast<long>(row0) + i * 64) * p.heads + head;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      float pv = 0.0f, ds = 0.0f;
+      if (k_ok && c < q_valid) {
+        pv = fast_exp2(fmaf(s[c], c2, -__ldg(lse_t + c * p.heads) * 1.44269504088896340736f));
+        ds = p.scale * pv * (dp[c] - __ldg(D_t + c * p.heads));
+      }
+      s[c] = pv;
+      dp[c] = ds;
+    }
+    store_split_row(tm + TM_PT + lane_base, s);
+    store_split_row(tm + TM_DST + lane_base, dp);
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      mma_ts_split(tm + TM_DV, tm + TM_PT, dOh, dOl, idesc_mn, 2048, i > 0);   // dV += P^T dO
+      mma_ts_split(tm + TM_DK, tm + TM_DST, dQh, dQl, idesc_mn, 2048, i > 0);  // dK += dS^T Q
+      tc_commit(bar_d);
+    }
+    mbar_wait(bar_d, ph);
+    tc_fence_after();
+    if (tid == 0 && i + 2 < n_q) load_q(i + 2);
+  }
+
+  float dv[64];
+  load_row64(tm + TM_DV + lane_base, dv);
+  if (k_ok) {
+    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + 2 * hd + head * 64);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+  }
+  load_row64(tm + TM_DK + lane_base, dv);
+  if (k_ok) {
+    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + hd + head * 64);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+// D[row][head] = sum_d dO[row][head*64 + d] * O[row][head*64 + d], both given as split planes
+__global__ void __launch_bounds__(256) attn_bwd_d_kernel(const __nv_bfloat16* __restrict__ do_hi, const __nv_bfloat16* __restrict__ do_lo,
+                                                         const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
+                                                         float* __restrict__ Dvec, int row_offset, int rows, int heads) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= rows * heads) return;
+  const int row = row_offset + item / heads, h = item % heads;
+  const long o = static_cast<long>(row) * heads * 64 + h * 64;
+  float s = 0.0f;
+  for (int d = lane; d < 64; d += 32)
+    s += (__bfloat162float(do_hi[o + d]) + __bfloat162float(do_lo[o + d])) * (__bfloat162float(o_hi[o + d]) + __bfloat162float(o_lo[o + d]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) Dvec[static_cast<long>(row) * heads + h] = s;
+}
+
+}  // namespace dupl
+
+extern "C" int dupl_attention_bwd(const dupl_attention_bwd_args* a, void* stream) {
+  using namespace dupl;
+  DUPL_CHECK_ARG(a != nullptr, "dupl_attention_bwd: args is NULL");
+  DUPL_CHECK_ARG(a->qkv_hi && a->qkv_lo && a->o_hi && a->o_lo && a->do_hi && a->do_lo && a->lse && a->Dvec && a->dqkv,
+                 "dupl_attention_bwd: NULL pointer");
+  DUPL_CHECK_ARG(a->batch > 0 && a->tokens > 0 && a->heads > 0 && a->M >= a->row_offset + a->batch * a->tokens,
+                 "dupl_attention_bwd: bad shape");
+  AttnBwdTcParams P;
+  memset(&P, 0, sizeof(P));
+  const int hd = a->heads * 64;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_qkv128_hi, a->qkv_hi, a->M, 3 * hd, 3 * hd, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_qkv128_lo, a->qkv_lo, a->M, 3 * hd, 3 * hd, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_qkv64_hi, a->qkv_hi, a->M, 3 * hd, 3 * hd, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_qkv64_lo, a->qkv_lo, a->M, 3 * hd, 3 * hd, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_do128_hi, a->do_hi, a->M, hd, hd, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_do128_lo, a->do_lo, a->M, hd, hd, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_do64_hi, a->do_hi, a->M, hd, hd, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&P.tm_do64_lo, a->do_lo, a->M, hd, hd, 64))) return rc;
+  P.lse = a->lse; P.Dvec = a->Dvec; P.dqkv = a->dqkv;
+  P.tokens = a->tokens; P.row_offset = a->row_offset; P.heads = a->heads; P.scale = a->scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr_set = true;
+  }
+  const int rows = a->batch * a->tokens;
+  attn_bwd_d_kernel<<<cdiv(rows * a->heads, 8), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(a->do_hi), static_cast<const __nv_bfloat16*>(a->do_lo),
+      static_cast<const __nv_bfloat16*>(a->o_hi), static_cast<const __nv_bfloat16*>(a->o_lo), a->Dvec, a->row_offset, rows, a->heads);
+  DUPL_LAUNCH_OK();
+  dim3 grid(cdiv(a->tokens, 128), a->heads, a->batch);
+  attn_bwd_dkv_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(P);
+  DUPL_LAUNCH_OK();
+  attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(P);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}

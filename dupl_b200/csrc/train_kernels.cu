@@ -7,9 +7,7 @@
 //   gelu_bwd, relu_bwd
 //   col2im3x3         gradient of the dilated im2col (gather form, deterministic)
 //   gmp_classify_bwd  global-max-pool + 1x1 classifier
-//   attention backward (attn_bwd_d / attn_bwd_dkv / attn_bwd_dq): fp32 on the CUDA cores from the saved
-//                     split-bf16 Q, K, V, O and the log-sum-exp rows — exact, and the known slow spot of
-//                     the training step (tensor-core version: next round).
+// (the attention backward lives in attention_bwd.cu)
 // All reductions have a fixed order: results are bit-reproducible.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -290,243 +288,6 @@ __global__ void __launch_bounds__(256) sum_over_first_kernel(const float* __rest
   out[i] = s;
 }
 
-// ------------------------------------------------------------------------------------------------
-// attention backward (fp32, CUDA cores).  Per (image, head): Q,K,V,O [N,64] from split planes,
-// dO fp32 [M, heads*64], lse [M, heads] (natural log of sum_j exp(scale * s_ij)).
-//   D_i   = sum_d dO_id O_id
-//   P_ij  = exp(scale * s_ij - lse_i),  dP_ij = sum_d dO_id V_jd,  dS_ij = scale * P_ij (dP_ij - D_i)
-//   dV_j += sum_i P_ij dO_i,  dK_j += sum_i dS_ij Q_i,  dQ_i += sum_j dS_ij K_j
-// dqkv: fp32 [M, 3*heads*64] (q | k | v like the forward planes).
-// ------------------------------------------------------------------------------------------------
-struct AttnBwdParams {
-  const __nv_bfloat16* qkv_hi;
-  const __nv_bfloat16* qkv_lo;
-  const __nv_bfloat16* o_hi;
-  const __nv_bfloat16* o_lo;
-  const float* dO;
-  const float* lse;
-  float* Dvec;   // [M, heads]
-  float* dqkv;
-  int tokens, row_offset, heads;
-  float scale;
-};
-
-__global__ void __launch_bounds__(256) attn_bwd_d_kernel(AttnBwdParams p, int rows) {
-  const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);  // (row, head)
-  if (item >= rows * p.heads) return;
-  const int row = p.row_offset + item / p.heads, h = item % p.heads;
-  const int hd = p.heads * 64;
-  const long o = static_cast<long>(row) * hd + h * 64;
-  float s = 0.0f;
-  for (int d = lane; d < 64; d += 32)
-    s += p.dO[o + d] * (__bfloat162float(p.o_hi[o + d]) + __bfloat162float(p.o_lo[o + d]));
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) p.Dvec[static_cast<long>(row) * p.heads + h] = s;
-}
-
-constexpr int AB = 64;  // tile edge
-// loads a [64 rows x 64] tile of a split-bf16 matrix (row stride ld) as fp32 into smem, rows >= valid -> 0
-__device__ __forceinline__ void load_tile_split(float (*dst)[AB + 1], const __nv_bfloat16* hi, const __nv_bfloat16* lo,
-                                                long row0, int valid, int ld, int col0) {
-  for (int e = threadIdx.x; e < AB * AB; e += 256) {
-    const int r = e / AB, c = e % AB;
-    float v = 0.0f;
-    if (r < valid) {
-      const long o = (row0 + r) * ld + col0 + c;
-      v = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
-    }
-    dst[r][c] = v;
-  }
-}
-__device__ __forceinline__ void load_tile_f32(float (*dst)[AB + 1], const float* src, long row0, int valid, int ld, int col0) {
-  for (int e = threadIdx.x; e < AB * AB; e += 256) {
-    const int r = e / AB, c = e % AB;
-    dst[r][c] = r < valid ? src[(row0 + r) * ld + col0 + c] : 0.0f;
-  }
-}
-// acc[i][j] += sum_k A[ty*4+i][k] * B[tx*4+j][k]      (A, B row-major tiles, "NT")
-__device__ __forceinline__ void mm_nt(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
-#pragma unroll 8
-  for (int k = 0; k < AB; ++k) {
-    float a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = A[ty * 4 + i][k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = B[tx * 4 + j][k];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-}
-// acc[i][j] += sum_k A[k][ty*4+i] * B[k][tx*4+j]      ("TN": contraction over tile rows)
-__device__ __forceinline__ void mm_tn(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
-#pragma unroll 8
-  for (int k = 0; k < AB; ++k) {
-    float a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = A[k][ty * 4 + i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = B[k][tx * 4 + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-}
-// acc[i][j] += sum_k A[ty*4+i][k] * B[k][tx*4+j]      ("NN")
-__device__ __forceinline__ void mm_nn(float (&acc)[4][4], float (*A)[AB + 1], float (*B)[AB + 1], int ty, int tx) {
-#pragma unroll 8
-  for (int k = 0; k < AB; ++k) {
-    float a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = A[ty * 4 + i][k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = B[k][tx * 4 + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-}
-
-// Computes, for query tile i and key tile j (already in smem), P into sP and dS into sS (both [q][key]).
-__device__ __forceinline__ void attn_tile_p_ds(float (*sQ)[AB + 1], float (*sK)[AB + 1], float (*sV)[AB + 1],
-                                               float (*sdO)[AB + 1], float (*sP)[AB + 1], float (*sS)[AB + 1],
-                                               const float* s_lse, const float* s_D, int q_valid, int k_valid, float scale,
-                                               int ty, int tx) {
-  float s[4][4], dp[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.0f;
-  mm_nt(s, sQ, sK, ty, tx);     // S = Q K^T
-  mm_nt(dp, sdO, sV, ty, tx);   // dP = dO V^T
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = ty * 4 + i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = tx * 4 + j;
-      float pv = 0.0f, ds = 0.0f;
-      if (q < q_valid && k < k_valid) {
-        pv = expf(s[i][j] * scale - s_lse[q]);
-        ds = scale * pv * (dp[i][j] - s_D[q]);
-      }
-      sP[q][k] = pv;
-      sS[q][k] = ds;
-    }
-  }
-}
-
-constexpr int ATTN_BWD_SMEM = (6 * AB * (AB + 1) + 2 * AB) * sizeof(float);
-
-// grid (kv tiles, heads, images): dK_j, dV_j
-__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnBwdParams p) {
-  extern __shared__ float smf[];
-  float (*sQ)[AB + 1] = reinterpret_cast<float (*)[AB + 1]>(smf);
-  float (*sK)[AB + 1] = sQ + AB;
-  float (*sV)[AB + 1] = sK + AB;
-  float (*sdO)[AB + 1] = sV + AB;
-  float (*sP)[AB + 1] = sdO + AB;
-  float (*sS)[AB + 1] = sP + AB;
-  float* s_lse = reinterpret_cast<float*>(sS + AB);
-  float* s_D = s_lse + AB;
-  const int j = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int hd = p.heads * 64, ld3 = 3 * hd;
-  const long row0 = p.row_offset + static_cast<long>(img) * p.tokens;
-  const int k_valid = min(AB, p.tokens - j * AB);
-  load_tile_split(sK, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, hd + h * 64);
-  load_tile_split(sV, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, 2 * hd + h * 64);
-  float dk[4][4], dv[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) dk[a][b] = dv[a][b] = 0.0f;
-  const int q_tiles = (p.tokens + AB - 1) / AB;
-  for (int i = 0; i < q_tiles; ++i) {
-    const int q_valid = min(AB, p.tokens - i * AB);
-    __syncthreads();
-    load_tile_split(sQ, p.qkv_hi, p.qkv_lo, row0 + i * AB, q_valid, ld3, h * 64);
-    load_tile_f32(sdO, p.dO, row0 + i * AB, q_valid, hd, h * 64);
-    if (threadIdx.x < AB) {
-      const int q = threadIdx.x;
-      const long r = row0 + i * AB + q;
-      s_lse[q] = q < q_valid ? p.lse[r * p.heads + h] : 0.0f;
-      s_D[q] = q < q_valid ? p.Dvec[r * p.heads + h] : 0.0f;
-    }
-    __syncthreads();
-    attn_tile_p_ds(sQ, sK, sV, sdO, sP, sS, s_lse, s_D, q_valid, k_valid, p.scale, ty, tx);
-    __syncthreads();
-    mm_tn(dv, sP, sdO, ty, tx);  // dV[key][d] += sum_q P[q][key] dO[q][d]
-    mm_tn(dk, sS, sQ, ty, tx);   // dK[key][d] += sum_q dS[q][key] Q[q][d]
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int key = ty * 4 + a;
-    if (key >= k_valid) continue;
-    const long r = row0 + j * AB + key;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      p.dqkv[r * ld3 + hd + h * 64 + tx * 4 + b] = dk[a][b];
-      p.dqkv[r * ld3 + 2 * hd + h * 64 + tx * 4 + b] = dv[a][b];
-    }
-  }
-}
-
-// grid (q tiles, heads, images): dQ_i
-__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnBwdParams p) {
-  extern __shared__ float smf[];
-  float (*sQ)[AB + 1] = reinterpret_cast<float (*)[AB + 1]>(smf);
-  float (*sK)[AB + 1] = sQ + AB;
-  float (*sV)[AB + 1] = sK + AB;
-  float (*sdO)[AB + 1] = sV + AB;
-  float (*sP)[AB + 1] = sdO + AB;
-  float (*sS)[AB + 1] = sP + AB;
-  float* s_lse = reinterpret_cast<float*>(sS + AB);
-  float* s_D = s_lse + AB;
-  const int i = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int hd = p.heads * 64, ld3 = 3 * hd;
-  const long row0 = p.row_offset + static_cast<long>(img) * p.tokens;
-  const int q_valid = min(AB, p.tokens - i * AB);
-  load_tile_split(sQ, p.qkv_hi, p.qkv_lo, row0 + i * AB, q_valid, ld3, h * 64);
-  load_tile_f32(sdO, p.dO, row0 + i * AB, q_valid, hd, h * 64);
-  if (threadIdx.x < AB) {
-    const int q = threadIdx.x;
-    const long r = row0 + i * AB + q;
-    s_lse[q] = q < q_valid ? p.lse[r * p.heads + h] : 0.0f;
-    s_D[q] = q < q_valid ? p.Dvec[r * p.heads + h] : 0.0f;
-  }
-  float dq[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) dq[a][b] = 0.0f;
-  const int k_tiles = (p.tokens + AB - 1) / AB;
-  for (int j = 0; j < k_tiles; ++j) {
-    const int k_valid = min(AB, p.tokens - j * AB);
-    __syncthreads();
-    load_tile_split(sK, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, hd + h * 64);
-    load_tile_split(sV, p.qkv_hi, p.qkv_lo, row0 + j * AB, k_valid, ld3, 2 * hd + h * 64);
-    __syncthreads();
-    attn_tile_p_ds(sQ, sK, sV, sdO, sP, sS, s_lse, s_D, q_valid, k_valid, p.scale, ty, tx);
-    __syncthreads();
-    mm_nn(dq, sS, sK, ty, tx);  // dQ[q][d] += sum_key dS[q][key] K[key][d]
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int q = ty * 4 + a;
-    if (q >= q_valid) continue;
-    const long r = row0 + i * AB + q;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) p.dqkv[r * ld3 + h * 64 + tx * 4 + b] = dq[a][b];
-  }
-}
-
 static RowMap make_map(int tokens, int np, int first) {
   RowMap m;
   m.tokens = tokens; m.np = np > 0 ? np : 1; m.first = first;
@@ -626,36 +387,6 @@ extern "C" int dupl_gmp_classify_bwd(const float* x, const float* w, const float
   DUPL_LAUNCH_OK();
   const long inner = static_cast<long>(K) * D;
   sum_over_first_kernel<<<static_cast<int>((inner + 255) / 256), 256, 0, st>>>(dw_partial, B, inner, dw);
-  DUPL_LAUNCH_OK();
-  return DUPL_OK;
-}
-
-extern "C" int dupl_attention_bwd(const dupl_attention_bwd_args* a, void* stream) {
-  DUPL_CHECK_ARG(a != nullptr, "dupl_attention_bwd: args is NULL");
-  DUPL_CHECK_ARG(a->qkv_hi && a->qkv_lo && a->o_hi && a->o_lo && a->dO && a->lse && a->Dvec && a->dqkv,
-                 "dupl_attention_bwd: NULL pointer");
-  DUPL_CHECK_ARG(a->batch > 0 && a->tokens > 0 && a->heads > 0, "dupl_attention_bwd: bad shape");
-  AttnBwdParams p;
-  p.qkv_hi = static_cast<const __nv_bfloat16*>(a->qkv_hi);
-  p.qkv_lo = static_cast<const __nv_bfloat16*>(a->qkv_lo);
-  p.o_hi = static_cast<const __nv_bfloat16*>(a->o_hi);
-  p.o_lo = static_cast<const __nv_bfloat16*>(a->o_lo);
-  p.dO = a->dO; p.lse = a->lse; p.Dvec = a->Dvec; p.dqkv = a->dqkv;
-  p.tokens = a->tokens; p.row_offset = a->row_offset; p.heads = a->heads; p.scale = a->scale;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
-    DUPL_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM));
-    attr_set = true;
-  }
-  const int rows = a->batch * a->tokens;
-  attn_bwd_d_kernel<<<cdiv(rows * a->heads, 8), 256, 0, st>>>(p, rows);
-  DUPL_LAUNCH_OK();
-  dim3 grid(cdiv(a->tokens, AB), a->heads, a->batch);
-  attn_bwd_dkv_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(p);
-  DUPL_LAUNCH_OK();
-  attn_bwd_dq_kernel<<<grid, 256, ATTN_BWD_SMEM, st>>>(p);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

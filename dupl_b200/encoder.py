@@ -55,9 +55,25 @@ class StudentPlanes:
         hit = self._planes.get(name)
         if hit is None or hit[0] != key:
             w = p.detach().reshape(p.shape[0], -1)
-            hit = (key, ops.split_bf16(w))
+            if hit is not None and hit[1][0].device == p.device:
+                ops.split_bf16(w, out=hit[1])   # refresh in place: plane addresses stay valid (CUDA graphs hold them)
+                hit = (key, hit[1])
+            else:
+                hit = (key, ops.split_bf16(w))
             self._planes[name] = hit
         return hit[1]
+
+    def refresh_all(self):
+        """Re-splits every GEMM weight into its (persistent) planes unconditionally.  Called inside a CUDA-graph
+        capture so that each replay picks up the weights the optimizer wrote since the previous one."""
+        for name in self.GEMM_WEIGHTS:
+            p = self._params()[name]
+            hit = self._planes.get(name)
+            w = p.detach().reshape(p.shape[0], -1)
+            if hit is None:
+                self._planes[name] = ((p.data_ptr(), p._version), ops.split_bf16(w))
+            else:
+                ops.split_bf16(w, out=hit[1])
 
     def plane_t(self, name):
         """Transposed planes [K, N] of a Linear weight [N, K] (B operand of the dgrad GEMM), cached like plane()."""

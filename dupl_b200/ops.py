@@ -28,11 +28,14 @@ def make_segments(shapes):
 
 
 # ------------------------------------------------------------------ dense path
-def split_bf16(x):
+def split_bf16(x, out=None):
     L.require_cuda(x)
     x = L.f32c(x)
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi)
+    if out is not None:
+        hi, lo = out
+    else:
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
     L.check(L.lib().dupl_split_bf16(L.ptr(x), L.ptr(hi), L.ptr(lo), x.numel(), L.stream_ptr(x.device)), "dupl_split_bf16")
     return hi, lo
 

@@ -261,13 +261,16 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
         dpl, dt = split_transpose(d_tok, M, D)
         grads["encoder." + bp + "attn.proj.bias"] = colsum(d_tok, M, D)
         grads["encoder." + bp + "attn.proj.weight"] = wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad)
-        d_att = dgrad(dpl, pl.plane_t(bp + "attn.proj.weight"), M, D, D)
+        bfk = dict(dtype=torch.bfloat16, device=dev)
+        d_att = (torch.empty(M, D, **bfk), torch.empty(M, D, **bfk))     # dO as split planes: operand of the attention backward
+        ops.gemm_bf16x3([dict(a=dpl, w=pl.plane_t(bp + "attn.proj.weight"), out=d_att)], M, D, D, L.EPI_SPLIT)
         d_qkv = torch.empty(M, 3 * D, **f32)
         a = L.AttentionBwdArgs()
         a.qkv_hi, a.qkv_lo, a.o_hi, a.o_lo = b.qkv[0].data_ptr(), b.qkv[1].data_ptr(), b.att[0].data_ptr(), b.att[1].data_ptr()
+        a.do_hi, a.do_lo = d_att[0].data_ptr(), d_att[1].data_ptr()
         dvec = torch.empty(M, E.HEADS, **f32)
-        a.dO, a.lse, a.Dvec, a.dqkv = d_att.data_ptr(), b.lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
-        a.batch, a.tokens, a.row_offset, a.heads, a.scale = B, N, 0, E.HEADS, scale
+        a.lse, a.Dvec, a.dqkv = b.lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
+        a.M, a.batch, a.tokens, a.row_offset, a.heads, a.scale = M, B, N, 0, E.HEADS, scale
         L.check(L.lib().dupl_attention_bwd(C.byref(a), _st(dev)), "dupl_attention_bwd")
         dpl, dt = split_transpose(d_qkv, M, 3 * D)
         grads["encoder." + bp + "attn.qkv.bias"] = colsum(d_qkv, M, 3 * D)

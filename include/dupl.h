@@ -299,18 +299,20 @@ int dupl_nchw_to_rows_add(const float* src, float* dst, int32_t B, int32_t np, i
 int dupl_gmp_classify_bwd(const float* x, const float* w, const float* dlogits, const int32_t* argmax, float* dx,
                           float* dw_partial, float* dw, int32_t B, int32_t np, int32_t D, int32_t K, int32_t ld,
                           int32_t tokens, int32_t first, void* stream);
-/* Attention backward for one segment (vit.py:120-135): from the forward's qkv / output planes, lse and the
- * gradient dO fp32 [M, heads*64] -> dqkv fp32 [M, 3*heads*64].  Dvec: scratch [M, heads]. */
+/* Attention backward for one segment (vit.py:120-135) on tcgen05: from the forward's qkv / output planes, lse and
+ * the gradient dO (split-bf16 planes [M, heads*64]) -> dqkv fp32 [M, 3*heads*64].  Dvec: scratch [M, heads].
+ * M = number of rows of the planes (bounds the TMA tensor maps). */
 typedef struct {
   const void* qkv_hi;
   const void* qkv_lo;
   const void* o_hi;
   const void* o_lo;
-  const float* dO;
+  const void* do_hi;
+  const void* do_lo;
   const float* lse;
   float* Dvec;
   float* dqkv;
-  int32_t batch, tokens, row_offset, heads;
+  int32_t M, batch, tokens, row_offset, heads;
   float scale;
 } dupl_attention_bwd_args;
 
