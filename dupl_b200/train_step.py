@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .model.losses import get_masked_ptc_loss, get_seg_loss
 from .model.PAR import PAR
-from .pipeline import denormalize_img2
+from .pipeline import CamParStep, denormalize_img2
 from .utils import cam_helper
 
 VOC_HIGH_THRES_TARGET = (0.70, 0.70, 0.70, 0.70, 0.55, 0.55, 0.55, 0.55, 0.70, 0.55,
@@ -92,27 +92,29 @@ def make_optimizer(model, args=Args):
 
 
 class PhaseBStep:
-    def __init__(self, model, optim=None, args=Args, device=None):
+    def __init__(self, model, optim=None, args=Args, device=None, graph=True):
         self.model = model          # siamese_network or DistributedDataParallel(siamese_network)
         self.optim = optim
         self.args = args
         dev = device or next(model.parameters()).device
         self.par = PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24]).to(dev)
+        # the no-grad half of the step (MS-CAM of both students + PAR refinement) replayed as one CUDA graph
+        self.pseudo = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph)
+        self.pseudo.par = self.par
         self.thres_start = torch.ones(20, device=dev) * args.high_thre
         self.thres_target = torch.tensor(VOC_HIGH_THRES_TARGET, device=dev)
 
     def losses(self, inputs, cls_label, img_box, n_iter):
         a = self.args
         model = self.model
-        inputs_denorm = denormalize_img2(inputs.clone())
         b, _, h, w = inputs.shape
         # per-image high threshold = max over the present classes of the cosine-annealed class thresholds
         thres = cosine_descent(self.thres_start, self.thres_target, n_iter - a.cam_iters, a.max_iters - a.cam_iters)
         high_thres = torch.where(cls_label > 0, thres[None, :], thres.new_full((), -math.inf)).amax(1)
-        high_thres_mask = high_thres.reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
 
-        cams_1, cams_aux_1 = cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=a.cam_scales, branch=1)
-        cams_2, cams_aux_2 = cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=a.cam_scales, branch=2)
+        # multi_scale_cam2_siamese x2 and refine_cams_with_dynamic_thres x2 (train_final_voc.py:279-284, 330-343).
+        # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels).
+        label_1, label_2, (cams_1, cams_aux_1), (cams_2, cams_aux_2) = self.pseudo(inputs, cls_label, img_box, high_thres)
         res = model(inputs)
         cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
         cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
@@ -128,11 +130,6 @@ class PhaseBStep:
                                                             ignore_index=a.ignore_index)
             ptc_loss = ptc_loss + get_masked_ptc_loss(fmap, cam_helper.label_to_aff_mask(pseudo))
 
-        kw = dict(cls_labels=cls_label, high_thre_map=high_thres_mask, low_thre=a.low_thre, ignore_index=a.ignore_index,
-                  img_box=img_box)
-        # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels)
-        label_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1.detach(), **kw)
-        label_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2.detach(), **kw)
         segs_1 = F.interpolate(segs_1, size=label_1.shape[1:], mode="bilinear", align_corners=False)
         segs_2 = F.interpolate(segs_2, size=label_2.shape[1:], mode="bilinear", align_corners=False)
         seg_loss = get_seg_loss(segs_1, label_2.type(torch.long)) + get_seg_loss(segs_2, label_1.type(torch.long))
