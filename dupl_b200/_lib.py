@@ -100,7 +100,7 @@ _PROTOTYPES = {
                                        C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "dupl_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
     "dupl_rows_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
-    "dupl_gmp_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
+    "dupl_gmp_classify": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 7 + [C.c_void_p]),
     "dupl_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "dupl_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Segment), C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -118,8 +118,8 @@ _PROTOTYPES = {
                                      C.c_int32, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_void_p]),
     "dupl_refine_prologue": (C.c_int, [C.POINTER(RefinePrologueArgs), C.c_void_p]),
     "dupl_refine_epilogue": (C.c_int, [C.POINTER(RefineEpilogueArgs), C.c_void_p]),
-    "dupl_split_transpose": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
-    "dupl_transpose_plane": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dupl_split_transpose": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3),
+    "dupl_transpose_planes": (C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 6 + [C.c_void_p] * 2 + [C.c_int32, C.c_void_p]),
     "dupl_colsum": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
     "dupl_layernorm_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "dupl_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -131,6 +131,8 @@ _PROTOTYPES = {
     "dupl_seg_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dupl_seg_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]),
+    "dupl_seg_loss_up_fwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_int64] + [C.c_void_p] * 4),
+    "dupl_seg_loss_up_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_int64, C.c_void_p, C.c_void_p]),
     "dupl_ptc_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "dupl_ptc_loss_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3),
     "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,

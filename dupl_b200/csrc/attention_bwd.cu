@@ -20,7 +20,7 @@ namespace dupl {
 constexpr int AB_THREADS = 128;
 constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
 constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
-constexpr int AB_SMEM = 4 * AB_T128 + 8 * AB_T64 + 1024 + 256;  // 128 KB + barriers
+constexpr int AB_SMEM = 4 * AB_T128 + 8 * AB_T64 + 1024 + 2048;  // 128 KB + alignment slack + barriers / per-tile statistics
 
 struct AttnBwdTcParams {
   CUtensorMap tm_qkv128_hi, tm_qkv128_lo, tm_qkv64_hi, tm_qkv64_lo;  // [M, 3*heads*64] planes, boxes of 128 / 64 rows
@@ -214,6 +214,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   uint64_t* bar_s = bars + 3;
   uint64_t* bar_d = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  // per 64-query tile: lse * log2(e) (+inf on padding rows) | D, double-buffered; [stage][0:64 lse2, 64:128 D]
+  float* s_stat = reinterpret_cast<float*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int kt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -263,8 +265,20 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   const uint64_t dKh = umma_desc_sw128(smem_u32(sK)), dKl = umma_desc_sw128(smem_u32(sK + AB_T128));
   const uint64_t dVh = umma_desc_sw128(smem_u32(sV)), dVl = umma_desc_sw128(smem_u32(sV + AB_T128));
 
+  // thread t < 64 fetches lse of query t of a tile, thread 64 + t its D (one coalesced-ish load per thread and tile,
+  // issued one tile ahead; the tile loop then reads them as shared-memory broadcasts)
+  auto fetch_stat = [&](int i) -> float {
+    const int q = i * 64 + (tid & 63);
+    if (q >= p.tokens) return tid < 64 ? __int_as_float(0x7f800000) : 0.0f;
+    const long r = (static_cast<long>(row0) + q) * p.heads + head;
+    return tid < 64 ? p.lse[r] * 1.44269504088896340736f : p.Dvec[r];
+  };
+  s_stat[tid] = fetch_stat(0);
+  __syncthreads();
+
   for (int i = 0; i < n_q; ++i) {
     const int st = i & 1;
+    const float stat_next = (i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
     const uint32_t ph = static_cast<uint32_t>(i & 1), q_ph = static_cast<uint32_t>((i >> 1) & 1);
     const uint64_t dQh = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64)), dQl = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64 + AB_T64));
     const uint64_t dOh = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64)), dOl = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64 + AB_T64));
@@ -281,21 +295,23 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     float s[64], dp[64];
     load_row64(tm + TM_ST + lane_base, s);
     load_row64(tm + TM_DPT + lane_base, dp);
-    const int q_valid = p.tokens - i * 64;
-    const float* lse_t = p.lse + (static_cast<long>(row0) + i * 64) * p.heads + head;
-    const float* D_t = p.Dvec + (static_cast<long>(row0) + i * 64) * p.heads + head;
+    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + st * 128);
+    const float kscale = k_ok ? p.scale : 0.0f;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      float pv = 0.0f, ds = 0.0f;
-      if (k_ok && c < q_valid) {
-        pv = fast_exp2(fmaf(s[c], c2, -__ldg(lse_t + c * p.heads) * 1.44269504088896340736f));
-        ds = p.scale * pv * (dp[c] - __ldg(D_t + c * p.heads));
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 l4 = stat4[c4], d4 = stat4[16 + c4];
+      const float l[4] = {l4.x, l4.y, l4.z, l4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c4 * 4 + e;
+        const float pv = k_ok ? fast_exp2(fmaf(s[c], c2, -l[e])) : 0.0f;  // padding queries: lse2 = +inf -> 0
+        s[c] = pv;
+        dp[c] = kscale * pv * (dp[c] - d[e]);
       }
-      s[c] = pv;
-      dp[c] = ds;
     }
     store_split_row(tm + TM_PT + lane_base, s);
     store_split_row(tm + TM_DST + lane_base, dp);
+    s_stat[(st ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier below, last turn)
     tc_wait_st();
     tc_fence_before();
     __syncthreads();

@@ -66,32 +66,52 @@ __global__ void __launch_bounds__(256) rows_to_nchw_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 // Global max pool over the patch tokens of each image + bias-free 1x1 classifier:
 // logits[b][k] = sum_d (max_p x[row(b,p)][d]) * w[k][d]      (model_dupl.py:88-95)
-// One block per image; arg-max rows are kept for the backward pass when `argmax` != NULL.
+// Two launches: max-pool with grid (D/32, B) into `pooled` [B][D] (8 row lanes per column, first maximum wins like
+// F.adaptive_max_pool2d; arg-max rows kept for the backward pass when `argmax` != NULL), then one block per image
+// for the K dot products.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gmp_classify_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           float* __restrict__ logits, int* __restrict__ argmax, int np,
-                                                           int D, int K, int row_offset, int row_stride, int first) {
-  extern __shared__ float pooled[];
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(256) gmp_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled,
+                                                       int* __restrict__ argmax, int np, int D, int row_offset, int row_stride,
+                                                       int first) {
+  __shared__ float s_best[8][33];
+  __shared__ int s_arg[8][33];
+  const int b = blockIdx.y, d = blockIdx.x * 32 + threadIdx.x;
   const long row0 = row_offset + static_cast<long>(b) * row_stride + first;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float best = -INFINITY;
-    int arg = 0;
-    for (int p = 0; p < np; ++p) {
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  if (d < D)
+    for (int p = threadIdx.y; p < np; p += 8) {
       const float v = __ldg(x + (row0 + p) * D + d);
-      if (v > best) {  // first maximum, like F.adaptive_max_pool2d
+      if (v > best || arg == 0x7fffffff) {
         best = v;
         arg = p;
       }
     }
-    pooled[d] = best;
+  s_best[threadIdx.y][threadIdx.x] = best;
+  s_arg[threadIdx.y][threadIdx.x] = arg;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float v = s_best[k][threadIdx.x];
+      const int a = s_arg[k][threadIdx.x];
+      if (v > best || (v == best && a < arg)) {
+        best = v;
+        arg = a;
+      }
+    }
+    pooled[static_cast<long>(b) * D + d] = best;
     if (argmax != nullptr) argmax[static_cast<long>(b) * D + d] = arg;
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gmp_logits_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
+                                                         float* __restrict__ logits, int D, int K) {
+  const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int k = warp; k < K; k += nwarps) {
     float acc = 0.0f;
-    for (int d = lane; d < D; d += 32) acc = fmaf(pooled[d], __ldg(w + static_cast<long>(k) * D + d), acc);
+    for (int d = lane; d < D; d += 32) acc = fmaf(pooled[static_cast<long>(b) * D + d], __ldg(w + static_cast<long>(k) * D + d), acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) logits[static_cast<long>(b) * K + k] = acc;
@@ -129,12 +149,14 @@ extern "C" int dupl_rows_to_nchw(const float* src, float* out, int32_t B, int32_
   return DUPL_OK;
 }
 
-extern "C" int dupl_gmp_classify(const float* x, const float* w, float* logits, int32_t* argmax, int32_t B, int32_t np,
-                                 int32_t D, int32_t K, int32_t row_offset, int32_t row_stride, int32_t first, void* stream) {
-  DUPL_CHECK_ARG(x && w && logits && B > 0 && np > 0 && D > 0 && K > 0, "dupl_gmp_classify: bad arguments");
-  DUPL_CHECK_ARG(D * sizeof(float) <= 48 * 1024, "dupl_gmp_classify: D=%d too large", D);
-  gmp_classify_kernel<<<B, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, w, logits, argmax, np, D, K,
-                                                                                      row_offset, row_stride, first);
+extern "C" int dupl_gmp_classify(const float* x, const float* w, float* logits, float* pooled, int32_t* argmax, int32_t B,
+                                 int32_t np, int32_t D, int32_t K, int32_t row_offset, int32_t row_stride, int32_t first,
+                                 void* stream) {
+  DUPL_CHECK_ARG(x && w && logits && pooled && B > 0 && np > 0 && D > 0 && K > 0, "dupl_gmp_classify: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gmp_pool_kernel<<<dim3(cdiv(D, 32), B), dim3(32, 8), 0, st>>>(x, pooled, argmax, np, D, row_offset, row_stride, first);
+  DUPL_LAUNCH_OK();
+  gmp_logits_kernel<<<B, 256, 0, st>>>(pooled, w, logits, D, K);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -5,6 +5,7 @@
 // bit-reproducible.  The Gram is computed in fp32 on the CUDA cores (0.94 GFLOP per image): exact
 // rather than fast; it is < 1 % of the step.
 #include "common.cuh"
+#include "resample.cuh"
 
 namespace dupl {
 
@@ -94,6 +95,133 @@ __global__ void __launch_bounds__(256) seg_ce_bwd_kernel(const float* __restrict
     float g = 0.0f;
     if (w != 0.0f) g = w * (expf(__ldg(x + c * hw) - l) - (c == lab ? 1.0f : 0.0f));
     d[c * hw] = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg loss on bilinearly up-sampled logits (train_final_voc.py:345-352: F.interpolate(segs, size=label.shape[1:],
+// mode='bilinear', align_corners=False) followed by get_seg_loss) without materialising the [b,C,H,W] logits:
+// forward samples the low-resolution logits per label pixel (online soft-max), backward is a gather per
+// low-resolution cell over the label pixels whose bilinear footprint contains it (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seg_up_fwd_kernel(const float* __restrict__ pred, const long long* __restrict__ label,
+                                                         int C, int h, int w, int H, int W, float sy, float sx,
+                                                         long long ignore, float* __restrict__ lse_out,
+                                                         float* __restrict__ partials) {
+  __shared__ float sh[8];
+  const int b = blockIdx.z;
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  float bg_loss = 0.0f, fg_loss = 0.0f, bg_cnt = 0.0f, fg_cnt = 0.0f;
+  const float* base = pred + static_cast<long>(b) * C * h * w;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int Y = blockIdx.y * 32 + (threadIdx.x >> 5) + 8 * k;
+    if (X >= W || Y >= H) continue;
+    const Lin ly = lin_coord(Y, h, sy), lx = lin_coord(X, w, sx);
+    const long i = (static_cast<long>(b) * H + Y) * W + X;
+    const long long lab = label[i];
+    float mx = -INFINITY, sum = 0.0f, picked = 0.0f;
+    for (int c = 0; c < C; ++c) {
+      const float v = bilerp(base + static_cast<long>(c) * h * w, w, ly, lx);
+      if (c == lab) picked = v;
+      const float m2 = fmaxf(mx, v);
+      sum = sum * expf(mx - m2) + expf(v - m2);
+      mx = m2;
+    }
+    const float lse = mx + logf(sum);
+    lse_out[i] = lse;
+    if (lab != ignore && lab >= 0 && lab < C) {
+      if (lab == 0) {
+        bg_loss += lse - picked;
+        bg_cnt += 1.0f;
+      } else {
+        fg_loss += lse - picked;
+        fg_cnt += 1.0f;
+      }
+    }
+  }
+  const int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  float r;
+  r = block_sum(bg_loss, sh); if (threadIdx.x == 0) partials[4 * blk + 0] = r;
+  r = block_sum(fg_loss, sh); if (threadIdx.x == 0) partials[4 * blk + 1] = r;
+  r = block_sum(bg_cnt, sh);  if (threadIdx.x == 0) partials[4 * blk + 2] = r;
+  r = block_sum(fg_cnt, sh);  if (threadIdx.x == 0) partials[4 * blk + 3] = r;
+}
+
+constexpr int SEGUP_PPT = 4;       // label pixels per thread and chunk in the backward gather
+constexpr int SEGUP_MAXC = 96;
+// one block per low-resolution cell (x, y, b)
+__global__ void __launch_bounds__(256) seg_up_bwd_kernel(const float* __restrict__ pred, const long long* __restrict__ label,
+                                                         const float* __restrict__ lse, const float* __restrict__ stats,
+                                                         const float* __restrict__ grad_out, int C, int h, int w, int H, int W,
+                                                         float sy, float sx, int fy, int fx, long long ignore,
+                                                         float* __restrict__ dpred) {
+  __shared__ float nb[SEGUP_MAXC * 9];     // logits of the 3x3 neighbourhood [c][dy][dx] (clamped at the border)
+  __shared__ float red[SEGUP_MAXC * 8];
+  const int cx = blockIdx.x, cy = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* base = pred + static_cast<long>(b) * C * h * w;
+  for (int i = tid; i < C * 9; i += 256) {
+    const int c = i / 9, dy = (i % 9) / 3, dx = i % 3;
+    const int yy = min(max(cy - 1 + dy, 0), h - 1), xx = min(max(cx - 1 + dx, 0), w - 1);
+    nb[i] = __ldg(base + (static_cast<long>(c) * h + yy) * w + xx);
+  }
+  // candidate label pixels: rows [Y0, Y0 + fy), columns [X0, X0 + fx) (a superset of the footprint; tested below)
+  const int Y0 = max(static_cast<int>(floorf((cy - 1 + 0.5f) / sy - 0.5f)) - 1, 0);
+  const int X0 = max(static_cast<int>(floorf((cx - 1 + 0.5f) / sx - 0.5f)) - 1, 0);
+  const float gw_bg = 0.5f / (stats[2] + 1e-6f) * grad_out[0], gw_fg = 0.5f / (stats[3] + 1e-6f) * grad_out[0];
+
+  for (int i = tid; i < C * 8; i += 256) red[i] = 0.0f;
+  __syncthreads();
+  for (int q0 = 0; q0 < fy * fx; q0 += 256 * SEGUP_PPT) {
+    float wgt[SEGUP_PPT], l_y0[SEGUP_PPT], l_y1[SEGUP_PPT], l_x0[SEGUP_PPT], l_x1[SEGUP_PPT], lsev[SEGUP_PPT];
+    int idx[SEGUP_PPT], lab[SEGUP_PPT];  // idx packs the neighbourhood offsets y0 | y1 << 2 | x0 << 4 | x1 << 6
+#pragma unroll
+    for (int k = 0; k < SEGUP_PPT; ++k) {
+      wgt[k] = 0.0f; l_y0[k] = l_y1[k] = l_x0[k] = l_x1[k] = lsev[k] = 0.0f; idx[k] = 0; lab[k] = -1;
+      const int q = q0 + tid + 256 * k;
+      if (q >= fy * fx) continue;
+      const int Y = Y0 + q / fx, X = X0 + q % fx;
+      if (Y >= H || X >= W) continue;
+      const Lin ly = lin_coord(Y, h, sy), lx = lin_coord(X, w, sx);
+      if ((ly.i0 != cy && ly.i1 != cy) || (lx.i0 != cx && lx.i1 != cx)) continue;
+      float wy = 0.0f, wx = 0.0f;
+      if (ly.i0 == cy) wy += ly.l0;
+      if (ly.i1 == cy) wy += ly.l1;
+      if (lx.i0 == cx) wx += lx.l0;
+      if (lx.i1 == cx) wx += lx.l1;
+      const long i = (static_cast<long>(b) * H + Y) * W + X;
+      const long long lb = label[i];
+      if (lb == ignore || lb < 0 || lb >= C) continue;
+      wgt[k] = wy * wx * (lb == 0 ? gw_bg : gw_fg);
+      lab[k] = static_cast<int>(lb);
+      lsev[k] = lse[i];
+      l_y0[k] = ly.l0; l_y1[k] = ly.l1; l_x0[k] = lx.l0; l_x1[k] = lx.l1;
+      idx[k] = (ly.i0 - cy + 1) | ((ly.i1 - cy + 1) << 2) | ((lx.i0 - cx + 1) << 4) | ((lx.i1 - cx + 1) << 6);
+    }
+    for (int c = 0; c < C; ++c) {
+      const float* n = nb + c * 9;
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < SEGUP_PPT; ++k) {
+        if (lab[k] < 0) continue;
+        const int y0 = idx[k] & 3, y1 = (idx[k] >> 2) & 3, x0 = (idx[k] >> 4) & 3, x1 = (idx[k] >> 6) & 3;
+        const float t0 = __fmaf_rn(l_x0[k], n[y0 * 3 + x0], __fmul_rn(l_x1[k], n[y0 * 3 + x1]));
+        const float t1 = __fmaf_rn(l_x0[k], n[y1 * 3 + x0], __fmul_rn(l_x1[k], n[y1 * 3 + x1]));
+        const float v = __fmaf_rn(l_y0[k], t0, __fmul_rn(l_y1[k], t1));
+        acc += wgt[k] * (expf(v - lsev[k]) - (c == lab[k] ? 1.0f : 0.0f));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) red[c * 8 + warp] += acc;  // slot owned by this warp's lane 0
+    }
+  }
+  __syncthreads();
+  if (tid < C) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[tid * 8 + k];
+    dpred[((static_cast<long>(b) * C + tid) * h + cy) * w + cx] = t;
   }
 }
 
@@ -308,6 +436,35 @@ extern "C" int dupl_seg_loss_bwd(const float* pred, const int64_t* label, const 
   const long hw = static_cast<long>(H) * W, total = hw * b;
   seg_ce_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       pred, reinterpret_cast<const long long*>(label), lse, stats, grad_out, C, hw, total, ignore_index, dpred);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_seg_loss_up_fwd(const float* pred, const int64_t* label, int32_t b, int32_t C, int32_t h, int32_t w,
+                                    int32_t H, int32_t W, int64_t ignore_index, float* lse, float* partials, float* stats,
+                                    void* stream) {
+  DUPL_CHECK_ARG(pred && label && lse && partials && stats && b > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0,
+                 "dupl_seg_loss_up_fwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(cdiv(W, 32), cdiv(H, 32), b);
+  seg_up_fwd_kernel<<<grid, 256, 0, st>>>(pred, reinterpret_cast<const long long*>(label), C, h, w, H, W,
+                                          static_cast<float>(h) / H, static_cast<float>(w) / W, ignore_index, lse, partials);
+  DUPL_LAUNCH_OK();
+  seg_ce_finish_kernel<<<1, 256, 0, st>>>(partials, static_cast<int>(grid.x * grid.y * grid.z), stats);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_seg_loss_up_bwd(const float* pred, const int64_t* label, const float* lse, const float* stats,
+                                    const float* grad_out, int32_t b, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W,
+                                    int64_t ignore_index, float* dpred, void* stream) {
+  DUPL_CHECK_ARG(pred && label && lse && stats && grad_out && dpred, "dupl_seg_loss_up_bwd: NULL pointer");
+  DUPL_CHECK_ARG(C <= SEGUP_MAXC, "dupl_seg_loss_up_bwd: C=%d > %d", C, SEGUP_MAXC);
+  // label pixels that can touch one low-resolution cell: source coordinate within (c-1, c+1) -> 2/scale (+ slack)
+  const int fy = min(H, static_cast<int>(2.0f * H / h) + 4), fx = min(W, static_cast<int>(2.0f * W / w) + 4);
+  seg_up_bwd_kernel<<<dim3(w, h, b), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, reinterpret_cast<const long long*>(label), lse, stats, grad_out, C, h, w, H, W, static_cast<float>(h) / H,
+      static_cast<float>(w) / W, fy, fx, ignore_index, dpred);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -25,17 +25,25 @@ struct RowMap {
   }
 };
 
+// 64-row x 32-column tile per block (8 warps x 8 rows).  Optionally also leaves the tile's column sums in
+// colsum_ws[tile_row][c] (bias gradients: summed over tile rows by colsum_finish_kernel, fixed order).
 __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, int R, int Cc, int ld, RowMap map,
                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                               __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
-                                                              int Rpad) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
+                                                              int Rpad, float* __restrict__ colsum_ws) {
+  __shared__ float tile[64][33];
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const int c = c0 + lane;
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = warp * 8 + i, r = r0 + rr;
     float v = 0.0f;
     if (r < R && c < Cc) v = src[map(r) * ld + c];
-    tile[i][threadIdx.x] = v;
+    tile[rr][lane] = v;
+    acc += v;
     if (hi != nullptr && r < R && c < Cc) {
       __nv_bfloat16 h, l;
       split_bf16(v, h, l);
@@ -43,32 +51,62 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
       lo[static_cast<long>(r) * Cc + c] = l;
     }
   }
+  if (colsum_ws != nullptr) part[warp][lane] = acc;
   __syncthreads();
+  if (colsum_ws != nullptr && warp == 0 && c < Cc) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    colsum_ws[static_cast<long>(blockIdx.x) * Cc + c] = t;
+  }
   if (t_hi != nullptr) {
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + threadIdx.x;
-      if (c < Cc && r < Rpad) {
-        __nv_bfloat16 h, l;
-        split_bf16(tile[threadIdx.x][i], h, l);  // rows >= R were loaded as 0 -> zero padding
-        t_hi[static_cast<long>(c) * Rpad + r] = h;
-        t_lo[static_cast<long>(c) * Rpad + r] = l;
+    const int rr = 2 * lane, r = r0 + rr;  // Rpad is even: r < Rpad implies r + 1 < Rpad; rows >= R were loaded as 0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cc = warp * 4 + i, co = c0 + cc;
+      if (co < Cc && r < Rpad) {
+        uint32_t h2, l2;
+        split2_bf16(tile[rr][cc], tile[rr + 1][cc], h2, l2);
+        *reinterpret_cast<uint32_t*>(t_hi + static_cast<long>(co) * Rpad + r) = h2;
+        *reinterpret_cast<uint32_t*>(t_lo + static_cast<long>(co) * Rpad + r) = l2;
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(256) transpose_u16_kernel(const unsigned short* __restrict__ in, int R, int Cc, int ld,
-                                                            RowMap map, unsigned short* __restrict__ out, int Rpad) {
-  __shared__ unsigned short tile[32][34];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[map(r) * ld + c] : static_cast<unsigned short>(0);
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ ws, int ntiles, int Cc,
+                                                            float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= Cc) return;
+  float t = 0.0f;
+  for (int k = 0; k < ntiles; ++k) t += ws[static_cast<long>(k) * Cc + c];
+  out[c] = t;
+}
+
+// transposes one or two bf16 planes (blockIdx.z); 64 x 64 tiles, 32-bit global accesses on both sides
+__global__ void __launch_bounds__(256) transpose_u16_kernel(const unsigned short* __restrict__ in0,
+                                                            const unsigned short* __restrict__ in1, int R, int Cc, int ld,
+                                                            RowMap map, unsigned short* __restrict__ out0,
+                                                            unsigned short* __restrict__ out1, int Rpad) {
+  __shared__ unsigned short tile_t[64][66];  // [column][row]
+  const unsigned short* __restrict__ in = blockIdx.z ? in1 : in0;
+  unsigned short* __restrict__ out = blockIdx.z ? out1 : out0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = warp * 8 + i, r = r0 + rr, c = c0 + 2 * lane;
+    uint32_t v = 0;
+    if (r < R && c < Cc) v = *reinterpret_cast<const uint32_t*>(in + map(r) * ld + c);
+    tile_t[2 * lane][rr] = static_cast<unsigned short>(v & 0xffffu);
+    tile_t[2 * lane + 1][rr] = static_cast<unsigned short>(v >> 16);
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < Cc && r < Rpad) out[static_cast<long>(c) * Rpad + r] = tile[threadIdx.x][i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int cc = warp * 8 + i, c = c0 + cc, r = r0 + 2 * lane;
+    if (c < Cc && r < Rpad)
+      *reinterpret_cast<uint32_t*>(out + static_cast<long>(c) * Rpad + r) = *reinterpret_cast<const uint32_t*>(&tile_t[cc][2 * lane]);
   }
 }
 
@@ -299,26 +337,36 @@ static RowMap make_map(int tokens, int np, int first) {
 using namespace dupl;
 
 extern "C" int dupl_split_transpose(const float* src, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np,
-                                    int32_t first, void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, void* stream) {
+                                    int32_t first, void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad,
+                                    float* colsum_ws, float* colsum, void* stream) {
   DUPL_CHECK_ARG(src && R > 0 && Cc > 0 && ld >= Cc, "dupl_split_transpose: bad arguments");
   DUPL_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (t_hi == nullptr) == (t_lo == nullptr) && (hi || t_hi),
                  "dupl_split_transpose: planes must come in hi/lo pairs");
-  DUPL_CHECK_ARG(t_hi == nullptr || Rpad >= R, "dupl_split_transpose: Rpad=%d < R=%d", Rpad, R);
+  DUPL_CHECK_ARG(t_hi == nullptr || (Rpad >= R && Rpad % 2 == 0), "dupl_split_transpose: Rpad=%d must be even and >= R=%d", Rpad, R);
+  DUPL_CHECK_ARG((colsum_ws == nullptr) == (colsum == nullptr), "dupl_split_transpose: colsum needs its workspace");
   const int rows = t_hi ? Rpad : R;
-  dim3 grid(cdiv(rows, 32), cdiv(Cc, 32)), block(32, 8);
-  split_transpose_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, R, Cc, ld, make_map(tokens, np, first), static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo),
-      static_cast<__nv_bfloat16*>(t_hi), static_cast<__nv_bfloat16*>(t_lo), Rpad);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(cdiv(rows, 64), cdiv(Cc, 32));
+  split_transpose_kernel<<<grid, 256, 0, st>>>(src, R, Cc, ld, make_map(tokens, np, first), static_cast<__nv_bfloat16*>(hi),
+                                               static_cast<__nv_bfloat16*>(lo), static_cast<__nv_bfloat16*>(t_hi),
+                                               static_cast<__nv_bfloat16*>(t_lo), Rpad, colsum_ws);
   DUPL_LAUNCH_OK();
+  if (colsum != nullptr) {
+    colsum_finish_kernel<<<cdiv(Cc, 256), 256, 0, st>>>(colsum_ws, static_cast<int>(grid.x), Cc, colsum);
+    DUPL_LAUNCH_OK();
+  }
   return DUPL_OK;
 }
 
-extern "C" int dupl_transpose_plane(const void* in, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np,
-                                    int32_t first, void* out, int32_t Rpad, void* stream) {
-  DUPL_CHECK_ARG(in && out && R > 0 && Cc > 0 && ld >= Cc && Rpad >= R, "dupl_transpose_plane: bad arguments");
-  dim3 grid(cdiv(Rpad, 32), cdiv(Cc, 32)), block(32, 8);
-  transpose_u16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const unsigned short*>(in), R, Cc, ld, make_map(tokens, np, first), static_cast<unsigned short*>(out), Rpad);
+extern "C" int dupl_transpose_planes(const void* in_hi, const void* in_lo, int32_t R, int32_t Cc, int32_t ld, int32_t tokens,
+                                     int32_t np, int32_t first, void* out_hi, void* out_lo, int32_t Rpad, void* stream) {
+  DUPL_CHECK_ARG(in_hi && out_hi && (in_lo == nullptr) == (out_lo == nullptr) && R > 0 && Cc > 0 && ld >= Cc && Rpad >= R,
+                 "dupl_transpose_planes: bad arguments");
+  DUPL_CHECK_ARG(Cc % 2 == 0 && ld % 2 == 0 && Rpad % 2 == 0, "dupl_transpose_planes: Cc=%d, ld=%d, Rpad=%d must be even", Cc, ld, Rpad);
+  dim3 grid(cdiv(Rpad, 64), cdiv(Cc, 64), in_lo ? 2 : 1);
+  transpose_u16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned short*>(in_hi), static_cast<const unsigned short*>(in_lo), R, Cc, ld, make_map(tokens, np, first),
+      static_cast<unsigned short*>(out_hi), static_cast<unsigned short*>(out_lo), Rpad);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -16,16 +16,15 @@ DEPTH = 12
 LN_EPS = 1e-6  # deit.py:100
 
 
-def transpose_planes(planes, R, Cc):
-    """(hi, lo) [R, Cc] bf16 -> (hi^T, lo^T) [Cc, pad64(R)] (zero padded): pure data movement."""
+def transpose_planes(planes, R, Cc, tokens=0, np_=0, first=0):
+    """(hi, lo) [R (mapped rows), Cc] bf16 -> (hi^T, lo^T) [Cc, pad64(R)] (zero padded): pure data movement, one launch."""
     Rpad = (R + 63) // 64 * 64
-    out = []
-    for p in planes:
-        o = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=p.device)
-        L.check(L.lib().dupl_transpose_plane(L.ptr(p), R, Cc, p.shape[1], 0, 0, 0, L.ptr(o), Rpad, L.stream_ptr(p.device)),
-                "dupl_transpose_plane")
-        out.append(o)
-    return tuple(out)
+    hi, lo = planes
+    ohi = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=hi.device)
+    olo = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=hi.device)
+    L.check(L.lib().dupl_transpose_planes(L.ptr(hi), L.ptr(lo), R, Cc, hi.shape[1], tokens, np_, first, L.ptr(ohi), L.ptr(olo),
+                                          Rpad, L.stream_ptr(hi.device)), "dupl_transpose_planes")
+    return ohi, olo
 
 
 class StudentPlanes:

@@ -94,7 +94,8 @@ def gmp_classify(x, w, B, np_, row_offset, row_stride, first, want_argmax=False)
     K, D = w.shape
     logits = torch.empty(B, K, dtype=torch.float32, device=x.device)
     arg = torch.empty(B, D, dtype=torch.int32, device=x.device) if want_argmax else None
-    L.check(L.lib().dupl_gmp_classify(L.ptr(x), L.ptr(w), L.ptr(logits), L.ptr(arg), B, np_, D, K, row_offset, row_stride,
+    pooled = torch.empty(B, D, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dupl_gmp_classify(L.ptr(x), L.ptr(w), L.ptr(logits), L.ptr(pooled), L.ptr(arg), B, np_, D, K, row_offset, row_stride,
                                       first, L.stream_ptr(x.device)), "dupl_gmp_classify")
     return (logits, arg) if want_argmax else logits
 

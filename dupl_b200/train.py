@@ -28,31 +28,29 @@ def _st(dev):
     return L.stream_ptr(dev)
 
 
-def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0):
+def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0, want_colsum=False):
+    """fp32 rows -> (hi, lo) planes, transposed planes [Cc, pad64(R)] and (optionally, same pass) the column sums."""
     dev = src.device
     bf = dict(dtype=torch.bfloat16, device=dev)
     Rpad = _pad64(R)
-    hi = lo = thi = tlo = None
+    hi = lo = thi = tlo = ws = cs = None
     if want_planes:
         hi, lo = torch.empty(R, Cc, **bf), torch.empty(R, Cc, **bf)
     if want_t:
         thi, tlo = torch.empty(Cc, Rpad, **bf), torch.empty(Cc, Rpad, **bf)
+    if want_colsum:
+        ws = torch.empty(((Rpad if want_t else R) + 63) // 64 * Cc, dtype=torch.float32, device=dev)
+        cs = torch.empty(Cc, dtype=torch.float32, device=dev)
     L.check(L.lib().dupl_split_transpose(L.ptr(src), R, Cc, src.shape[1], tokens, np_, first, L.ptr(hi), L.ptr(lo),
-                                         L.ptr(thi), L.ptr(tlo), Rpad, _st(dev)), "dupl_split_transpose")
+                                         L.ptr(thi), L.ptr(tlo), Rpad, L.ptr(ws), L.ptr(cs), _st(dev)), "dupl_split_transpose")
+    if want_colsum:
+        return (hi, lo), (thi, tlo), cs
     return (hi, lo), (thi, tlo)
 
 
 def transpose_planes(planes, R, Cc, tokens=0, np_=0, first=0):
     """(hi, lo) [*, Cc] -> (hi^T, lo^T) [Cc, pad64(R)]"""
-    dev = planes[0].device
-    Rpad = _pad64(R)
-    out = []
-    for p in planes:
-        o = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=dev)
-        L.check(L.lib().dupl_transpose_plane(L.ptr(p), R, Cc, p.shape[1], tokens, np_, first, L.ptr(o), Rpad, _st(dev)),
-                "dupl_transpose_plane")
-        out.append(o)
-    return tuple(out)
+    return E.transpose_planes(planes, R, Cc, tokens, np_, first)
 
 
 def colsum(x, R, Cc, tokens=0, np_=0, first=0):
@@ -246,20 +244,17 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
             # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
             grads["aux_classifier.weight"] = _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_tok, S).reshape(K, D, 1, 1)
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
-        dpl, dt = split_transpose(d_tok, M, D)
-        grads["encoder." + bp + "mlp.fc2.bias"] = colsum(d_tok, M, D)
+        dpl, dt, grads["encoder." + bp + "mlp.fc2.bias"] = split_transpose(d_tok, M, D, want_colsum=True)
         grads["encoder." + bp + "mlp.fc2.weight"] = wgrad(dt, transpose_planes(b.hid, M, 4 * D), D, 4 * D, Mpad)
         d_hid = dgrad(dpl, pl.plane_t(bp + "mlp.fc2.weight"), M, 4 * D, D)
         L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid), L.ptr(b.h_pre), d_hid.numel(), _st(dev)), "dupl_gelu_bwd")
-        dpl, dt = split_transpose(d_hid, M, 4 * D)
-        grads["encoder." + bp + "mlp.fc1.bias"] = colsum(d_hid, M, 4 * D)
+        dpl, dt, grads["encoder." + bp + "mlp.fc1.bias"] = split_transpose(d_hid, M, 4 * D, want_colsum=True)
         grads["encoder." + bp + "mlp.fc1.weight"] = wgrad(dt, transpose_planes(b.xn2, M, D), 4 * D, D, Mpad)
         d_xn2 = dgrad(dpl, pl.plane_t(bp + "mlp.fc1.weight"), M, D, 4 * D)
         dg, db = layernorm_bwd(d_xn2, b.x_mid, pl.vec(bp + "norm2.weight"), d_tok)
         grads["encoder." + bp + "norm2.weight"], grads["encoder." + bp + "norm2.bias"] = dg, db
         # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-        dpl, dt = split_transpose(d_tok, M, D)
-        grads["encoder." + bp + "attn.proj.bias"] = colsum(d_tok, M, D)
+        dpl, dt, grads["encoder." + bp + "attn.proj.bias"] = split_transpose(d_tok, M, D, want_colsum=True)
         grads["encoder." + bp + "attn.proj.weight"] = wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad)
         bfk = dict(dtype=torch.bfloat16, device=dev)
         d_att = (torch.empty(M, D, **bfk), torch.empty(M, D, **bfk))     # dO as split planes: operand of the attention backward
@@ -272,16 +267,15 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
         a.lse, a.Dvec, a.dqkv = b.lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
         a.M, a.batch, a.tokens, a.row_offset, a.heads, a.scale = M, B, N, 0, E.HEADS, scale
         L.check(L.lib().dupl_attention_bwd(C.byref(a), _st(dev)), "dupl_attention_bwd")
-        dpl, dt = split_transpose(d_qkv, M, 3 * D)
-        grads["encoder." + bp + "attn.qkv.bias"] = colsum(d_qkv, M, 3 * D)
+        dpl, dt, grads["encoder." + bp + "attn.qkv.bias"] = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
         grads["encoder." + bp + "attn.qkv.weight"] = wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad)
         d_xn1 = dgrad(dpl, pl.plane_t(bp + "attn.qkv.weight"), M, D, 3 * D)
         dg, db = layernorm_bwd(d_xn1, b.x_in, pl.vec(bp + "norm1.weight"), d_tok)
         grads["encoder." + bp + "norm1.weight"], grads["encoder." + bp + "norm1.bias"] = dg, db
 
     # ---- patch embedding (pos_embed is frozen, vit.py:243)
-    _, dt = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1)
-    grads["encoder.patch_embed.proj.bias"] = colsum(d_tok, Mp, D, tokens=N, np_=np_, first=1)
+    _, dt, grads["encoder.patch_embed.proj.bias"] = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1,
+                                                                      want_colsum=True)
     dwpe = wgrad(dt, transpose_planes(S.patch, Mp, D), D, D, _pad64(Mp))
     grads["encoder.patch_embed.proj.weight"] = dwpe.reshape(D, 3, 16, 16)
     grads["encoder.cls_token"] = colsum(d_tok, B, D, tokens=N, np_=1, first=0).reshape(1, 1, D)

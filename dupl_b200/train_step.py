@@ -9,6 +9,7 @@ reaches through model(...), cam_helper, PAR and model.losses runs in libdupl.so.
 Differences from the script, none of which changes a number:
   * the per-image high threshold is computed on the device (masked max) instead of through
     torch.nonzero + a Python loop (train_final_voc.py:268-275) — no host sync;
+  * the up-sampling of the seg logits and the seg loss are one kernel pair (model.losses.get_seg_loss_upsampled);
   * no logging / validation / checkpointing.
 """
 import math
@@ -17,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .model.losses import get_masked_ptc_loss, get_seg_loss
+from .model.losses import get_masked_ptc_loss, get_seg_loss_upsampled
 from .model.PAR import PAR
 from .pipeline import CamParStep, denormalize_img2
 from .utils import cam_helper
@@ -59,8 +60,9 @@ def cosine_descent(max_thres, min_thres, step, num_steps):
 class PolyWarmupAdamW(torch.optim.AdamW):
     """utils/optimizer.py:38-68: AdamW whose step() first sets the warm-up / polynomial learning rate."""
 
-    def __init__(self, params, lr, weight_decay, betas, warmup_iter=None, max_iter=None, warmup_ratio=None, power=None):
-        super().__init__(params, lr=lr, betas=betas, weight_decay=weight_decay, eps=1e-8)
+    def __init__(self, params, lr, weight_decay, betas, warmup_iter=None, max_iter=None, warmup_ratio=None, power=None,
+                 fused=None):
+        super().__init__(params, lr=lr, betas=betas, weight_decay=weight_decay, eps=1e-8, fused=fused)
         self.global_step = 0
         self.warmup_iter, self.warmup_ratio, self.max_iter, self.power = warmup_iter, warmup_ratio, max_iter, power
         self._init_lr = [g["lr"] for g in self.param_groups]
@@ -82,13 +84,14 @@ class PolyWarmupAdamW(torch.optim.AdamW):
 def make_optimizer(model, args=Args):
     """utils/train_helper.py:21-87 (get_optimizer): 4 groups, heads and decoders at 10x learning rate."""
     g = model.get_param_groups()
+    on_gpu = all(p.is_cuda for grp in g for p in grp)  # torch's single-kernel-per-chunk AdamW (same update rule)
     return PolyWarmupAdamW(
         params=[{"params": g[0], "lr": args.lr, "weight_decay": args.wt_decay},
                 {"params": g[1], "lr": args.lr, "weight_decay": args.wt_decay},
                 {"params": g[2], "lr": args.lr * 10, "weight_decay": args.wt_decay},
                 {"params": g[3], "lr": args.lr * 10, "weight_decay": args.wt_decay}],
         lr=args.lr, weight_decay=args.wt_decay, betas=args.betas, warmup_iter=args.warmup_iters, max_iter=args.max_iters,
-        warmup_ratio=args.warmup_lr, power=args.power)
+        warmup_ratio=args.warmup_lr, power=args.power, fused=True if on_gpu else None)
 
 
 class PhaseBStep:
@@ -130,9 +133,8 @@ class PhaseBStep:
                                                             ignore_index=a.ignore_index)
             ptc_loss = ptc_loss + get_masked_ptc_loss(fmap, cam_helper.label_to_aff_mask(pseudo))
 
-        segs_1 = F.interpolate(segs_1, size=label_1.shape[1:], mode="bilinear", align_corners=False)
-        segs_2 = F.interpolate(segs_2, size=label_2.shape[1:], mode="bilinear", align_corners=False)
-        seg_loss = get_seg_loss(segs_1, label_2.type(torch.long)) + get_seg_loss(segs_2, label_1.type(torch.long))
+        # F.interpolate(segs, size=label.shape[1:]) + get_seg_loss (train_final_voc.py:345-352), fused
+        seg_loss = get_seg_loss_upsampled(segs_1, label_2) + get_seg_loss_upsampled(segs_2, label_1)
 
         f1 = fmap_1.view(fmap_1.shape[0], fmap_1.shape[1], -1)
         f2 = fmap_2.view(fmap_2.shape[0], fmap_2.shape[1], -1)

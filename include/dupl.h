@@ -164,9 +164,10 @@ int dupl_im2col3x3(const void* in_hi, const void* in_lo, void* out_hi, void* out
 /* out[b][c][p] = src[row(b,p)][c], c < C (src row stride ld): token-major -> NCHW (to_2D, model_dupl.py:64-67). */
 int dupl_rows_to_nchw(const float* src, float* out, int32_t B, int32_t np, int32_t C, int32_t ld, int32_t row_offset,
                       int32_t row_stride, int32_t first, void* stream);
-/* logits[b][k] = sum_d (max_p x[row(b,p)][d]) w[k][d]; argmax (optional, int32 [B][D]) keeps the pooled rows. */
-int dupl_gmp_classify(const float* x, const float* w, float* logits, int32_t* argmax, int32_t B, int32_t np, int32_t D,
-                      int32_t K, int32_t row_offset, int32_t row_stride, int32_t first, void* stream);
+/* logits[b][k] = sum_d (max_p x[row(b,p)][d]) w[k][d]  (GMP + bias-free 1x1 classifier, model_dupl.py:88-98);
+ * pooled: [B][D] output of the max pool (scratch for the caller); argmax (optional, int32 [B][D]) keeps the pooled rows. */
+int dupl_gmp_classify(const float* x, const float* w, float* logits, float* pooled, int32_t* argmax, int32_t B, int32_t np,
+                      int32_t D, int32_t K, int32_t row_offset, int32_t row_stride, int32_t first, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * multi_scale_cam2_siamese post-processing (utils/cam_helper.py:173-202): per scale bilinear
@@ -273,10 +274,14 @@ int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
 /* src fp32 [R rows (mapped), Cc] (row stride ld) -> planes hi/lo [R, Cc] (optional) and transposed planes
  * t_hi/t_lo [Cc, Rpad] (optional; columns R..Rpad-1 zero so that Rpad % 64 == 0 can be a GEMM contraction). */
 int dupl_split_transpose(const float* src, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
-                         void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, void* stream);
-/* one bf16 plane [R (mapped), Cc] (row stride ld) -> its transpose [Cc, Rpad], zero padded. */
-int dupl_transpose_plane(const void* in, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
-                         void* out, int32_t Rpad, void* stream);
+                         void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, float* colsum_ws, float* colsum,
+                         void* stream);
+/* (with colsum != NULL the same pass also produces colsum[c] = sum_r src[row(r)][c], the bias gradient of the
+ * layer; colsum_ws: scratch of ceil(rows/64)*Cc floats, rows = Rpad when t_hi is given, else R.) */
+/* one or two bf16 planes [R (mapped), Cc] (row stride ld) -> their transposes [Cc, Rpad], zero padded;
+ * in_lo/out_lo may be NULL.  Cc, ld, Rpad even. */
+int dupl_transpose_planes(const void* in_hi, const void* in_lo, int32_t R, int32_t Cc, int32_t ld, int32_t tokens,
+                          int32_t np, int32_t first, void* out_hi, void* out_lo, int32_t Rpad, void* stream);
 /* out[c] = sum_r x[row(r)][c]  (bias gradients) */
 int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first, float* out,
                 void* stream);
@@ -331,6 +336,15 @@ int dupl_seg_loss_fwd(const float* pred, const int64_t* label, int32_t b, int32_
 int dupl_seg_loss_bwd(const float* pred, const int64_t* label, const float* lse, const float* stats,
                       const float* grad_out, int32_t b, int32_t C, int32_t H, int32_t W, int64_t ignore_index,
                       float* dpred, void* stream);
+/* The same loss on logits that the caller would first up-sample (train_final_voc.py:345-352: F.interpolate(segs,
+ * size=label.shape[1:], mode='bilinear', align_corners=False) then get_seg_loss), without materialising them:
+ * pred fp32 [b,C,h,w] low resolution, label int64 [b,H,W]; lse [b,H,W]; partials: 4*b*ceil(H/32)*ceil(W/32) floats;
+ * dpred [b,C,h,w] is the gradient wrt the LOW-resolution logits (the transpose of the interpolation applied). */
+int dupl_seg_loss_up_fwd(const float* pred, const int64_t* label, int32_t b, int32_t C, int32_t h, int32_t w, int32_t H,
+                         int32_t W, int64_t ignore_index, float* lse, float* partials, float* stats, void* stream);
+int dupl_seg_loss_up_bwd(const float* pred, const int64_t* label, const float* lse, const float* stats,
+                         const float* grad_out, int32_t b, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W,
+                         int64_t ignore_index, float* dpred, void* stream);
 /* get_masked_ptc_loss (losses.py:6-21): x fp32 [b,C,n] (n = h*w), mask int64 [b,n,n] with values {0,1,other};
  * inv: [b,n]; Gs: [b,n,n] signed cosine matrix kept for backward; partials: 4*b*ceil(n/64)^2 floats;
  * stats: 5 floats (sum_pos, sum_neg, n_pos, n_neg, loss). */

@@ -36,6 +36,27 @@ def test_seg_loss_value_and_gradient(b, C, H, W):
     assert rel_err(p_gpu.grad, p_ref.grad) < 1e-4
 
 
+@pytest.mark.parametrize("b,C,h,w,H,W", [(2, 21, 28, 28, 448, 448), (1, 81, 5, 7, 37, 50), (2, 21, 21, 21, 448, 448), (1, 4, 6, 6, 6, 6),
+                                         (1, 3, 9, 8, 5, 4)])
+def test_seg_loss_upsampled_equals_interpolate_then_seg_loss(b, C, h, w, H, W):
+    """get_seg_loss_upsampled == get_seg_loss(F.interpolate(..., bilinear, align_corners=False)) of the oracle (CPU autograd),
+    value and the gradient at the low resolution; ratios 16x, ragged, 21.3x (the 0.75 view), 1x and a down-sampling."""
+    import torch.nn.functional as F
+    from dupl_b200.model.losses import get_seg_loss_upsampled
+    from oracle import dupl_oracle as O
+    g = torch.Generator().manual_seed(b * C + h)
+    pred = torch.randn(b, C, h, w, generator=g) * 2
+    lab = _labels(b, H, W, seed=H + w)
+    p_ref = pred.clone().requires_grad_(True)
+    want = O.seg_loss(F.interpolate(p_ref, size=(H, W), mode="bilinear", align_corners=False), lab)
+    (want * 0.2).backward()
+    p_gpu = pred.cuda().requires_grad_(True)
+    got = get_seg_loss_upsampled(p_gpu, lab.cuda(), ignore_index=255)
+    (got * 0.2).backward()
+    assert abs(got.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    assert rel_err(p_gpu.grad, p_ref.grad) < 1e-4
+
+
 def test_seg_loss_without_foreground_or_background_is_finite():
     from dupl_b200.model.losses import get_seg_loss
     pred = torch.randn(1, 4, 8, 8).cuda().requires_grad_(True)
