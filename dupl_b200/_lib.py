@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libdupl.so")
 
 MAX_SEGMENTS = 8
 MAX_GROUPS = 2
+MAX_KSPLIT = 8
 PAR_MAX_DIL = 8
 
 EPI_F32, EPI_SPLIT, EPI_GELU_SPLIT, EPI_RESID, EPI_PATCH, EPI_RELU_SPLIT = 0, 1, 2, 3, 4, 5
@@ -30,12 +31,14 @@ class Segment(C.Structure):
 class GemmGroup(C.Structure):
     _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("out_f32", C.c_void_p),
-                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("pos", C.c_void_p * MAX_SEGMENTS)]
+                ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("pos", C.c_void_p * MAX_SEGMENTS),
+                ("splitk_ws", C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
     _fields_ = [("groups", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("lda", C.c_int32), ("ldo", C.c_int32), ("epilogue", C.c_int32), ("nseg", C.c_int32),
+                ("ldw", C.c_int32), ("max_ksplit", C.c_int32), ("f32_rows", C.c_int32), ("reserved", C.c_int32),
                 ("seg", Segment * MAX_SEGMENTS), ("g", GemmGroup * MAX_GROUPS)]
 
 

@@ -23,6 +23,7 @@
 // The M dimension concatenates every image of every scale (and the grid covers both students), so
 // tile-quantisation loss stays below 1 % although 148 is an awkward SM count.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -46,6 +47,9 @@ struct GemmParamsDev {
   GemmGroupDev g[DUPL_MAX_GROUPS];
   dupl_segment seg[DUPL_MAX_SEGMENTS];
   int groups, M, N, K, ldo, epilogue, nseg;
+  int ksplit;    // split-K factor: work item (group, k-split, tile); partial s lands at out_f32 + s*M*ldo (EPI_F32 only)
+  int kper;      // k-blocks per split
+  int f32_rows;  // GELU_SPLIT: rows below this get the fp32 pre-activation side output
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -113,8 +117,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   const int m_pairs = (m_tiles + 1) >> 1;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles_per_group = m_pairs * n_tiles;
-  const int total_tiles = tiles_per_group * p.groups;
+  const int total_tiles = tiles_per_group * p.groups * p.ksplit;
   const int k_blocks = p.K / BK;
+  // work item t -> (group g, k-split ks, tile r): gs = t / tiles_per_group, g = gs / ksplit, ks = gs % ksplit
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -122,12 +127,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int g = t / tiles_per_group;
-        const int r = t - g * tiles_per_group;
+        const int gs = t / tiles_per_group;
+        const int r = t - gs * tiles_per_group;
+        const int g = gs / p.ksplit, ks = gs - g * p.ksplit;
         const int m0 = (2 * (r / n_tiles) + rank) * GEMM_BM;
         const int n0 = (r % n_tiles) * BN;
         const GemmGroupDev& G = p.g[g];
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb_end = min(k_blocks, (ks + 1) * p.kper);
+        for (int kb = ks * p.kper; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
@@ -156,7 +163,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int ks = (t / tiles_per_group) % p.ksplit;
+        const int kb_count = min(k_blocks, (ks + 1) * p.kper) - ks * p.kper;
+        for (int kb = 0; kb < kb_count; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -189,8 +198,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-      const int g = t / tiles_per_group;
-      const int r = t - g * tiles_per_group;
+      const int gs = t / tiles_per_group;
+      const int r = t - gs * tiles_per_group;
+      const int g = gs / p.ksplit, ks = gs - g * p.ksplit;
       const int m0 = (2 * (r / n_tiles) + rank) * GEMM_BM;
       const int n0 = (r % n_tiles) * BN;
       const GemmGroupDev& G = p.g[g];
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           }
           const int ncols = min(32, p.N - col0);  // multiple of 16 by contract
           if (p.epilogue == DUPL_EPI_F32 || p.epilogue == DUPL_EPI_RESID || p.epilogue == DUPL_EPI_PATCH) {
-            float* o = G.out_f32 + out_row * p.ldo + col0;
+            float* o = G.out_f32 + (static_cast<long>(ks) * p.M + out_row) * p.ldo + col0;
             const float* add = nullptr;
             if (p.epilogue == DUPL_EPI_RESID) add = G.resid + static_cast<long>(row) * p.ldo + col0;
             if (p.epilogue == DUPL_EPI_PATCH) add = pos_row + col0;
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             }
           } else {
             if (p.epilogue == DUPL_EPI_GELU_SPLIT) {
-              if (G.out_f32 != nullptr) {  // training: keep the pre-activation for the GELU backward
+              if (G.out_f32 != nullptr && row < p.f32_rows) {  // training: keep the pre-activation for the GELU backward
                 float* o = G.out_f32 + static_cast<long>(row) * p.ldo + col0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -294,6 +304,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   }
 }
 
+// Deterministic split-K tail: out[i] = sum_s ws[s][i] in fixed order.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ out, int ks,
+                                                            long n4) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = __ldcs(ws + i);
+  for (int s = 1; s < ks; ++s) {
+    const float4 b = __ldcs(ws + s * n4 + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+
 template <int BN, int BK>
 static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, BK>;
@@ -304,10 +327,9 @@ static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
     attr_set = true;
   }
   const int m_pairs = cdiv(cdiv(P.M, GEMM_BM), 2), n_tiles = cdiv(P.N, BN);
-  const int total = m_pairs * n_tiles * P.groups;  // work items, one per cluster of 2 CTAs
+  const int total = m_pairs * n_tiles * P.groups * P.ksplit;  // work items, one per cluster of 2 CTAs
   const int clusters = total < sm_count() / 2 ? total : sm_count() / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -324,6 +346,39 @@ static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
   return DUPL_OK;
 }
 
+// Tile width and split-K factor by a small cost model (microseconds; constants from the round-1 profiles: one
+// 256-wide k-block of 3 x 4 MMAs takes ~0.9 us, a 256-wide fp32 epilogue ~3 us and is hidden behind the next
+// tile's main loop except for the last tile of a CTA pair).  The persistent grid has sm_count/2 pairs; 148 SMs
+// make 74 = 2 x 37 slots, so the M=3140 training shapes (39 / 117 / 156 tiles of 256) fit badly without this.
+static void choose_tiling(int M, int N, int k_blocks, int groups, int max_split, bool allow_192, int& bn_out, int& ks_out,
+                          int& kper_out) {
+  const int slots = sm_count() / 2;
+  const int m_pairs = cdiv(cdiv(M, GEMM_BM), 2);
+  double best = 1e30;
+  bn_out = 256; ks_out = 1; kper_out = k_blocks;
+  const int cand[3] = {256, 192, 128};
+  // smaller tiles re-read more operand bytes per MMA from shared memory (DUPL_GEMM_PEN192 / _PEN128 override for tuning)
+  static const double pen192 = getenv("DUPL_GEMM_PEN192") ? atof(getenv("DUPL_GEMM_PEN192")) : 1.08;
+  static const double pen128 = getenv("DUPL_GEMM_PEN128") ? atof(getenv("DUPL_GEMM_PEN128")) : 1.25;
+  const double pen[3] = {1.0, pen192, pen128};
+  for (int c = 0; c < 3; ++c) {
+    const int bn = cand[c];
+    if (bn == 192 && !allow_192) continue;
+    const int n_tiles = cdiv(N, bn);
+    for (int ks = 1; ks <= max_split && ks <= k_blocks; ++ks) {
+      const int kper = cdiv(k_blocks, ks);
+      if ((ks - 1) * kper >= k_blocks) continue;  // every split needs at least one k-block
+      const long tiles = static_cast<long>(m_pairs) * n_tiles * groups * ks;
+      const long waves = (tiles + slots - 1) / slots;
+      double t = waves * kper * 0.9 * (bn / 256.0) * pen[c] + 3.0 * (bn / 256.0);
+      if (ks > 1) t += 3.0 + (ks + 1.0) * M * static_cast<double>(N) * 4.0 * groups / 5e6;
+      if (t < best - 1e-9) {
+        best = t; bn_out = bn; ks_out = ks; kper_out = kper;
+      }
+    }
+  }
+}
+
 }  // namespace dupl
 
 extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
@@ -338,22 +393,46 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     const char* e = getenv("DUPL_GEMM_BK");
     return (e != nullptr && atoi(e) == 32) ? 32 : 64;
   }();
+  // DUPL_GEMM_TILING=fixed restores the round-1 behaviour (256-wide tiles, no split-K) for A/B measurements.
+  static const bool fixed_tiling = [] {
+    const char* e = getenv("DUPL_GEMM_TILING");
+    return e != nullptr && strcmp(e, "fixed") == 0;
+  }();
   DUPL_CHECK_ARG(a->N % 16 == 0, "dupl_gemm_bf16x3: N=%d must be a multiple of 16", a->N);
   DUPL_CHECK_ARG(a->lda % 8 == 0 && a->lda >= a->K, "dupl_gemm_bf16x3: lda=%d", a->lda);
+  DUPL_CHECK_ARG(a->ldw == 0 || (a->ldw % 8 == 0 && a->ldw >= a->K), "dupl_gemm_bf16x3: ldw=%d", a->ldw);
   DUPL_CHECK_ARG(a->ldo % 8 == 0 && a->ldo >= a->N, "dupl_gemm_bf16x3: ldo=%d", a->ldo);
   DUPL_CHECK_ARG(a->epilogue >= DUPL_EPI_F32 && a->epilogue <= DUPL_EPI_RELU_SPLIT, "dupl_gemm_bf16x3: epilogue=%d",
                  a->epilogue);
+  DUPL_CHECK_ARG(a->max_ksplit >= 0 && a->max_ksplit <= DUPL_MAX_KSPLIT, "dupl_gemm_bf16x3: max_ksplit=%d (0..%d)",
+                 a->max_ksplit, DUPL_MAX_KSPLIT);
+  const bool can_split = a->max_ksplit > 1 && a->epilogue == DUPL_EPI_F32;
+  if (a->max_ksplit > 1) {
+    DUPL_CHECK_ARG(a->epilogue == DUPL_EPI_F32, "dupl_gemm_bf16x3: split-K needs the plain F32 epilogue");
+    for (int g = 0; g < a->groups; ++g)
+      DUPL_CHECK_ARG(a->g[g].splitk_ws != nullptr && a->g[g].bias == nullptr,
+                     "dupl_gemm_bf16x3: split-K needs splitk_ws and no bias (group %d)", g);
+  }
   GemmParamsDev P;
   memset(&P, 0, sizeof(P));
   P.groups = a->groups; P.M = a->M; P.N = a->N; P.K = a->K; P.ldo = a->ldo; P.epilogue = a->epilogue;
+  P.f32_rows = a->f32_rows > 0 ? a->f32_rows : a->M;
   P.nseg = 0;
   if (a->epilogue == DUPL_EPI_PATCH) {
     DUPL_CHECK_ARG(a->nseg >= 1 && a->nseg <= DUPL_MAX_SEGMENTS, "dupl_gemm_bf16x3: nseg=%d", a->nseg);
     P.nseg = a->nseg;
     for (int s = 0; s < a->nseg; ++s) P.seg[s] = a->seg[s];
   }
-  // Wide tiles for wide outputs; N <= 128 (CAM-sized heads) uses the narrow instantiation.
-  const int bn = (a->N >= 256) ? 256 : ((a->N > 64) ? 128 : 64);
+  // Wide tiles for wide outputs; N <= 128 (CAM-sized heads) uses the narrow instantiations.
+  int bn, ks = 1, kper = a->K / bk;
+  if (a->N < 256 || fixed_tiling || bk != 64) {
+    bn = (a->N >= 256) ? 256 : ((a->N > 64) ? 128 : 64);
+  } else {
+    choose_tiling(a->M, a->N, a->K / bk, a->groups, can_split ? a->max_ksplit : 1, true, bn, ks, kper);
+  }
+  P.ksplit = ks;
+  P.kper = kper;
+  const int ldw = a->ldw > 0 ? a->ldw : a->K;
   for (int g = 0; g < a->groups; ++g) {
     const dupl_gemm_group& G = a->g[g];
     DUPL_CHECK_ARG(G.a_hi && G.a_lo && G.w_hi && G.w_lo, "dupl_gemm_bf16x3: NULL operand plane in group %d", g);
@@ -364,9 +443,10 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     int rc;
     if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
     if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, a->K, bn / 2, bk))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, a->K, bn / 2, bk))) return rc;
-    P.g[g].bias = G.bias; P.g[g].resid = G.resid; P.g[g].out_f32 = G.out_f32;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, ldw, bn / 2, bk))) return rc;
+    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, ldw, bn / 2, bk))) return rc;
+    P.g[g].bias = G.bias; P.g[g].resid = G.resid;
+    P.g[g].out_f32 = ks > 1 ? G.splitk_ws : G.out_f32;
     P.g[g].out_hi = static_cast<__nv_bfloat16*>(G.out_hi);
     P.g[g].out_lo = static_cast<__nv_bfloat16*>(G.out_lo);
     for (int s = 0; s < DUPL_MAX_SEGMENTS; ++s) P.g[g].pos[s] = G.pos[s];
@@ -375,12 +455,25 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
         DUPL_CHECK_ARG(G.pos[s] != nullptr, "dupl_gemm_bf16x3: pos[%d] is NULL in group %d", s, g);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
   if (bk == 64) {
-    if (bn == 256) return launch_gemm<256, 64>(P, st);
-    if (bn == 128) return launch_gemm<128, 64>(P, st);
-    return launch_gemm<64, 64>(P, st);
+    if (bn == 256) rc = launch_gemm<256, 64>(P, st);
+    else if (bn == 192) rc = launch_gemm<192, 64>(P, st);
+    else if (bn == 128) rc = launch_gemm<128, 64>(P, st);
+    else rc = launch_gemm<64, 64>(P, st);
+  } else {
+    if (bn == 256) rc = launch_gemm<256, 32>(P, st);
+    else if (bn == 128) rc = launch_gemm<128, 32>(P, st);
+    else rc = launch_gemm<64, 32>(P, st);
   }
-  if (bn == 256) return launch_gemm<256, 32>(P, st);
-  if (bn == 128) return launch_gemm<128, 32>(P, st);
-  return launch_gemm<64, 32>(P, st);
+  if (rc) return rc;
+  if (ks > 1) {
+    const long n4 = static_cast<long>(a->M) * a->ldo / 4;
+    for (int g = 0; g < a->groups; ++g) {
+      splitk_reduce_kernel<<<static_cast<int>((n4 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(a->g[g].splitk_ws), reinterpret_cast<float4*>(a->g[g].out_f32), ks, n4);
+      DUPL_LAUNCH_OK();
+    }
+  }
+  return DUPL_OK;
 }

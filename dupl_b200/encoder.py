@@ -97,11 +97,20 @@ class StudentPlanes:
         return hit[1]
 
 
-class EncoderOutput:
-    __slots__ = ("segs", "tok", "aux_tok", "M")
+class KeptBlock:
+    """Activations of one encoder block that the training backward reads (same fields as train._forward saves)."""
+    __slots__ = ("x_in", "xn1", "qkv", "att", "lse", "x_mid", "xn2", "hid", "h_pre")
 
 
-def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=None):
+class KeptActivations:
+    """What a no-grad encoder pass leaves behind for the leading `rows` token rows (the un-flipped scale-1.0 images of
+    multi_scale_cam2_siamese): with no dropout and no batch statistics (vit.py:87-184, drop rates 0) those rows are
+    bit-identical to the training forward `model(inputs)` of the same step (SURVEY §7 step 4 "dedupe"), so the
+    training pass can start from them instead of recomputing 12 blocks."""
+    __slots__ = ("rows", "patch_rows", "batch", "gh", "gw", "patch", "blocks", "tok_final")
+
+
+def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=None, keep_batch=0):
     """Runs the 12 blocks for every student in `planes` over the given segments.
 
     images_per_seg: list of source image tensors [b,3,H,W] (fp32, cuda); segment i is patchified from
@@ -109,6 +118,9 @@ def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=
     aux_index: block index whose output feeds the aux head (embeds[aux_layer], vit.py:319-326).
     on_aux(g, tok_g, segs): called right after block `aux_index` (0-based) for every student when that
     index is not the last block (the last entry of `embeds` is the final-normed tensor, vit.py:323-324).
+    keep_batch > 0: every block writes into buffers of its own (no reuse across blocks), also emits the attention
+    log-sum-exp and, for the first keep_batch images of segment 0, the fc1 pre-activation; a KeptActivations per
+    student is returned as third value.  Costs memory (0.8 GB per block and student at 21 976 rows), no extra pass.
     Returns (segs, [tok_g]) with tok_g the fp32 residual stream BEFORE the final LayerNorm.
     """
     G = len(planes)
@@ -117,17 +129,28 @@ def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=
     dev = images_per_seg[0].device
     bf = dict(dtype=torch.bfloat16, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
+    keep = keep_batch > 0
+    kr = keep_batch * segs[0].tokens            # kept token rows
+    kpr = keep_batch * segs[0].gh * segs[0].gw  # kept patch rows
 
     patch_hi = torch.empty(Mp, EMBED, **bf)
     patch_lo = torch.empty(Mp, EMBED, **bf)
     for s, img, size in zip(segs, images_per_seg, seg_sizes):
         ops.patchify(L.f32c(img), s, size, flip_twin, patch_hi, patch_lo)
 
+    def planes_buf(cols):
+        return [(torch.empty(M, cols, **bf), torch.empty(M, cols, **bf)) for _ in range(G)]
+
     tok = [torch.empty(M, EMBED, **f32) for _ in range(G)]
-    xn = [(torch.empty(M, EMBED, **bf), torch.empty(M, EMBED, **bf)) for _ in range(G)]
-    qkv = [(torch.empty(M, 3 * EMBED, **bf), torch.empty(M, 3 * EMBED, **bf)) for _ in range(G)]
-    att = [(torch.empty(M, EMBED, **bf), torch.empty(M, EMBED, **bf)) for _ in range(G)]
-    hid = [(torch.empty(M, 4 * EMBED, **bf), torch.empty(M, 4 * EMBED, **bf)) for _ in range(G)]
+    if not keep:
+        xn, qkv, att, hid = planes_buf(EMBED), planes_buf(3 * EMBED), planes_buf(EMBED), planes_buf(4 * EMBED)
+    kept = None
+    if keep:
+        kept = [KeptActivations() for _ in range(G)]
+        for k in kept:
+            k.rows, k.patch_rows, k.batch, k.gh, k.gw = kr, kpr, keep_batch, segs[0].gh, segs[0].gw
+            k.patch = (patch_hi[:kpr], patch_lo[:kpr])
+            k.blocks = []
 
     pos = [[pl.pos(s.gh, s.gw) for s in segs] for pl in planes]
     ops.gemm_bf16x3(
@@ -140,21 +163,44 @@ def run_encoder(planes, images_per_seg, seg_sizes, flip_twin, aux_index, on_aux=
     scale = (EMBED // HEADS) ** -0.5
     for i in range(DEPTH):
         bp = f"blocks.{i}."
+        if keep:
+            xn1, qkv, att, xn2, hid = planes_buf(EMBED), planes_buf(3 * EMBED), planes_buf(EMBED), planes_buf(EMBED), planes_buf(4 * EMBED)
+            lse = [torch.empty(M, HEADS, **f32) for _ in range(G)]
+            h_pre = [torch.empty(kr, 4 * EMBED, **f32) for _ in range(G)]
+            tok_mid = [torch.empty(M, EMBED, **f32) for _ in range(G)]
+            tok_out = [torch.empty(M, EMBED, **f32) for _ in range(G)]
+        else:
+            xn1 = xn2 = xn
+            lse = h_pre = [None] * G
+            tok_mid = tok_out = tok
         for g, pl in enumerate(planes):
-            ops.layernorm_split(tok[g], pl.vec(bp + "norm1.weight"), pl.vec(bp + "norm1.bias"), *xn[g], eps=LN_EPS)
-        ops.gemm_bf16x3([dict(a=xn[g], w=pl.plane(bp + "attn.qkv.weight"), bias=pl.vec(bp + "attn.qkv.bias"), out=qkv[g])
+            ops.layernorm_split(tok[g], pl.vec(bp + "norm1.weight"), pl.vec(bp + "norm1.bias"), *xn1[g], eps=LN_EPS)
+        ops.gemm_bf16x3([dict(a=xn1[g], w=pl.plane(bp + "attn.qkv.weight"), bias=pl.vec(bp + "attn.qkv.bias"), out=qkv[g])
                          for g, pl in enumerate(planes)], M, 3 * EMBED, EMBED, L.EPI_SPLIT)
         for g in range(G):
-            ops.attention_fwd(qkv[g][0], qkv[g][1], att[g][0], att[g][1], segs, HEADS, scale)
+            ops.attention_fwd(qkv[g][0], qkv[g][1], att[g][0], att[g][1], segs, HEADS, scale, lse=lse[g])
         ops.gemm_bf16x3([dict(a=att[g], w=pl.plane(bp + "attn.proj.weight"), bias=pl.vec(bp + "attn.proj.bias"),
-                              resid=tok[g], out_f32=tok[g]) for g, pl in enumerate(planes)], M, EMBED, EMBED, L.EPI_RESID)
+                              resid=tok[g], out_f32=tok_mid[g]) for g, pl in enumerate(planes)], M, EMBED, EMBED, L.EPI_RESID)
         for g, pl in enumerate(planes):
-            ops.layernorm_split(tok[g], pl.vec(bp + "norm2.weight"), pl.vec(bp + "norm2.bias"), *xn[g], eps=LN_EPS)
-        ops.gemm_bf16x3([dict(a=xn[g], w=pl.plane(bp + "mlp.fc1.weight"), bias=pl.vec(bp + "mlp.fc1.bias"), out=hid[g])
-                         for g, pl in enumerate(planes)], M, 4 * EMBED, EMBED, L.EPI_GELU_SPLIT)
+            ops.layernorm_split(tok_mid[g], pl.vec(bp + "norm2.weight"), pl.vec(bp + "norm2.bias"), *xn2[g], eps=LN_EPS)
+        ops.gemm_bf16x3([dict(a=xn2[g], w=pl.plane(bp + "mlp.fc1.weight"), bias=pl.vec(bp + "mlp.fc1.bias"), out=hid[g],
+                              out_f32=h_pre[g]) for g, pl in enumerate(planes)], M, 4 * EMBED, EMBED, L.EPI_GELU_SPLIT,
+                        f32_rows=kr if keep else 0)
         ops.gemm_bf16x3([dict(a=hid[g], w=pl.plane(bp + "mlp.fc2.weight"), bias=pl.vec(bp + "mlp.fc2.bias"),
-                              resid=tok[g], out_f32=tok[g]) for g, pl in enumerate(planes)], M, EMBED, 4 * EMBED, L.EPI_RESID)
+                              resid=tok_mid[g], out_f32=tok_out[g]) for g, pl in enumerate(planes)], M, EMBED, 4 * EMBED, L.EPI_RESID)
+        if keep:
+            for g in range(G):
+                kb = KeptBlock()
+                kb.x_in, kb.x_mid, kb.lse, kb.h_pre = tok[g][:kr], tok_mid[g][:kr], lse[g][:kr], h_pre[g]
+                kb.xn1, kb.qkv, kb.att = (xn1[g][0][:kr], xn1[g][1][:kr]), (qkv[g][0][:kr], qkv[g][1][:kr]), (att[g][0][:kr], att[g][1][:kr])
+                kb.xn2, kb.hid = (xn2[g][0][:kr], xn2[g][1][:kr]), (hid[g][0][:kr], hid[g][1][:kr])
+                kept[g].blocks.append(kb)
+        tok = tok_out
         if on_aux is not None and i == aux_index and i != DEPTH - 1:
             for g in range(G):
                 on_aux(g, tok[g], segs)
+    if keep:
+        for g in range(G):
+            kept[g].tok_final = tok[g][:kr]
+        return segs, tok, kept
     return segs, tok

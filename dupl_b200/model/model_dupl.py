@@ -28,6 +28,8 @@ class network(nn.Module):
         self.classifier = nn.Conv2d(self.in_channels[-1], self.num_classes - 1, kernel_size=1, bias=False)
         self.aux_classifier = nn.Conv2d(self.in_channels[-1], self.num_classes - 1, kernel_size=1, bias=False)
         self._planes = None  # split-bf16 weight planes live outside the module state (no buffers: SURVEY §8(b))
+        self._kept = None    # encoder.KeptActivations left by an MS-CAM pass run with keep_activations (train_step.py)
+        self._keep_next = False
 
     # -- reference API -----------------------------------------------------------------------
     def get_param_groups(self):
@@ -56,11 +58,13 @@ class network(nn.Module):
         return dense.network_forward(self, x, val=val, cam_with_grad=cam_with_grad)
 
 
-def cam_only_forward(nets, x, seg_images=None, seg_sizes=None, flip_twin=False):
+def cam_only_forward(nets, x, seg_images=None, seg_sizes=None, flip_twin=False, keep_batch=0):
     """cam_only path of `network.forward` (model_dupl.py:69-84) for one or two students at once.
 
     Default: one segment holding the batch `x` as given.  multi_scale_cam2_siamese passes several
     segments (one per scale, with flipped twins) so that all scales share each GEMM launch.
+    keep_batch > 0: the encoder keeps the activations of the first keep_batch images of segment 0 on each
+    student (`net._kept`, encoder.KeptActivations) for a training forward of the same images in the same step.
     Returns, per student, (cam_aux, cam) as lists over segments when seg_sizes is given, else tensors.
     """
     L.require_cuda(x)
@@ -78,7 +82,12 @@ def cam_only_forward(nets, x, seg_images=None, seg_sizes=None, flip_twin=False):
             w = nets[g].aux_classifier.weight.detach().reshape(nets[g].num_classes - 1, -1)
             aux_out[g] = ops.cam_contract(tok_g, None, None, L.f32c(w), segs)
 
-        segs, tok = E.run_encoder(planes, seg_images, seg_sizes, flip_twin, aux_idx, on_aux)
+        if keep_batch > 0:
+            segs, tok, kept = E.run_encoder(planes, seg_images, seg_sizes, flip_twin, aux_idx, on_aux, keep_batch=keep_batch)
+            for n, k in zip(nets, kept):
+                n._kept = k
+        else:
+            segs, tok = E.run_encoder(planes, seg_images, seg_sizes, flip_twin, aux_idx, on_aux)
         res = []
         for g, n in enumerate(nets):
             gam, bet = n.encoder.norm.weight.detach(), n.encoder.norm.bias.detach()

@@ -40,13 +40,19 @@ def split_bf16(x, out=None):
     return hi, lo
 
 
-def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None):
-    """groups: list of dicts with keys a=(hi,lo), w=(hi,lo), bias, resid, out_f32, out=(hi,lo), pos=[...]."""
+def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=None, ksplit=0, f32_rows=0):
+    """groups: list of dicts with keys a=(hi,lo), w=(hi,lo), bias, resid, out_f32, out=(hi,lo), pos=[...].
+    ksplit > 1 lets the library split the contraction up to that many ways (plain F32 epilogue, no bias): the
+    partial sums go through a workspace allocated here and are added in a fixed order."""
     a = L.GemmArgs()
     a.groups, a.M, a.N, a.K = len(groups), M, N, K
     a.lda = K if lda is None else lda
     a.ldo = N if ldo is None else ldo
+    a.ldw = 0 if ldw is None else ldw
+    a.max_ksplit = ksplit
+    a.f32_rows = f32_rows
     a.epilogue = epilogue
+    ws = []
     a.nseg = 0
     if segs is not None:
         a.nseg = len(segs)
@@ -65,6 +71,9 @@ def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None):
             G.out_hi, G.out_lo = g["out"][0].data_ptr(), g["out"][1].data_ptr()
         for i, p in enumerate(g.get("pos") or []):
             G.pos[i] = p.data_ptr()
+        if ksplit > 1:
+            ws.append(torch.empty(ksplit * M * a.ldo, dtype=torch.float32, device=dev))
+            G.splitk_ws = ws[-1].data_ptr()
     L.check(L.lib().dupl_gemm_bf16x3(C.byref(a), L.stream_ptr(dev)), "dupl_gemm_bf16x3")
 
 

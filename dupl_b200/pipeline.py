@@ -27,7 +27,7 @@ class CamParStep:
     """multi_scale_cam2_siamese for both students + refine_cams_with_dynamic_thres for both students."""
 
     def __init__(self, model, cam_scales=(1.0, 0.5, 1.5), low_thre=0.25, ignore_index=255,
-                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False, graph=False):
+                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False, graph=False, keep_activations=False):
         self.model = model
         self.scales = tuple(cam_scales)
         self.low_thre = low_thre
@@ -35,6 +35,9 @@ class CamParStep:
         self.par = PAR(num_iter=num_iter, dilations=list(dilations))  # train_final_voc.py:160
         self.fuse_students = fuse_students
         self.graph = graph      # replay the whole step as ONE CUDA graph (the ~220 launches cost the host nothing)
+        # keep the encoder activations of the un-flipped scale-1.0 images on each student (network._kept) so that the
+        # training forward of the same step does not recompute them (encoder.KeptActivations)
+        self.keep_activations = keep_activations
         self._g = None
 
     def __call__(self, inputs, cls_label, img_box, high_thres):
@@ -84,6 +87,9 @@ class CamParStep:
         Returns (label_1, label_2, cams_1, cams_2): refined labels float32 [b,H,W] in {0..K,255}."""
         b, _, h, w = inputs.shape
         inputs_denorm = denormalize_img2(inputs.clone())
+        net = self.model.module if hasattr(self.model, "module") else self.model
+        for n in (net.branch1, net.branch2):
+            n._keep_next = bool(self.keep_activations) and 1.0 in self.scales  # scale 1.0 is always segment 0
         if self.fuse_students:
             (cams_1, aux_1), (cams_2, aux_2) = cam_helper.multi_scale_cam2_pair(self.model, inputs, self.scales)
         else:
@@ -95,6 +101,8 @@ class CamParStep:
         thr_map = high_thres.to(inputs.device, torch.float32).reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
         kw = dict(cls_labels=cls_label, high_thre_map=thr_map, low_thre=self.low_thre,
                   ignore_index=self.ignore_index, img_box=img_box)
+        for n in (net.branch1, net.branch2):
+            n._keep_next = False
         lab_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1, **kw)
         lab_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2, **kw)
         return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)

@@ -79,7 +79,7 @@ def dgrad(dy_planes, wt_planes, M, n_out, k_contr):
 def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr):
     """dW[n_rows, n_cols] = dY^T @ X, operands as transposed planes [n_rows, k_contr], [n_cols, k_contr]."""
     out = torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt_planes[0].device)
-    ops.gemm_bf16x3([dict(a=dyt_planes, w=xt_planes, out_f32=out)], n_rows, n_cols, k_contr, L.EPI_F32)
+    ops.gemm_bf16x3([dict(a=dyt_planes, w=xt_planes, out_f32=out)], n_rows, n_cols, k_contr, L.EPI_F32, ksplit=L.MAX_KSPLIT)
     return out
 
 
@@ -88,8 +88,9 @@ class _Saved:
 
 
 # ------------------------------------------------------------------ forward with saved activations
-def _forward(net, x, size=None):
-    """size: (hs, ws) to resize the input to first (bilinear, align_corners=False) — the 0.75x view of need_sp."""
+def _forward(net, x, size=None, kept=None):
+    """size: (hs, ws) to resize the input to first (bilinear, align_corners=False) — the 0.75x view of need_sp.
+    kept: encoder.KeptActivations of the SAME images left by this step's MS-CAM pass: the 12 blocks are not run again."""
     L.require_cuda(x)
     x = L.f32c(x)
     B, _, H, W = x.shape
@@ -105,6 +106,11 @@ def _forward(net, x, size=None):
     S = _Saved()
     S.B, S.gh, S.gw, S.np, S.N, S.M, S.Mp, S.sg = B, gh, gw, np_, N, M, Mp, sg
 
+    if kept is not None:
+        if (kept.batch, kept.gh, kept.gw, kept.rows, kept.patch_rows) != (B, gh, gw, M, Mp):
+            raise RuntimeError("kept activations do not match this batch")
+        S.patch, S.blocks, tok = kept.patch, kept.blocks, kept.tok_final
+        return _forward_heads(net, S, tok, pl, dp)
     S.patch = (torch.empty(Mp, D, **bf), torch.empty(Mp, D, **bf))
     ops.patchify(x, sg, (hs, ws), False, *S.patch)
     pos = [pl.pos(gh, gw)]
@@ -141,6 +147,16 @@ def _forward(net, x, size=None):
         ops.gemm_bf16x3([dict(a=b.hid, w=pl.plane(bp + "mlp.fc2.weight"), bias=pl.vec(bp + "mlp.fc2.bias"),
                               resid=b.x_mid, out_f32=tok)], M, D, 4 * D, L.EPI_RESID)
         S.blocks.append(b)
+    return _forward_heads(net, S, tok, pl, dp)
+
+
+def _forward_heads(net, S, tok, pl, dp):
+    """Final LayerNorm, LargeFOV decoder and the two GMP classifiers on top of the residual stream `tok`."""
+    B, gh, gw, np_, N, M, Mp = S.B, S.gh, S.gw, S.np, S.N, S.M, S.Mp
+    dev = tok.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    aux_idx = net.encoder.aux_block_index()
     S.tok_final = tok
     S.aux_is_final = aux_idx == E.DEPTH - 1
     S.aux_idx = aux_idx
@@ -296,7 +312,10 @@ class StudentFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, size, *params):
         ctx.set_materialize_grads(False)
-        outs, S = _forward(net, x, size)
+        kept = None
+        if size is None and getattr(net, "_use_kept", False) and net._kept is not None:
+            kept, net._use_kept = net._kept, False
+        outs, S = _forward(net, x, size, kept)
         ctx.net, ctx.S = net, S
         ctx.names = [(n, tuple(p.shape)) for n, p in trainable_parameters(net)]
         return outs

@@ -95,14 +95,19 @@ def make_optimizer(model, args=Args):
 
 
 class PhaseBStep:
-    def __init__(self, model, optim=None, args=Args, device=None, graph=True):
+    def __init__(self, model, optim=None, args=Args, device=None, graph=True, reuse_forward=True):
         self.model = model          # siamese_network or DistributedDataParallel(siamese_network)
         self.optim = optim
         self.args = args
         dev = device or next(model.parameters()).device
         self.par = PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24]).to(dev)
         # the no-grad half of the step (MS-CAM of both students + PAR refinement) replayed as one CUDA graph
-        self.pseudo = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph)
+        # reuse_forward: `model(inputs)` of train_final_voc.py:287 recomputes what the MS-CAM pass has just computed for
+        # the un-flipped scale-1.0 images (identical arithmetic: no dropout, no batch statistics); keep those activations
+        # and start the training pass at the final LayerNorm.
+        self.reuse_forward = reuse_forward and 1.0 in tuple(args.cam_scales)
+        self.pseudo = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph,
+                                 keep_activations=self.reuse_forward)
         self.pseudo.par = self.par
         self.thres_start = torch.ones(20, device=dev) * args.high_thre
         self.thres_target = torch.tensor(VOC_HIGH_THRES_TARGET, device=dev)
@@ -118,7 +123,12 @@ class PhaseBStep:
         # multi_scale_cam2_siamese x2 and refine_cams_with_dynamic_thres x2 (train_final_voc.py:279-284, 330-343).
         # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels).
         label_1, label_2, (cams_1, cams_aux_1), (cams_2, cams_aux_2) = self.pseudo(inputs, cls_label, img_box, high_thres)
+        net = model.module if hasattr(model, "module") else model
+        for n in (net.branch1, net.branch2):
+            n._use_kept = self.reuse_forward
         res = model(inputs)
+        for n in (net.branch1, net.branch2):
+            n._use_kept = False
         cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
         cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
 

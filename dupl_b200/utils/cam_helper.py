@@ -54,7 +54,10 @@ def _fused_mscam(nets, inputs, scales):
     inputs = L.f32c(inputs)
     b, _, h, w = inputs.shape
     sizes = [(int(s * h), int(s * w)) for s in _scale_order(scales)]  # cam_helper.py:183
-    res = cam_only_forward(nets, inputs, seg_images=[inputs] * len(sizes), seg_sizes=sizes, flip_twin=True)
+    # The un-flipped scale-1.0 half of this pass IS the training forward of `inputs` (no dropout / batch statistics in
+    # the model): a fused step driver may ask to keep its activations (network._keep_next) and skip that forward.
+    keep = b if all(getattr(n, "_keep_next", False) for n in nets) else 0
+    res = cam_only_forward(nets, inputs, seg_images=[inputs] * len(sizes), seg_sizes=sizes, flip_twin=True, keep_batch=keep)
     return [(ops.mscam_post(cams, b, h, w), ops.mscam_post(aux, b, h, w)) for (aux, cams) in res]
 
 

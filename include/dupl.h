@@ -48,6 +48,7 @@ int64_t dupl_launch_count(void);
 
 #define DUPL_MAX_SEGMENTS 8
 #define DUPL_MAX_GROUPS 2
+#define DUPL_MAX_KSPLIT 8
 
 /* A "segment" is a batch of equally-sized images flowing through the encoder: `batch` images of
  * `tokens` = 1 + gh*gw tokens each, stored at rows [row_offset, row_offset + batch*tokens) of the
@@ -84,16 +85,24 @@ typedef struct {
   void* out_hi;
   void* out_lo;        /* SPLIT / GELU_SPLIT: [M, ldo] */
   const float* pos[DUPL_MAX_SEGMENTS]; /* PATCH: per segment [tokens, N] resized pos_embed */
+  float* splitk_ws;    /* max_ksplit > 1: [max_ksplit, M, ldo] fp32 workspace for the split-K partial sums */
 } dupl_gemm_group;
 
 /* C[M,N] = A[M,K] * W[N,K]^T for `groups` independent problems of identical shape (the two
- * students).  K % 64 == 0, N % 16 == 0, 16-byte aligned planes and row strides. */
+ * students).  K % 64 == 0, N % 16 == 0, 16-byte aligned planes and row strides.
+ * Tile width (256/192/128 columns per CTA pair) and, when max_ksplit > 1, a split-K factor are chosen per
+ * shape so that the work items fill the 74 CTA pairs of a B200; split-K partial sums go through splitk_ws
+ * and are added in a fixed order (bit-reproducible). */
 typedef struct {
   int32_t groups;
   int32_t M, N, K;
   int32_t lda, ldo;
   int32_t epilogue;
   int32_t nseg;                         /* PATCH only */
+  int32_t ldw;                          /* row stride of the W planes in elements (0 = K) */
+  int32_t max_ksplit;                   /* 0/1 = no split-K; else the workspace holds this many partials (F32 epilogue, no bias) */
+  int32_t f32_rows;                     /* GELU_SPLIT: only rows < f32_rows get the out_f32 side output (0 = all rows) */
+  int32_t reserved;
   dupl_segment seg[DUPL_MAX_SEGMENTS];  /* PATCH only: patch row -> token row mapping */
   dupl_gemm_group g[DUPL_MAX_GROUPS];
 } dupl_gemm_args;

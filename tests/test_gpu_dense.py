@@ -62,6 +62,54 @@ def test_gemm_epilogues():
     assert rel_err(out, ref + resid.double()) < 3e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(3140, 768, 768), (3140, 3072, 768), (3140, 768, 3072), (6280, 2304, 768)])
+def test_gemm_tile_width_chosen_by_the_cost_model(M, N, K):
+    """The training shapes (M = 4 x 785) pick 192-wide tiles on a 148-SM part; results must not depend on the tiling."""
+    L, ops = _ops()
+    a, w, bias = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.05), _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm_bf16x3([dict(a=ops.split_bf16(a), w=ops.split_bf16(w), bias=bias, out_f32=out)], M, N, K, L.EPI_F32)
+    ref = a.double() @ w.double().t() + bias.double()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 3200), (3072, 768, 3200), (2304, 768, 3200), (64, 512, 3136), (512, 6912, 3136)])
+def test_gemm_split_k_is_exact_and_reproducible(M, N, K):
+    """wgrad shapes: few output tiles, long contraction -> split-K through a workspace, fixed summation order."""
+    L, ops = _ops()
+    a, w = _rand(M, K, seed=5), _rand(N, K, seed=6, scale=0.05)
+    A, W = ops.split_bf16(a), ops.split_bf16(w)
+    outs = []
+    for _ in range(2):
+        out = torch.full((M, N), float("nan"), device="cuda")
+        ops.gemm_bf16x3([dict(a=A, w=W, out_f32=out)], M, N, K, L.EPI_F32, ksplit=L.MAX_KSPLIT)
+        outs.append(out)
+    ref = a.double() @ w.double().t()
+    assert torch.isfinite(outs[0]).all()
+    assert rel_err(outs[0], ref) < 3e-5
+    assert torch.equal(outs[0], outs[1])
+    plain = torch.empty(M, N, device="cuda")
+    ops.gemm_bf16x3([dict(a=A, w=W, out_f32=plain)], M, N, K, L.EPI_F32)
+    assert rel_err(outs[0], plain.double()) < 3e-5
+
+
+def test_gemm_gelu_side_output_row_limit():
+    L, ops = _ops()
+    M, N, K, keep = 700, 768, 256, 300
+    a, w, bias = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.1), _rand(N, seed=3)
+    hi, lo = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"), torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    pre = torch.full((keep, N), float("nan"), device="cuda")
+    guard = torch.full((M - keep, N), 7.0, device="cuda")  # would be overwritten if the limit were ignored
+    buf = torch.cat([pre, guard])
+    ops.gemm_bf16x3([dict(a=ops.split_bf16(a), w=ops.split_bf16(w), bias=bias, out=(hi, lo), out_f32=buf)], M, N, K,
+                    L.EPI_GELU_SPLIT, f32_rows=keep)
+    ref = a.double() @ w.double().t() + bias.double()
+    assert rel_err(buf[:keep], ref[:keep]) < 3e-5
+    assert (buf[keep:] == 7.0).all()
+    assert rel_err(hi.float() + lo.float(), torch.nn.functional.gelu(ref)) < 5e-5
+
+
 def test_gemm_rejects_bad_arguments():
     L, ops = _ops()
     a, w = _rand(16, 60), _rand(16, 60)

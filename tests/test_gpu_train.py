@@ -112,3 +112,30 @@ def test_phase_b_step_losses_and_gradients_match_oracle_loop():
         if e >= 2e-3:
             bad.append((name, round(e, 5)))
     assert not bad, bad[:10]
+
+
+def test_forward_reuse_from_the_mscam_pass_is_bit_identical():
+    """PhaseBStep(reuse_forward=True) starts the training pass from the activations the MS-CAM pass kept for the
+    un-flipped scale-1.0 images instead of running model(inputs) again: losses and every gradient must be bit-equal."""
+    from dupl_b200.train_step import PhaseBStep
+    from helpers import synth_boxes, synth_cls_labels
+    b, S = 2, 64
+    x = synth_images(b, S, S, seed=21).cuda()
+    cls = synth_cls_labels(b, 20, seed=22).cuda()
+    box = synth_boxes(b, S, S, seed=23)
+    results = []
+    for reuse, graph in ((False, False), (True, False), (True, True)):
+        m, _ = _models()
+        step = PhaseBStep(m, None, graph=graph, reuse_forward=reuse)
+        for _ in range(2):  # second call replays the captured graph
+            m.zero_grad(set_to_none=True)
+            loss, parts, labels = step.losses(x, cls, box, 3000)
+            loss.backward()
+        torch.cuda.synchronize()
+        results.append((loss.detach().clone(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    base_loss, base_grads = results[0]
+    for loss, grads in results[1:]:
+        assert torch.equal(loss, base_loss)
+        assert grads.keys() == base_grads.keys()
+        for n in grads:
+            assert torch.equal(grads[n], base_grads[n]), n

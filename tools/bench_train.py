@@ -47,7 +47,7 @@ def main():
     wrapped = model
     if world > 1:
         wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=True)
-    step = PhaseBStep(wrapped, optim, device=dev)
+    step = PhaseBStep(wrapped, optim, device=dev, reuse_forward=not os.environ.get("DUPL_NO_REUSE"))
     x = synth_images(args.batch, args.size, args.size, seed=rank).to(dev)
     cls = synth_cls_labels(args.batch, 20, seed=rank).to(dev)
     box = synth_boxes(args.batch, args.size, args.size, seed=rank)
