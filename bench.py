@@ -1,11 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the DuPL CAM -> PAR -> pseudo-label step (BASELINE.json configs[1]) on B200.
+"""Benchmarks of the DuPL hot path on B200 (BASELINE.json configs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cam_par|train|crf_sweep]
 
-One "step" = one pass of the hot path over one synthetic VOC batch (b=4 per GPU, 448x448, K=20):
-multi_scale_cam2_siamese (scales 1.0/0.5/1.5 + flip) for both students, then
-refine_cams_with_dynamic_thres (PAR, 10 iterations, 48 neighbours) for both students.
+Workloads ("step" = one pass of the path over one synthetic batch):
+  cam_par    (default; BASELINE.json configs[1]) VOC, b=4 per GPU, 448x448: multi_scale_cam2_siamese (scales 1.0/0.5/1.5 +
+             flip) for both students, then refine_cams_with_dynamic_thres (PAR, 10 iterations, 48 neighbours) for both.
+             The line also carries `train_step`: the full dual-student training step measured in the same run.
+  train      (configs[2]/[3]) the full phase-B training step (MS-CAM + PAR pseudo-labels + both students'
+             forward/backward + all losses + AdamW); DDP over NCCL when launched under torchrun.  --dataset voc|coco.
+  crf_sweep  (configs[4]) COCO eval sweep per image: MS-CAM labels (one student) + multi-scale/flip seg logits (both
+             students) + DenseCRF mean-field (10 iterations, 640x480x81) on the GPU; images strided over ranks.
 Prints ONE JSON line on rank 0 (contract in the task statement; keys explained in DESIGN.md §Measurement).
 """
 import argparse
@@ -14,7 +19,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -23,16 +27,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
-K_CLASSES = 20
 BATCH = 4
 SIZE = 448
 SCALES = (1.0, 0.5, 1.5)
-METRIC = "cam_par_refine_images_per_sec"
 UNIT = "images/s"
 
-# Algorithmic work of the step: matmul+conv FLOPs of the reference's cam_only passes,
-# both students, flip twins included: 2 * 2 * (157.04 + 35.14 + 416.85) GFLOP per image.
-GFLOP_PER_IMAGE = 2436.1
+# Algorithmic work: matmul+conv FLOPs of the reference, both students, flip twins included.
+GFLOP_PER_IMAGE_CAM = 2436.1      # 2 * 2 * (157.04 + 35.14 + 416.85)
+GFLOP_PER_IMAGE_TRAIN = 3433.6    # + 2 * 166.25 * 3 (fwd + dgrad + wgrad)
 
 
 def load_peaks():
@@ -44,10 +46,10 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def make_inputs(rank):
+def make_inputs(rank, K):
     from helpers import synth_boxes, synth_cls_labels, synth_images
     x = synth_images(BATCH, SIZE, SIZE, seed=rank)
-    cls = synth_cls_labels(BATCH, K_CLASSES, seed=rank)
+    cls = synth_cls_labels(BATCH, K, seed=rank)
     box = synth_boxes(BATCH, SIZE, SIZE, seed=rank)
     thr = torch.full((BATCH,), 0.65)
     return x, cls, box, thr
@@ -98,9 +100,9 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_step(P, x, cls, box, thr, n_images, students=(1, 2)):
-    """The same step on the host cores through the CPU oracle (reference restatement), on `n_images`
-    images of the batch.  Returns seconds."""
+# ======================================================================================= CPU arms (oracle port)
+def cpu_cam_par(P, x, cls, box, thr, n_images, students=(1, 2)):
+    """cam_par on the host cores through the CPU oracle (reference restatement), on `n_images` images.  Seconds."""
     from oracle import dupl_oracle as O
     x, cls, box, thr = x[:n_images], cls[:n_images], box[:n_images], thr[:n_images]
     h, w = x.shape[-2:]
@@ -114,105 +116,283 @@ def cpu_oracle_step(P, x, cls, box, thr, n_images, students=(1, 2)):
     return time.perf_counter() - t0
 
 
+def cpu_train(P, x, cls, box, size):
+    """one image of the phase-B step (losses + backward) through the CPU oracle at a reduced resolution `size`
+    (the full 448^2 step costs minutes per image on the host).  Seconds."""
+    from oracle import dupl_oracle as O
+    xs = torch.nn.functional.interpolate(x[:1], size=(size, size), mode="bilinear", align_corners=False)
+    bx = torch.tensor([[0, size, 0, size]], dtype=torch.int16)
+    Pg = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+    t0 = time.perf_counter()
+    loss, _, _ = O.phase_b_losses(Pg, xs, cls[:1], bx, 3000)
+    loss.backward()
+    return time.perf_counter() - t0
+
+
+def cpu_crf(img_u8, prob, iters=10):
+    from oracle.densecrf_ref import DenseCRF as RefCRF
+    t0 = time.perf_counter()
+    RefCRF(iters, 1, 1, 4, 121, 5)(img_u8, prob)
+    return time.perf_counter() - t0
+
+
+def synth_coco_image(seed, H=480, W=640):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 256, (H, W, 3)).astype("uint8")
+    t = torch.from_numpy(img).permute(2, 0, 1).float()[None]
+    return torch.nn.functional.avg_pool2d(t, 5, 1, 2, count_include_pad=False)[0].permute(1, 2, 0).round().to(torch.uint8).contiguous()
+
+
+def normalise_u8(img_u8):
+    from helpers import MEAN, STD
+    x = img_u8.permute(2, 0, 1).float()[None]
+    for c in range(3):
+        x[:, c] = (x[:, c] - MEAN[c]) / STD[c]
+    return x
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The reference is pure Python/PyTorch (no compiled
-    code of its own) and /root/reference does not exist on the GPU box, so its CPU restatement
-    (oracle/dupl_oracle.py, pinned against the reference in tests/) is timed with all host threads."""
+    """--impl reference: the reference's CPU path.  The reference is pure Python/PyTorch (no compiled code of its own)
+    and /root/reference does not exist on the GPU box, so its CPU restatement (oracle/, pinned against the reference
+    in tests/) is timed with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from helpers import init_state_dict
-    P = init_state_dict(K_CLASSES + 1)
-    x, cls, box, thr = make_inputs(0)
-    n_img = 1
-    times = []
-    for i in range(args.warmup + args.steps):
-        # bounded sample: one image of the batch, ONE student (the two students cost the same)
-        t = cpu_oracle_step(P, x, cls, box, thr, n_img, students=(1,)) * 2.0
-        if i >= args.warmup:
-            times.append(t)
-    ms = 1000.0 * sum(times) / len(times)
-    val = n_img / (ms / 1000.0)
+    K = 80 if (args.dataset == "coco" or args.workload == "crf_sweep") else 20
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    times = []
+    if args.workload == "cam_par":
+        P = init_state_dict(K + 1)
+        x, cls, box, thr = make_inputs(0, K)
+        sample = "1 of 4 images; MS-CAM + PAR refine for student 1, time doubled for the two students"
+        for i in range(args.warmup + args.steps):
+            t = cpu_cam_par(P, x, cls, box, thr, 1, students=(1,)) * 2.0
+            if i >= args.warmup:
+                times.append(t)
+        metric, workload = "cam_par_refine_images_per_sec", "voc21_dual_student_cam_par_refine_448_bs4"
+    elif args.workload == "train":
+        P = init_state_dict(K + 1)
+        x, cls, box, thr = make_inputs(0, K)
+        size = 224
+        sample = (f"1 image at {size}x{size} (full phase-B losses + backward of both students), time scaled by the "
+                  f"algorithmic FLOP ratio of 448^2 to {size}^2 (x4.47)")
+        for i in range(args.warmup + args.steps):
+            t = cpu_train(P, x, cls, box, size) * 4.47
+            if i >= args.warmup:
+                times.append(t)
+        metric, workload = "train_images_per_sec", f"{args.dataset}_dual_student_phaseB_step_448_bs4"
+    else:
+        img = synth_coco_image(0)
+        g = torch.Generator().manual_seed(0)
+        lg = torch.randn(1, 81, 28, 28, generator=g) * 2.0
+        prob = torch.softmax(torch.nn.functional.interpolate(lg, size=img.shape[:2], mode="bilinear", align_corners=False), 1)[0].numpy()
+        sample = "DenseCRF stage only (C restatement, 1 thread) of 1 image 640x480x81; the dense passes of the sweep are not included"
+        cores = 1
+        for i in range(args.warmup + args.steps):
+            t = cpu_crf(img.numpy(), prob)
+            if i >= args.warmup:
+                times.append(t)
+        metric, workload = "crf_sweep_images_per_sec", "coco81_mscam_mscseg_densecrf_640x480"
+    ms = 1000.0 * sum(times) / len(times)
+    val = 1.0 / (ms / 1000.0)
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "voc21_dual_student_cam_par_refine_448_bs4 (sample: 1 image, student 1 timed and doubled)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "1 of 4 images; MS-CAM + PAR refine for student 1, time doubled for the two students"},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload + f" (sample: {sample})"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="dupl_b200", choices=["dupl_b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fuse-students", action="store_true", help="both students per grouped GEMM launch")
-    ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 0)
-    if args.impl == "reference":
-        return run_reference(args)
+# ======================================================================================= GPU arm
+class Harness:
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: dupl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.stream = torch.cuda.current_stream()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: dupl_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
 
+    def time_device(self, fn, steps):
+        """CUDA events on the launching stream around `steps` calls, barrier + synchronize on both sides."""
+        self.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        t1.record(self.stream)
+        self.barrier()
+        return t0.elapsed_time(t1)
+
+    def time_wall(self, fn, steps):
+        self.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        return (time.perf_counter() - w0) * 1000.0
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def finish(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+class GemmTimer:
+    """Per-launch CUDA-event timing of the dominant kernel (the tcgen05 GEMM) on the launching stream."""
+
+    def __init__(self, stream):
+        from dupl_b200 import ops
+        import dupl_b200.encoder as enc_mod
+        import dupl_b200.train as train_mod
+        import dupl_b200.dense as dense_mod
+        self.ops, self.mods, self.stream = ops, (ops, enc_mod.ops, train_mod.ops, dense_mod.ops), stream
+        self.orig = ops.gemm_bf16x3
+        self.events = []
+
+    def __enter__(self):
+        orig, events, stream = self.orig, self.events, self.stream
+
+        def timed(groups, M, N, K, epilogue, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            orig(groups, M, N, K, epilogue, **kw)
+            e1.record(stream)
+            events.append((e0, e1, 2.0 * M * N * K * len(groups)))
+        for m in self.mods:
+            m.gemm_bf16x3 = timed
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            m.gemm_bf16x3 = self.orig
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.events)
+        flop = sum(f for _, _, f in self.events)
+        return ms, flop, len(self.events)
+
+
+def gemm_roofline(timer, peaks, peak_kind, step_tflops, timed_in):
+    gemm_ms, gemm_flop, n_gemm = timer.summary()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "gemm_bf16x3_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved / peak_tf if peak_tf else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fc1-shaped launch (M=21976, N=3072, K=768),
+            # ncu --set full capture of this command, profiles/r01_summary.md
+            "traffic": TRAFFIC_GEMM_BYTES,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})",
+            "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "timed_in": timed_in,
+            "note": "achieved = algorithmic fp32-GEMM FLOPs (2MNK) / CUDA-event time; the kernel issues 3 bf16 MMAs per "
+                    "product (split operands), so the tensor pipe does 3x this figure and frac is capped at 1/3",
+            "step_tflops": step_tflops}
+
+
+TRAFFIC_GEMM_BYTES = None  # filled from the committed ncu capture (profiles/); None until one exists for this build
+
+
+def build_model(K, dev, train=False):
     from helpers import init_state_dict
-    from dupl_b200 import _lib as L, ops
     from dupl_b200.model.model_dupl import siamese_network
-    from dupl_b200.pipeline import CamParStep
-
-    P = init_state_dict(K_CLASSES + 1)
-    model = siamese_network("deit_base_patch16_224", num_classes=K_CLASSES + 1, pretrained=False, aux_layer=-3)
+    P = init_state_dict(K + 1)
+    model = siamese_network("deit_base_patch16_224", num_classes=K + 1, pretrained=False, aux_layer=-3 if K == 20 else 9)
     model.load_state_dict(P, strict=True)
-    model = model.to(dev).eval()
+    model = model.to(dev)
+    return (model.train() if train else model.eval()), P
+
+
+def measure_train(h, args, K, steps, warmup, want_roofline):
+    """Full phase-B step.  Returns dict(ms, e2e_ms, launches, timer, h2d, d2h, loss)."""
+    from dupl_b200 import _lib as L
+    from dupl_b200.train_step import PhaseBStep, make_optimizer, Args
+    model, P = build_model(K, h.dev, train=True)
+    optim = make_optimizer(model)
+    wrapped = model
+    if h.world > 1:
+        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[h.local_rank], find_unused_parameters=True)
+    targs = Args if K == 20 else Args.coco()
+    step = PhaseBStep(wrapped, optim, args=targs, device=h.dev)
+    x, cls, box, _ = make_inputs(h.rank, K)
+    x_pin, cls_pin = x.pin_memory(), cls.pin_memory()
+    x_dev, cls_dev = x.to(h.dev), cls.to(h.dev)
+    it = [3000]
+    last = {}
+
+    def device_step():
+        last["loss"], _ = step(x_dev, cls_dev, box, it[0])
+        it[0] += 1
+
+    def e2e_step():
+        xi = x_pin.to(h.dev, non_blocking=True)
+        ci = cls_pin.to(h.dev, non_blocking=True)
+        loss, _ = step(xi, ci, box, it[0])
+        it[0] += 1
+        last["loss_host"] = loss.item()   # device -> host read of the step's result
+
+    for _ in range(warmup):
+        device_step()
+    ms = h.time_device(device_step, steps)
+    out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 + cls_pin.numel() * 4), d2h=4, P=P, inputs=(x, cls, box))
+    timer = None
+    if want_roofline:
+        eager = PhaseBStep(wrapped, optim, args=targs, device=h.dev, graph=False)
+        eager(x_dev, cls_dev, box, it[0])
+        launches0 = L.lib().dupl_launch_count()
+        with GemmTimer(h.stream) as timer:
+            h.barrier()
+            for _ in range(steps):
+                eager(x_dev, cls_dev, box, it[0])
+            h.barrier()
+        out["launches"] = int(L.lib().dupl_launch_count() - launches0)
+    e2e_step()
+    out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps
+    out["timer"] = timer
+    out["loss"] = float(last["loss"].item())
+    out["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    return out
+
+
+def run_cam_par(h, args):
+    from dupl_b200 import _lib as L, ops
+    from dupl_b200.pipeline import CamParStep
+    K = 20
+    model, P = build_model(K, h.dev)
     step = CamParStep(model, SCALES, fuse_students=args.fuse_students, graph=not args.no_graph)
     eager = CamParStep(model, SCALES, fuse_students=args.fuse_students)
-    step.par.to(dev)
-
-    x, cls, box, thr = make_inputs(rank)
+    step.par.to(h.dev)
+    x, cls, box, thr = make_inputs(h.rank, K)
     x_pin, cls_pin, thr_pin = x.pin_memory(), cls.pin_memory(), thr.pin_memory()
-    x_dev, cls_dev, thr_dev = x.to(dev), cls.to(dev), thr.to(dev)
+    x_dev, cls_dev, thr_dev = x.to(h.dev), cls.to(h.dev), thr.to(h.dev)
     out_pin = torch.empty(2, BATCH, SIZE, SIZE, dtype=torch.float32).pin_memory()
-    stream = torch.cuda.current_stream()
-
-    # per-launch timing of the dominant kernel (the tcgen05 GEMM): events on the launching stream
-    gemm_events = []
-    orig_gemm = ops.gemm_bf16x3
-
-    def timed_gemm(groups, M, N, K, epilogue, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        orig_gemm(groups, M, N, K, epilogue, **kw)
-        e1.record(stream)
-        gemm_events.append((e0, e1, 2.0 * M * N * K * len(groups)))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def device_step():
         return step(x_dev, cls_dev, box, thr_dev)
 
     def e2e_step():
-        xi = x_pin.to(dev, non_blocking=True)
-        ci = cls_pin.to(dev, non_blocking=True)
-        ti = thr_pin.to(dev, non_blocking=True)
+        xi = x_pin.to(h.dev, non_blocking=True)
+        ci = cls_pin.to(h.dev, non_blocking=True)
+        ti = thr_pin.to(h.dev, non_blocking=True)
         l1, l2, _, _ = step(xi, ci, box, ti)
         out_pin[0].copy_(l1, non_blocking=True)
         out_pin[1].copy_(l2, non_blocking=True)
@@ -220,53 +400,29 @@ def main():
 
     for _ in range(args.warmup):
         device_step()
-    barrier()
-
-    # ---- timed region 1: inputs resident in HBM (the step is replayed as one CUDA graph unless --no-graph)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    h.barrier()
+    sampler = ClockSampler(h.local_rank)
+    if h.rank == 0:
         sampler.start()
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    for _ in range(args.steps):
-        device_step()
-    t1.record(stream)
-    barrier()
-    ms_total = t0.elapsed_time(t1)
-
+    # ---- timed region 1: inputs resident in HBM (the step is replayed as one CUDA graph unless --no-graph)
+    ms_total = h.time_device(device_step, args.steps)
     # ---- same K steps launched kernel by kernel with CUDA events around every GEMM launch (roofline of the dominant
     #      kernel) and the library's launch counter (kernels per step)
-    import dupl_b200.encoder as enc_mod
     eager(x_dev, cls_dev, box, thr_dev)
-    ops.gemm_bf16x3 = timed_gemm
-    enc_mod.ops.gemm_bf16x3 = timed_gemm
     launches0 = L.lib().dupl_launch_count()
-    barrier()
-    for _ in range(args.steps):
-        eager(x_dev, cls_dev, box, thr_dev)
-    barrier()
+    with GemmTimer(h.stream) as timer:
+        h.barrier()
+        for _ in range(args.steps):
+            eager(x_dev, cls_dev, box, thr_dev)
+        h.barrier()
     launches = L.lib().dupl_launch_count() - launches0
-    ops.gemm_bf16x3 = orig_gemm
-    enc_mod.ops.gemm_bf16x3 = orig_gemm
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
-    gemm_flop = sum(f for _, _, f in gemm_events)
-    n_gemm = len(gemm_events)
-
     # ---- timed region 2: end to end through the public API with host buffers
     e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms_total = (time.perf_counter() - w0) * 1000.0
-    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms_total = h.time_wall(e2e_step, args.steps)
+    clocks = sampler.stop() if h.rank == 0 else None
 
     breakdown = None
-    if args.breakdown and rank == 0:
-        import dupl_b200.utils.cam_helper as ch_mod
-        import dupl_b200.model.model_dupl as md_mod
+    if args.breakdown and h.rank == 0:
         recs = []
         names = ["gemm_bf16x3", "attention_fwd", "layernorm_split", "patchify", "cls_rows", "cam_contract", "mscam_post",
                  "par_affinity", "par_propagate", "refine_prologue", "refine_epilogue", "split_bf16", "pos_embed_resize"]
@@ -275,18 +431,18 @@ def main():
         def wrap(n, fn):
             def f(*a, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
+                e0.record(h.stream)
                 r = fn(*a, **k)
-                e1.record(stream)
+                e1.record(h.stream)
                 recs.append((n, e0, e1))
                 return r
             return f
         for n in names:
             setattr(ops, n, wrap(n, saved[n]))
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record(stream)
+        w0.record(h.stream)
         eager(x_dev, cls_dev, box, thr_dev)
-        w1.record(stream)
+        w1.record(h.stream)
         torch.cuda.synchronize()
         for n in names:
             setattr(ops, n, saved[n])
@@ -295,51 +451,187 @@ def main():
             breakdown[n] = breakdown.get(n, 0.0) + e0.elapsed_time(e1)
         breakdown = {k: round(v, 3) for k, v in breakdown.items()}
 
-    t = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t[0].item() / args.steps
-    e2e_ms_step = t[1].item() / args.steps
-    imgs = BATCH * world
+    ms_step, e2e_ms_step = [v / args.steps for v in h.max_over_ranks(ms_total, e2e_ms_total)]
+    imgs = BATCH * h.world
 
-    if rank == 0:
+    # ---- secondary figure: the full dual-student training step (configs[2] per-GPU shape) in the same run
+    train = None
+    if not args.no_train_step:
+        del step, eager
+        torch.cuda.empty_cache()
+        t = measure_train(h, args, K, steps=max(5, args.steps // 2), warmup=3, want_roofline=False)
+        tms, te2e = h.max_over_ranks(t["ms"], t["e2e_ms"])
+        train = {"metric": "train_images_per_sec", "value": imgs / (tms / 1000.0), "unit": UNIT, "ms_per_step": tms,
+                 "e2e": {"value": imgs / (te2e / 1000.0), "unit": UNIT, "ms_per_step": te2e},
+                 "workload": "voc21_dual_student_phaseB_step_448_bs4 (MS-CAM + PAR labels + fwd/bwd of both students + losses + AdamW"
+                             + (", DDP all-reduce)" if h.world > 1 else ")"),
+                 "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2)}
+
+    if h.rank == 0:
         peaks, peak_kind = load_peaks()
-        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "cam_par_refine_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": "voc21_dual_student_cam_par_refine_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
-                       "classes": K_CLASSES + 1, "cam_scales": list(SCALES), "par_iters": 10,
-                       "parallelism": f"dp{world} (independent batches, no collective on this path)",
+                       "classes": K + 1, "cam_scales": list(SCALES), "par_iters": 10,
+                       "parallelism": f"dp{h.world} (independent batches, no collective on this path)",
                        "l2_policy": "per-step working set ~1.5 GB per student >> 126 MB L2; no explicit flush",
-                       "fuse_students": bool(args.fuse_students),
-                       "cuda_graph": not args.no_graph},
+                       "fuse_students": bool(args.fuse_students), "cuda_graph": not args.no_graph},
             "e2e": {"value": imgs / (e2e_ms_step / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(x_pin.numel() * 4 + cls_pin.numel() * 4 + thr_pin.numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": e2e_ms_step},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})",
-                         "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
-                         "timed_in": "the same K steps launched eagerly right after the (graph-replayed) timed region",
-                         "note": "achieved = algorithmic fp32-GEMM FLOPs (2MNK) / CUDA-event time; the kernel issues 3 bf16 "
-                                 "MMAs per product (split operands), so the tensor pipe does 3x this figure",
-                         "step_tflops": GFLOP_PER_IMAGE * 1e9 * BATCH / (ms_step * 1e-3) / 1e12},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": gemm_roofline(timer, peaks, peak_kind, GFLOP_PER_IMAGE_CAM * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
+                                      "the same K steps launched eagerly right after the (graph-replayed) timed region"),
         }
+        if train is not None:
+            line["train_step"] = train
         if breakdown is not None:
             line["breakdown_ms"] = breakdown
-        if world == 1 and not args.no_cpu_baseline:
+        if h.world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            secs = cpu_oracle_step(P, x, cls, box, thr, 1, students=(1,)) * 2.0
+            secs = cpu_cam_par(P, x, cls, box, thr, 1, students=(1,)) * 2.0
             line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "1 of 4 images; MS-CAM + PAR refine for student 1 timed once, doubled for the two students"}
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+
+
+def run_train(h, args):
+    K = 80 if args.dataset == "coco" else 20
+    sampler = ClockSampler(h.local_rank)
+    if h.rank == 0:
+        sampler.start()
+    t = measure_train(h, args, K, args.steps, args.warmup, want_roofline=True)
+    clocks = sampler.stop() if h.rank == 0 else None
+    ms_step, e2e_ms = h.max_over_ranks(t["ms"], t["e2e_ms"])
+    imgs = BATCH * h.world
+    if h.rank == 0:
+        peaks, peak_kind = load_peaks()
+        line = {
+            "metric": "train_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"{args.dataset}{K + 1}_dual_student_phaseB_step_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
+                       "classes": K + 1, "parallelism": f"ddp{h.world} (NCCL all-reduce of 732.7 MB fp32 grads per step)" if h.world > 1 else "single GPU",
+                       "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush",
+                       "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images"},
+            "e2e": {"value": imgs / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": t.get("launches"), "clocks": clocks, "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
+            "roofline": gemm_roofline(t["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_TRAIN * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
+                                      "the same K steps with the CAM half launched eagerly (no graph) right after the timed region"),
+        }
+        if h.world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            x, cls, box = t["inputs"]
+            secs = cpu_train(t["P"], x, cls, box, 224) * 4.47
+            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "1 image at 224x224 through the oracle's phase-B losses + backward, scaled by the FLOP ratio 4.47 to 448x448"}
+        print(json.dumps(line))
+
+
+def run_crf_sweep(h, args):
+    """configs[4]: COCO eval sweep; `--steps` images per rank (strided shard of a synthetic list), batch 1 like the tools."""
+    from dupl_b200 import _lib as L, ops
+    from dupl_b200.eval_sweep import SegCrfSweep, shard_indices
+    from helpers import synth_cls_labels
+    K = 80
+    model, _ = build_model(K, h.dev)
+    sweep = SegCrfSweep(model, flavour="coco")
+    n_total = (args.warmup + args.steps) * h.world
+    mine = shard_indices(n_total, h.rank, h.world)
+    imgs_u8 = [synth_coco_image(i) for i in mine]
+    inputs = [torch.nn.functional.interpolate(normalise_u8(im), size=(SIZE, SIZE), mode="bilinear", align_corners=False) for im in imgs_u8]
+    cls = [synth_cls_labels(1, K, seed=i) for i in mine]
+    pin = [(a.pin_memory(), b.pin_memory(), c.pin_memory()) for a, b, c in zip(imgs_u8, inputs, cls)]
+    dev_in = [(a.to(h.dev), b.to(h.dev), c.to(h.dev)) for a, b, c in zip(imgs_u8, inputs, cls)]
+    out_pin = torch.empty(480, 640, dtype=torch.int64).pin_memory()
+    k = [0]
+
+    def device_step():
+        a, b, c = dev_in[k[0] % len(dev_in)]
+        k[0] += 1
+        return sweep([a], b, c, branch=1)
+
+    def e2e_step():
+        a, b, c = pin[k[0] % len(pin)]
+        k[0] += 1
+        out = sweep([a.to(h.dev, non_blocking=True)], b.to(h.dev, non_blocking=True), c.to(h.dev, non_blocking=True), branch=1)
+        out_pin.copy_(out["crf_pred"][0], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(h.local_rank)
+    if h.rank == 0:
+        sampler.start()
+    launches0 = L.lib().dupl_launch_count()
+    ms_total = h.time_device(device_step, args.steps)
+    launches = L.lib().dupl_launch_count() - launches0
+    # CRF stage alone (its own events) for the roofline of the mean-field kernels
+    a, b, c = dev_in[0]
+    seg1, _ = sweep.msc_seg(b)
+    crf_ms = h.time_device(lambda: sweep.crf_prob(a, seg1[:1]), args.steps) / args.steps
+    e2e_step()
+    e2e_total = h.time_wall(e2e_step, args.steps)
+    clocks = sampler.stop() if h.rank == 0 else None
+    ms_step, e2e_ms, crf_ms = h.max_over_ranks(ms_total / args.steps, e2e_total / args.steps, crf_ms)
+    if h.rank == 0:
+        peaks, peak_kind = load_peaks()
+        N, Cn, T = 480 * 640, 81, 10
+        m2, m5 = ops.last_crf_lattice_sizes()
+        per_iter = 0
+        for d, M in ((2, m2), (5, m5)):   # SURVEY §8(d): splat + (d+1) blurs + slice
+            per_iter += (N * Cn * 4 + N * (d + 1) * 8 + M * Cn * 4) + (d + 1) * (2 * M * Cn * 4 + M * 8) + (N * (d + 1) * 8 + M * Cn * 4 + N * Cn * 4)
+        per_iter += 2 * N * Cn * 4
+        achieved = per_iter * T / (crf_ms * 1e-3) / 1e9
+        line = {
+            "metric": "crf_sweep_images_per_sec", "value": h.world / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (CRF) / bf16x3 (dense)", "data": "synthetic",
+            "config": {"workload": "coco81_mscam_mscseg_densecrf_640x480", "images_per_step": 1, "seg_scales": list(sweep.scales),
+                       "cam_scales": list(sweep.cam_scales), "crf": "T=10, (pos_w 1, sxy 1), (bi_w 4, sxy 121, srgb 5)",
+                       "parallelism": f"dp{h.world} (images strided over ranks, no collective)",
+                       "l2_policy": "a different image every step; CRF working set ~0.5 GB >> 126 MB L2"},
+            "e2e": {"value": h.world / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(480 * 640 * 3 + 3 * SIZE * SIZE * 4 + K * 4), "d2h_bytes_per_step": int(480 * 640 * 8)},
+            "gpu_launches": int(launches), "clocks": clocks, "crf_ms_per_image": crf_ms,
+            "lattice_vertices": {"gaussian_d2": m2, "bilateral_d5": m5},
+            "roofline": {"bound": "hbm", "kernel": "crf_* (splat / blur / slice of the two lattices, 10 iterations)", "achieved": achieved,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                         "note": "achieved = SURVEY §8(d) streaming bytes of one image's mean-field / CUDA-event time of the CRF stage"},
+        }
+        if h.world == 1 and not args.no_cpu_baseline:
+            lg = torch.nn.functional.interpolate(seg1[:1].cpu(), size=(480, 640), mode="bilinear", align_corners=False)
+            secs = cpu_crf(imgs_u8[0].numpy(), torch.softmax(lg, 1)[0].numpy())
+            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "DenseCRF stage only of 1 image (C restatement of the lattice mean-field, not pydensecrf)",
+                                    "crf_speedup_vs_1_thread": secs * 1000.0 / crf_ms}
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dupl_b200", choices=["dupl_b200", "reference"])
+    ap.add_argument("--workload", default="cam_par", choices=["cam_par", "train", "crf_sweep"])
+    ap.add_argument("--dataset", default="voc", choices=["voc", "coco"], help="train workload: class count / loss weights")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="cam_par: skip the secondary training-step measurement")
+    ap.add_argument("--fuse-students", action="store_true", help="both students per grouped GEMM launch")
+    ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    h = Harness(args)
+    {"cam_par": run_cam_par, "train": run_train, "crf_sweep": run_crf_sweep}[args.workload](h, args)
+    h.finish()
 
 
 if __name__ == "__main__":

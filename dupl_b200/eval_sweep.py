@@ -1,0 +1,120 @@
+"""Test-time sweep of the reference's eval tools as ONE device-resident pipeline (BASELINE.json configs[4]):
+
+    tools/eval_seg_coco_ddp.py:75-132   multi-scale + flip segmentation logits of both students ("msc_seg")
+    tools/eval_seg_voc.py:50-84         same, VOC flavour (max over scales at label resolution)
+    utils/train_helper.py:120-150       MS-CAM + cam_to_label of the validation loop
+    tools/eval_seg_*.py crf_proc        F.interpolate -> softmax -> DenseCRF(10, 1, 1, 4, 121, 5) -> argmax
+
+The reference writes the logits of every image to .npy files and runs pydensecrf in a joblib CPU pool afterwards
+(rank 0 only).  Here the logits never leave the device and the mean-field runs on the GPU that produced them; images
+are strided over ranks exactly like tools/eval_seg_coco_ddp.py:241 (`range(rank, N, world)`), no collective.
+
+The interpolate / flip / stack glue below is the scripts' own inline torch code (it is not part of any reference
+module); all dense math and the CRF are libdupl.so kernels behind the drop-in modules.
+"""
+import torch
+import torch.nn.functional as F
+
+from .utils import cam_helper
+from .utils.dcrf import DenseCRF
+
+
+def shard_indices(n_items, rank, world):
+    """tools/eval_seg_coco_ddp.py:241: image i belongs to rank i % world."""
+    return list(range(rank, n_items, world))
+
+
+class SegCrfSweep:
+    def __init__(self, model, flavour="coco", scales=None, cam_scales=(1.0, 0.5, 1.5), crop_size=448,
+                 crf=None, bkg_thre=0.5, high_thre=0.7, low_thre=0.25, ignore_index=255):
+        if flavour not in ("coco", "voc"):
+            raise ValueError("flavour must be 'coco' or 'voc'")
+        self.model = model
+        self.flavour = flavour
+        # argparse defaults of the two tools (eval_seg_coco_ddp.py:51, eval_seg_voc.py:35)
+        self.scales = tuple(scales) if scales is not None else ((1.0, 1.25, 1.5) if flavour == "coco" else (1.0, 1.5, 1.25))
+        self.cam_scales = tuple(cam_scales)
+        self.crop_size = crop_size
+        self.crf = crf or DenseCRF(iter_max=10, pos_w=1, pos_xy_std=1, bi_w=4, bi_xy_std=121, bi_rgb_std=5)
+        self.bkg_thre, self.high_thre, self.low_thre, self.ignore_index = bkg_thre, high_thre, low_thre, ignore_index
+
+    # ------------------------------------------------------------------ multi-scale + flip seg logits
+    @torch.no_grad()
+    def _pair_segs(self, x):
+        """both students on [x, flip(x)]; returns the seg logits of the cat batch (eval_seg_*: `model(inputs_cat)`)."""
+        res = self.model(torch.cat([x, x.flip(-1)], dim=0))
+        return res["branch1"][1], res["branch2"][1]
+
+    @staticmethod
+    def _unflip_sum(segs, b):
+        return segs[:b] + segs[b:].flip(-1)
+
+    @torch.no_grad()
+    def msc_seg(self, inputs, label_size=None):
+        """-> (seg_1, seg_2): what the tools store as {"msc_seg": ...} per image (here for a batch of b images).
+
+        coco (eval_seg_coco_ddp.py:77-122): inputs resized to crop_size^2; the un-scaled pass defines (h_s, w_s); other
+        scales are resized to it; flip twin added; SUM over scales.
+        voc (eval_seg_voc.py:54-78): every scale is up-sampled to label_size first; flip twin added; MAX over scales."""
+        b = inputs.shape[0]
+        if self.flavour == "coco":
+            inputs = F.interpolate(inputs, size=[self.crop_size, self.crop_size], mode="bilinear", align_corners=False)
+            _, _, h, w = inputs.shape
+            s1, s2 = self._pair_segs(inputs)
+            acc = [self._unflip_sum(s1, b), self._unflip_sum(s2, b)]
+            hs, ws = acc[0].shape[-2:]
+            for sc in self.scales:
+                if sc == 1.0:
+                    continue
+                x = F.interpolate(inputs, size=[int(h * sc), int(w * sc)], mode="bilinear", align_corners=False)
+                for k, s in enumerate(self._pair_segs(x)):
+                    s = F.interpolate(s, size=(hs, ws), mode="bilinear", align_corners=False)
+                    acc[k] = acc[k] + self._unflip_sum(s, b)
+            return acc[0], acc[1]
+        if label_size is None:
+            label_size = tuple(inputs.shape[-2:])
+        _, _, h, w = inputs.shape
+        best = [None, None]
+        for sc in self.scales:
+            x = F.interpolate(inputs, size=[int(h * sc), int(w * sc)], mode="bilinear", align_corners=False)
+            for k, s in enumerate(self._pair_segs(x)):
+                s = F.interpolate(s, size=label_size, mode="bilinear", align_corners=False)
+                s = self._unflip_sum(s, b)
+                best[k] = s if best[k] is None else torch.maximum(best[k], s)
+        return best[0], best[1]
+
+    # ------------------------------------------------------------------ CRF stage (crf_proc._job)
+    @torch.no_grad()
+    def crf_prob(self, image_u8, logits):
+        """image_u8 uint8 [H,W,3] (cuda), logits [1,C,h,w] -> Q float32 [C,H,W] on the device."""
+        H, W = image_u8.shape[:2]
+        logit = F.interpolate(logits, size=(H, W), mode="bilinear", align_corners=False)
+        prob = F.softmax(logit, dim=1)[0]
+        return self.crf(image_u8, prob)
+
+    # ------------------------------------------------------------------ CAM pseudo labels (validate_siamase*)
+    @torch.no_grad()
+    def cam_label(self, inputs, cls_label, label_size, branch=1):
+        x = F.interpolate(inputs, size=[self.crop_size, self.crop_size], mode="bilinear", align_corners=False)
+        cams, _aux = cam_helper.multi_scale_cam2_siamese(self.model, inputs=x, scales=self.cam_scales, branch=branch)
+        resized = F.interpolate(cams, size=label_size, mode="bilinear", align_corners=False)
+        return cam_helper.cam_to_label(resized, cls_label, bkg_thre=self.bkg_thre, high_thre=self.high_thre,
+                                       low_thre=self.low_thre, ignore_index=self.ignore_index)
+
+    @torch.no_grad()
+    def __call__(self, images_u8, inputs, cls_label, branch=1):
+        """One batch of the sweep.  images_u8: list of uint8 [H_i,W_i,3] cuda tensors (original images, CRF appearance
+        term); inputs [b,3,H,W] normalised (already at crop size for coco); cls_label [b,K].
+        Returns dict(seg_pred=[...], crf_pred=[...], cam_label=Tensor) with per-image int64 label maps on the device."""
+        b = inputs.shape[0]
+        label_size = tuple(images_u8[0].shape[:2])
+        seg_1, seg_2 = self.msc_seg(inputs, label_size)
+        seg = seg_1 if branch == 1 else seg_2
+        out = dict(seg_pred=[], crf_pred=[])
+        for i in range(b):
+            H, W = images_u8[i].shape[:2]
+            up = F.interpolate(seg[i:i + 1], size=(H, W), mode="bilinear", align_corners=False)
+            out["seg_pred"].append(up.argmax(1)[0])
+            out["crf_pred"].append(self.crf_prob(images_u8[i], seg[i:i + 1]).argmax(0))
+        out["cam_label"] = self.cam_label(inputs, cls_label, label_size, branch)
+        return out

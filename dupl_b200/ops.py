@@ -353,4 +353,13 @@ def crf_inference(image_u8, unary_or_probs, iters, pos_w, pos_xy_std, bi_w, bi_x
     vals = ws.get_values(nv.value, dev)
     a.values, a.values_bytes = vals.data_ptr(), vals.numel()
     L.check(L.lib().dupl_crf_infer(C.byref(a), m[0], m[1], st), "dupl_crf_infer")
+    _LAST_CRF_SIZES[:] = [m[0], m[1]]
     return out, (m[0], m[1])
+
+
+_LAST_CRF_SIZES = [0, 0]
+
+
+def last_crf_lattice_sizes():
+    """(vertices of the d=2 Gaussian lattice, vertices of the d=5 bilateral lattice) of the most recent crf_inference."""
+    return tuple(_LAST_CRF_SIZES)

@@ -27,7 +27,8 @@ class CamParStep:
     """multi_scale_cam2_siamese for both students + refine_cams_with_dynamic_thres for both students."""
 
     def __init__(self, model, cam_scales=(1.0, 0.5, 1.5), low_thre=0.25, ignore_index=255,
-                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False, graph=False, keep_activations=False):
+                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False, graph=False, keep_activations=False,
+                 refine="dynamic", scalar_high_thre=None):
         self.model = model
         self.scales = tuple(cam_scales)
         self.low_thre = low_thre
@@ -38,6 +39,13 @@ class CamParStep:
         # keep the encoder activations of the un-flipped scale-1.0 images on each student (network._kept) so that the
         # training forward of the same step does not recompute them (encoder.KeptActivations)
         self.keep_activations = keep_activations
+        # refine: "dynamic"    refine_cams_with_dynamic_thres on `cams`   (train_final_voc.py:330-343, coco n_iter > 12000)
+        #         "aux_scalar" refine_cams_with_bkg_v2 on `cams_aux` with a scalar high threshold (train_final_coco.py:312-322)
+        #         None         MS-CAM only (phase A: no pseudo-labels yet)
+        if refine not in ("dynamic", "aux_scalar", None):
+            raise ValueError("refine must be 'dynamic', 'aux_scalar' or None")
+        self.refine = refine
+        self.scalar_high_thre = scalar_high_thre
         self._g = None
 
     def __call__(self, inputs, cls_label, img_box, high_thres):
@@ -78,7 +86,8 @@ class CamParStep:
         st["x"].copy_(inputs, non_blocking=True)
         st["cls"].copy_(cls_label, non_blocking=True)
         st["box"].copy_(torch.as_tensor(img_box).to(torch.int32), non_blocking=True)
-        st["thr"].copy_(high_thres, non_blocking=True)
+        if high_thres is not None:
+            st["thr"].copy_(high_thres, non_blocking=True)
 
     @torch.no_grad()
     def _run(self, inputs, cls_label, img_box, high_thres):
@@ -98,11 +107,16 @@ class CamParStep:
         # train_final_voc.py:330-335 multiplies the CAMs by the broadcast cls_label before refining.
         # cls_label is one-hot {0,1}: present classes are multiplied by exactly 1.0 and absent classes are
         # never read by the refine kernels, so the 64 MB elementwise pass is skipped without changing a bit.
-        thr_map = high_thres.to(inputs.device, torch.float32).reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
-        kw = dict(cls_labels=cls_label, high_thre_map=thr_map, low_thre=self.low_thre,
-                  ignore_index=self.ignore_index, img_box=img_box)
         for n in (net.branch1, net.branch2):
             n._keep_next = False
-        lab_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1, **kw)
-        lab_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2, **kw)
+        if self.refine is None:
+            return None, None, (cams_1, aux_1), (cams_2, aux_2)
+        kw = dict(cls_labels=cls_label, low_thre=self.low_thre, ignore_index=self.ignore_index, img_box=img_box)
+        if self.refine == "aux_scalar":
+            lab_1 = cam_helper.refine_cams_with_bkg_v2(self.par, inputs_denorm, cams=aux_1, high_thre=self.scalar_high_thre, **kw)
+            lab_2 = cam_helper.refine_cams_with_bkg_v2(self.par, inputs_denorm, cams=aux_2, high_thre=self.scalar_high_thre, **kw)
+            return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)
+        thr_map = high_thres.to(inputs.device, torch.float32).reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
+        lab_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1, high_thre_map=thr_map, **kw)
+        lab_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2, high_thre_map=thr_map, **kw)
         return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)

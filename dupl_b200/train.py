@@ -231,14 +231,15 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
     if g_seg is not None:
         # conv8 (1x1): seg_rows = h7 @ W8^T
         Cn = net.num_classes
-        d_seg_rows = torch.zeros(Mp, 64, **f32)  # contraction dim of the dgrad padded to 64
-        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_seg)), L.ptr(d_seg_rows), B, np_, Cn, 64, 0, 0, _st(dev)), "dupl_nchw_to_rows_add")
-        dsp, dst = split_transpose(d_seg_rows, Mp, 64)
+        Cp = _pad64(Cn)                             # contraction dim of the dgrad padded to a multiple of 64 (21 -> 64, 81 -> 128)
+        d_seg_rows = torch.zeros(Mp, Cp, **f32)
+        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_seg)), L.ptr(d_seg_rows), B, np_, Cn, Cp, 0, 0, _st(dev)), "dupl_nchw_to_rows_add")
+        dsp, dst = split_transpose(d_seg_rows, Mp, Cp)
         w8 = dp.get("conv8")
-        w8t = transpose_planes(w8, S.n8, 512)                       # [512, 64]
-        d_h7 = dgrad(dsp, w8t, Mp, 512, 64)
+        w8t = transpose_planes(w8, S.n8, 512)                       # [512, pad64(n8)]
+        d_h7 = dgrad(dsp, w8t, Mp, 512, Cp)
         h7t = transpose_planes(S.h7, Mp, 512)
-        dw8 = wgrad(dst, h7t, 64, 512, _pad64(Mp))
+        dw8 = wgrad(dst, h7t, Cp, 512, _pad64(Mp))
         grads["decoder.conv8.weight"] = dw8[:Cn].reshape(Cn, 512, 1, 1).contiguous()
         # conv7 + relu, conv6 + relu
         d_h6 = torch.empty(Mp, 512, **f32)

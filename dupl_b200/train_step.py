@@ -1,7 +1,7 @@
 """The dual-student training step as one callable (driver "M2" of SURVEY §8(b)): a restatement of the
-loop body of train_final_voc.py:186-472 for the phase cam_iters <= n_iter < gmm_iters ("phase B": CAM +
-PAR pseudo-labels + decoder + all losses, no GMM filter / consistency term), built from the drop-in
-modules of this package.  The script-side glue the reference executes with stock torch ops between the
+loop body of train_final_voc.py:186-472 / train_final_coco.py:182-464 for all three phases (A: n_iter < cam_iters,
+CAM + cls/PTC losses; B: + PAR pseudo-labels and seg loss; C: n_iter >= gmm_iters, + the strongly augmented view, the GMM
+noise filter on the GPU and the consistency term), built from the drop-in modules of this package.  The script-side glue the reference executes with stock torch ops between the
 calls into the model / helpers (classification loss, F.interpolate of logits and CAMs, cosine
 discrepancy loss, loss weighting, AdamW) stays stock torch here as well; everything the reference
 reaches through model(...), cam_helper, PAR and model.losses runs in libdupl.so.
@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from .gmm import gmm_noise_filter
 from .model.losses import get_masked_ptc_loss, get_seg_loss_upsampled
 from .model.PAR import PAR
 from .pipeline import CamParStep, denormalize_img2
@@ -45,6 +46,49 @@ class Args:
     warmup_iters = 1500
     warmup_lr = 1e-6
     power = 0.9
+    num_classes = 21
+    gmm_valid_thre = 1.0
+    gamma = 0.95
+    high_thres_target = VOC_HIGH_THRES_TARGET
+    thres_anneal_from = 2000       # cosine_descent(.., n_iter - cam_iters, max_iters - cam_iters), train_final_voc.py:263-265
+    aux_refine_until = None        # COCO only: refine_cams_with_bkg_v2 on cams_aux while n_iter <= 12000
+    ptc_in_phase_a = True          # COCO sets ptc_loss = 1 (weight 0) before cam_iters, train_final_coco.py:216
+
+    @staticmethod
+    def loss_weights(n_iter):
+        """train_final_voc.py:451-456"""
+        if n_iter <= Args.cam_iters:
+            return dict(cls=1.0, ptc=Args.w_ptc, seg=0.0, sim=0.1, reg=0.0)
+        if n_iter <= Args.gmm_iters:
+            return dict(cls=1.0, ptc=Args.w_ptc, seg=Args.w_seg, sim=0.1, reg=0.0)
+        return dict(cls=1.0, ptc=Args.w_ptc, seg=Args.w_seg, sim=0.1, reg=0.05)
+
+    @staticmethod
+    def coco():
+        return CocoArgs
+
+
+class CocoArgs(Args):
+    """Defaults of train_final_coco.py:33-90 and the constants inlined in its loop body."""
+    num_classes = 81
+    bkg_thre = 0.45
+    high_thre = 0.65
+    cam_iters = 8000
+    gmm_iters = 32000
+    max_iters = 80000
+    high_thres_target = (0.55,) * 80   # train_final_coco.py:161-162
+    thres_anneal_from = 12000          # train_final_coco.py:240-242
+    aux_refine_until = 12000           # train_final_coco.py:312-333
+    ptc_in_phase_a = False
+
+    @staticmethod
+    def loss_weights(n_iter):
+        """train_final_coco.py:441-448"""
+        if n_iter <= 8000:
+            return dict(cls=1.0, ptc=0.0, seg=0.0, sim=0.0, reg=0.0)
+        if n_iter <= 12000:
+            return dict(cls=1.0, ptc=0.0, seg=0.2, sim=0.05, reg=0.0)
+        return dict(cls=1.0, ptc=0.2, seg=0.2, sim=0.05, reg=0.05)
 
 
 def cosine_descent(max_thres, min_thres, step, num_steps):
@@ -94,69 +138,140 @@ def make_optimizer(model, args=Args):
         warmup_ratio=args.warmup_lr, power=args.power, fused=True if on_gpu else None)
 
 
-class PhaseBStep:
+class TrainStep:
+    """One iteration of the training loop for any n_iter (phases A / B / C of train_final_voc.py:186-472 and
+    train_final_coco.py:182-464).  `PhaseBStep` is the historical name of the same class."""
+
     def __init__(self, model, optim=None, args=Args, device=None, graph=True, reuse_forward=True):
         self.model = model          # siamese_network or DistributedDataParallel(siamese_network)
         self.optim = optim
         self.args = args
         dev = device or next(model.parameters()).device
         self.par = PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24]).to(dev)
-        # the no-grad half of the step (MS-CAM of both students + PAR refinement) replayed as one CUDA graph
         # reuse_forward: `model(inputs)` of train_final_voc.py:287 recomputes what the MS-CAM pass has just computed for
         # the un-flipped scale-1.0 images (identical arithmetic: no dropout, no batch statistics); keep those activations
         # and start the training pass at the final LayerNorm.
         self.reuse_forward = reuse_forward and 1.0 in tuple(args.cam_scales)
+        # the no-grad half of the step (MS-CAM of both students + PAR refinement) replayed as one CUDA graph
         self.pseudo = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph,
                                  keep_activations=self.reuse_forward)
         self.pseudo.par = self.par
-        self.thres_start = torch.ones(20, device=dev) * args.high_thre
-        self.thres_target = torch.tensor(VOC_HIGH_THRES_TARGET, device=dev)
+        # phase A and the COCO 8000 < n_iter <= 12000 window need other label sources: separate (graph-replayed) variants
+        self._cam_only = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph,
+                                    keep_activations=self.reuse_forward, refine=None)
+        self._cam_aux = CamParStep(model, args.cam_scales, low_thre=args.low_thre, ignore_index=args.ignore_index, graph=graph,
+                                   keep_activations=self.reuse_forward, refine="aux_scalar", scalar_high_thre=args.high_thre)
+        for st in (self._cam_only, self._cam_aux):
+            st.par = self.par
+        K = args.num_classes - 1
+        self.thres_start = torch.ones(K, device=dev) * args.high_thre
+        self.thres_target = torch.tensor(args.high_thres_target, dtype=torch.float32, device=dev)
 
-    def losses(self, inputs, cls_label, img_box, n_iter):
-        a = self.args
+    # ------------------------------------------------------------------ pieces
+    def _forward(self, inputs, inputs_aug=None):
         model = self.model
-        b, _, h, w = inputs.shape
-        # per-image high threshold = max over the present classes of the cosine-annealed class thresholds
-        thres = cosine_descent(self.thres_start, self.thres_target, n_iter - a.cam_iters, a.max_iters - a.cam_iters)
-        high_thres = torch.where(cls_label > 0, thres[None, :], thres.new_full((), -math.inf)).amax(1)
-
-        # multi_scale_cam2_siamese x2 and refine_cams_with_dynamic_thres x2 (train_final_voc.py:279-284, 330-343).
-        # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels).
-        label_1, label_2, (cams_1, cams_aux_1), (cams_2, cams_aux_2) = self.pseudo(inputs, cls_label, img_box, high_thres)
         net = model.module if hasattr(model, "module") else model
         for n in (net.branch1, net.branch2):
             n._use_kept = self.reuse_forward
-        res = model(inputs)
+        if inputs_aug is None:
+            res = model(inputs)
+        else:
+            res = model(torch.cat([inputs, inputs_aug], dim=0), need_sp=True)
         for n in (net.branch1, net.branch2):
             n._use_kept = False
+        return res
+
+    def _ptc(self, cams_aux, fmap, cls_label, img_box, high):
+        a = self.args
+        resized = F.interpolate(cams_aux, size=fmap.shape[2:], mode="bilinear", align_corners=False)
+        fn = cam_helper.cam_to_label if not torch.is_tensor(high) else cam_helper.cam_to_label_dynamic_cls
+        _, pseudo = fn(resized.detach(), cls_label=cls_label, img_box=img_box, ignore_mid=True, bkg_thre=a.bkg_thre,
+                       high_thre=high, low_thre=a.low_thre, ignore_index=a.ignore_index)
+        return get_masked_ptc_loss(fmap, cam_helper.label_to_aff_mask(pseudo))
+
+    def losses(self, inputs, cls_label, img_box, n_iter, inputs_aug=None):
+        """-> (loss, dict of parts, (refined_label_1, refined_label_2) or None).  inputs_aug: the strongly augmented view
+        (imutils.augment_data_strong, CPU PIL in the reference: the caller's business); required once n_iter >= gmm_iters."""
+        a = self.args
+        cls_f = cls_label.float()
+        one = inputs.new_ones(())
+        labels = None
+        if n_iter < a.cam_iters:
+            # ---------------- phase A (train_final_voc.py:194-258, train_final_coco.py:190-231)
+            (cams_1, cams_aux_1), (cams_2, cams_aux_2) = self._cam_only(inputs, cls_f, img_box, None)[2:]
+            res = self._forward(inputs)
+            high_thres = a.high_thre
+        else:
+            # per-image high threshold = max over the present classes of the cosine-annealed class thresholds
+            thres = cosine_descent(self.thres_start, self.thres_target, n_iter - a.thres_anneal_from, a.max_iters - a.thres_anneal_from)
+            high_thres = torch.where(cls_f > 0, thres[None, :], thres.new_full((), -math.inf)).amax(1)
+            # multi_scale_cam2_siamese x2 and refine_cams_with_* x2 (train_final_voc.py:279-284, 330-343; coco :312-333).
+            # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels).
+            pseudo = self._cam_aux if (a.aux_refine_until is not None and n_iter <= a.aux_refine_until) else self.pseudo
+            label_1, label_2, (cams_1, cams_aux_1), (cams_2, cams_aux_2) = pseudo(inputs, cls_f, img_box, high_thres)
+            labels = (label_1, label_2)
+            phase_c = n_iter >= a.gmm_iters
+            if phase_c and inputs_aug is None:
+                raise ValueError("n_iter >= gmm_iters needs inputs_aug (the strongly augmented view)")
+            res = self._forward(inputs, inputs_aug if phase_c else None)
         cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
         cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
 
         cls_loss = (F.multilabel_soft_margin_loss(cls_1, cls_label) + F.multilabel_soft_margin_loss(cls_aux_1, cls_label) +
                     F.multilabel_soft_margin_loss(cls_2, cls_label) + F.multilabel_soft_margin_loss(cls_aux_2, cls_label))
 
-        ptc_loss = 0
-        for cams_aux, fmap in ((cams_aux_1, fmap_1), (cams_aux_2, fmap_2)):
-            resized = F.interpolate(cams_aux, size=fmap.shape[2:], mode="bilinear", align_corners=False)
-            _, pseudo = cam_helper.cam_to_label_dynamic_cls(resized.detach(), cls_label=cls_label, img_box=img_box, ignore_mid=True,
-                                                            bkg_thre=a.bkg_thre, high_thre=high_thres, low_thre=a.low_thre,
-                                                            ignore_index=a.ignore_index)
-            ptc_loss = ptc_loss + get_masked_ptc_loss(fmap, cam_helper.label_to_aff_mask(pseudo))
+        if n_iter < a.cam_iters and not a.ptc_in_phase_a:
+            ptc_loss = one                                     # train_final_coco.py:216
+        else:
+            ptc_loss = (self._ptc(cams_aux_1, fmap_1, cls_label, img_box, high_thres) +
+                        self._ptc(cams_aux_2, fmap_2, cls_label, img_box, high_thres))
 
-        # F.interpolate(segs, size=label.shape[1:]) + get_seg_loss (train_final_voc.py:345-352), fused
-        seg_loss = get_seg_loss_upsampled(segs_1, label_2) + get_seg_loss_upsampled(segs_2, label_1)
+        reg_loss = one * 0
+        if labels is None:
+            seg_loss = one                                     # train_final_voc.py:244
+        else:
+            label_1, label_2 = labels
+            if n_iter >= a.gmm_iters:
+                # ---------------- phase C: GMM noise filter on each student's OWN per-pixel CE (train_final_voc.py:358-394)
+                size = label_1.shape[1:]
+                with torch.no_grad():
+                    up_1 = F.interpolate(segs_1, size=size, mode="bilinear", align_corners=False)
+                    up_2 = F.interpolate(segs_2, size=size, mode="bilinear", align_corners=False)
+                    ce_1 = F.cross_entropy(up_1, label_1.long(), ignore_index=a.ignore_index, reduction="none")
+                    ce_2 = F.cross_entropy(up_2, label_2.long(), ignore_index=a.ignore_index, reduction="none")
+                    gmm_noise_filter(ce_1, label_1, ignore_index=a.ignore_index, gmm_valid_thre=a.gmm_valid_thre, gamma=a.gamma)
+                    gmm_noise_filter(ce_2, label_2, ignore_index=a.ignore_index, gmm_valid_thre=a.gmm_valid_thre, gamma=a.gamma)
+            # F.interpolate(segs, size=label.shape[1:]) + get_seg_loss (train_final_voc.py:345-352, 396-401), fused
+            seg_loss = get_seg_loss_upsampled(segs_1, label_2, a.ignore_index) + get_seg_loss_upsampled(segs_2, label_1, a.ignore_index)
+            if n_iter >= a.gmm_iters:
+                # ---------------- consistency regularisation on the augmented view (train_final_voc.py:407-436)
+                regs = []
+                for up, other_label, aug in ((up_1, label_2, res["branch1_aug"]), (up_2, label_1, res["branch2_aug"])):
+                    with torch.no_grad():
+                        conf, pseudo_seg = torch.softmax(up, dim=1).max(1)
+                        uncertain = (other_label == a.ignore_index) & (conf > 0.9)
+                        target = torch.where(uncertain, pseudo_seg, torch.full_like(pseudo_seg, a.ignore_index))
+                    aug_up = F.interpolate(torch.flip(aug, dims=[3]), size=size, mode="bilinear", align_corners=False)
+                    ce = F.cross_entropy(aug_up, target, ignore_index=a.ignore_index, reduction="none")
+                    # `if uncertain.sum() > 0` of the script without the host sync: an empty mask gives 0 / 1 = 0
+                    regs.append(ce.sum() / uncertain.sum().clamp_min(1))
+                reg_loss = regs[0] + regs[1]
 
         f1 = fmap_1.view(fmap_1.shape[0], fmap_1.shape[1], -1)
         f2 = fmap_2.view(fmap_2.shape[0], fmap_2.shape[1], -1)
         cos = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
         sim_loss = (1 + cos(f1.detach(), f2).mean()) + (1 + cos(f2.detach(), f1).mean())
 
-        loss = 1.0 * cls_loss + a.w_ptc * ptc_loss + a.w_seg * seg_loss + 0.1 * sim_loss
-        return loss, dict(cls_loss=cls_loss, ptc_loss=ptc_loss, seg_loss=seg_loss, sim_loss=sim_loss), (label_1, label_2)
+        w = a.loss_weights(n_iter)
+        loss = w["cls"] * cls_loss + w["ptc"] * ptc_loss + w["seg"] * seg_loss + w["sim"] * sim_loss + w["reg"] * reg_loss
+        return loss, dict(cls_loss=cls_loss, ptc_loss=ptc_loss, seg_loss=seg_loss, sim_loss=sim_loss, reg_loss=reg_loss), labels
 
-    def __call__(self, inputs, cls_label, img_box, n_iter):
-        loss, parts, _ = self.losses(inputs, cls_label, img_box, n_iter)
+    def __call__(self, inputs, cls_label, img_box, n_iter, inputs_aug=None):
+        loss, parts, _ = self.losses(inputs, cls_label, img_box, n_iter, inputs_aug)
         self.optim.zero_grad()
         loss.backward()
         self.optim.step()
         return loss.detach(), {k: v.detach() for k, v in parts.items()}
+
+
+PhaseBStep = TrainStep

@@ -96,3 +96,12 @@ def test_segments_are_packed():
     segs, M, Mp = ops.make_segments([(8, 28, 28), (8, 14, 14), (8, 42, 42)])
     assert (M, Mp) == (8 * (785 + 197 + 1765), 8 * (784 + 196 + 1764))
     assert [s.row_offset for s in segs] == [0, 6280, 7856] and [s.patch_row_offset for s in segs] == [0, 6272, 7840]
+
+
+def test_eval_sweep_shards_images_like_the_reference_tool():
+    """tools/eval_seg_coco_ddp.py:241: rank r takes images r, r+world, ...; every image exactly once."""
+    from dupl_b200.eval_sweep import shard_indices
+    for n, world in ((10, 1), (10, 4), (7, 8), (0, 2)):
+        parts = [shard_indices(n, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert all(p == list(range(r, n, world)) for r, p in enumerate(parts))

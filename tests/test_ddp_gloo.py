@@ -22,7 +22,7 @@ def _worker(rank, world, port, out):
     from dupl_b200 import dense, train
     from dupl_b200.model.model_dupl import siamese_network
 
-    def fake_forward(net, x, size=None):
+    def fake_forward(net, x, size=None, kept=None):
         B = x.shape[0]
         K = net.num_classes - 1
         outs = (torch.zeros(B, K), torch.zeros(B, K + 1, 2, 2), torch.zeros(B, 768, 2, 2), torch.zeros(B, K))

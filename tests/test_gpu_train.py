@@ -139,3 +139,71 @@ def test_forward_reuse_from_the_mscam_pass_is_bit_identical():
         assert grads.keys() == base_grads.keys()
         for n in grads:
             assert torch.equal(grads[n], base_grads[n]), n
+
+
+def _check_step(m, P, cfg, args, n_iter, num_classes, cls_dtype=torch.float32, with_aug=False, seed=50):
+    from dupl_b200.train_step import TrainStep
+    from helpers import synth_boxes, synth_cls_labels, synth_images
+    from oracle import dupl_oracle as O
+    b, S = 2, 64
+    x = synth_images(b, S, S, seed=seed)
+    x_aug = synth_images(b, S, S, seed=seed + 1) if with_aug else None
+    cls = synth_cls_labels(b, num_classes - 1, seed=seed + 2).to(cls_dtype)
+    box = synth_boxes(b, S, S, seed=seed + 3)
+    Pg = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+    want, wparts, wlabels = O.train_losses(Pg, x, cls, box, n_iter, cfg, thres_target=list(args.high_thres_target), inputs_aug=x_aug)
+    want.backward()
+    step = TrainStep(m, None, args=args)
+    got, parts, labels = step.losses(x.cuda(), cls.cuda(), box, n_iter, inputs_aug=None if x_aug is None else x_aug.cuda())
+    got.backward()
+    for k in wparts:
+        assert abs(float(parts[k]) - float(wparts[k])) < 1e-3 * max(1.0, abs(float(wparts[k]))), (k, float(parts[k]), float(wparts[k]))
+    assert abs(got.item() - want.item()) < 1e-3 * max(1.0, abs(want.item()))
+    if wlabels is None:
+        assert labels is None
+    else:
+        for a, w in zip(labels, wlabels):
+            assert (a.cpu() != w).float().mean().item() < 1e-3
+    bad = []
+    for name, p in m.named_parameters():
+        ref = Pg[name].grad
+        if ".head." in name or "pos_embed" in name:
+            continue
+        if ref is None or ref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max() == 0, name
+            continue
+        e = _nrel(p.grad, ref)
+        if e >= 2e-3:
+            bad.append((name, round(e, 5)))
+    assert not bad, bad[:10]
+
+
+def test_phase_a_step_matches_oracle_loop():
+    """n_iter < cam_iters (train_final_voc.py:194-258): CAM + cls + PTC (static thresholds) + discrepancy loss, no refine."""
+    from dupl_b200.train_step import Args
+    from oracle import dupl_oracle as O
+    m, P = _models()
+    _check_step(m, P, O.VOC_CFG, Args, 500, 21)
+
+
+def test_phase_c_step_matches_oracle_loop():
+    """n_iter >= gmm_iters (train_final_voc.py:290-436): need_sp forward of the augmented view, GMM noise filter (GPU kernel vs
+    sklearn in the oracle), consistency term."""
+    from dupl_b200.train_step import Args
+    from oracle import dupl_oracle as O
+    m, P = _models()
+    _check_step(m, P, O.VOC_CFG, Args, 9000, 21, with_aug=True)
+
+
+@pytest.mark.parametrize("n_iter", [10000, 20000])
+def test_coco_step_matches_oracle_loop(n_iter):
+    """train_final_coco.py: 81 classes, uint8 cls_label, aux_layer=9; n_iter <= 12000 refines cams_aux with the scalar
+    threshold (refine_cams_with_bkg_v2, :312-322), later the dynamic variant; COCO loss weights (:441-448)."""
+    from dupl_b200.model.model_dupl import siamese_network
+    from dupl_b200.train_step import CocoArgs
+    from oracle import dupl_oracle as O
+    P = init_state_dict(81)
+    m = siamese_network("deit_base_patch16_224", num_classes=81, pretrained=False, aux_layer=9)
+    m.load_state_dict(P, strict=True)
+    m = m.cuda().train()
+    _check_step(m, P, O.COCO_CFG, CocoArgs, n_iter, 81, cls_dtype=torch.uint8, seed=60)

@@ -99,3 +99,140 @@ def test_phase_b_loop_matches_the_reference_functions_composed_like_the_script()
         assert abs(got[k].item() - want[k].item()) < 1e-5 * max(1.0, abs(want[k].item())), k
     assert abs(got_loss.item() - loss.item()) < 1e-5
     assert torch.equal(labels[0], lab_1) and torch.equal(labels[1], lab_2)
+
+
+@pytest.mark.parametrize("flavour", ["coco", "voc"])
+def test_msc_seg_matches_the_eval_tool_loop_on_the_reference_model(flavour):
+    """tools/eval_seg_coco_ddp.py:77-122 / tools/eval_seg_voc.py:54-78 re-executed with the reference's own model and
+    torch's F.interpolate vs oracle.msc_seg."""
+    import torch.nn.functional as F
+    from helpers import init_state_dict, synth_images
+    ref = ref_import.load()
+    P = init_state_dict(21)
+    model = ref.model_dupl.siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
+    model.load_state_dict(P, strict=True)
+    model.eval()
+    inputs = synth_images(1, 48, 80, seed=31)
+    scales = (1.0, 1.25, 1.5) if flavour == "coco" else (1.0, 1.5, 1.25)
+    with torch.no_grad():
+        if flavour == "coco":
+            x = F.interpolate(inputs, size=[64, 64], mode="bilinear", align_corners=False)
+            _, _, h, w = x.shape
+            segs = model(torch.cat([x, x.flip(-1)], 0))["branch2"][1]
+            acc = segs[:1] + segs[1:].flip(-1)
+            hs, ws = acc.shape[-2:]
+            for sc in scales:
+                if sc != 1.0:
+                    xi = F.interpolate(x, size=[int(h * sc), int(w * sc)], mode="bilinear", align_corners=False)
+                    s = model(torch.cat([xi, xi.flip(-1)], 0))["branch2"][1]
+                    s = F.interpolate(s, size=(hs, ws), mode="bilinear", align_corners=False)
+                    acc = acc + (s[:1] + s[1:].flip(-1))
+            want = acc
+            got = O.msc_seg(P, 2, inputs, scales, "coco", crop_size=64)
+        else:
+            _, _, h, w = inputs.shape
+            lst = []
+            for sc in scales:
+                xi = F.interpolate(inputs, size=[int(h * sc), int(w * sc)], mode="bilinear", align_corners=False)
+                s = model(torch.cat([xi, xi.flip(-1)], 0))["branch2"][1]
+                s = F.interpolate(s, size=(48, 80), mode="bilinear", align_corners=False)
+                lst.append(s[:1] + s[1:].flip(-1))
+            want = torch.max(torch.stack(lst, 0), 0)[0]
+            got = O.msc_seg(P, 2, inputs, scales, "voc", label_size=(48, 80))
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 2e-5 * want.abs().max().item()
+
+
+def test_general_loop_equals_the_pinned_phase_b_loop():
+    from helpers import init_state_dict, synth_boxes, synth_cls_labels, synth_images
+    P = init_state_dict(21)
+    x, cls, box = synth_images(2, 64, 64, seed=11), synth_cls_labels(2, 20, seed=12), synth_boxes(2, 64, 64, seed=13)
+    with torch.no_grad():
+        l0, p0, lab0 = O.phase_b_losses(P, x, cls, box, 3000)
+        l1, p1, lab1 = O.train_losses(P, x, cls, box, 3000, O.VOC_CFG)
+    assert torch.equal(l0, l1) and all(torch.equal(a, b) for a, b in zip(lab0, lab1))
+
+
+def test_phase_c_loop_matches_the_reference_functions_composed_like_the_script():
+    """train_final_voc.py:277-447 for n_iter >= gmm_iters (need_sp forward, sklearn GMM filter, consistency term) re-executed
+    with the reference's OWN modules vs oracle.train_losses."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from helpers import init_state_dict, synth_boxes, synth_cls_labels, synth_images
+    from sklearn.mixture import GaussianMixture
+    ref = ref_import.load()
+    P = init_state_dict(21)
+    model = ref.model_dupl.siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
+    model.load_state_dict(P, strict=True)
+    model.train()
+    par = ref.PAR.PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24])
+    b, S = 2, 64
+    inputs, inputs_aug = synth_images(b, S, S, seed=41), synth_images(b, S, S, seed=42)
+    cls_label, img_box = synth_cls_labels(b, 20, seed=43), synth_boxes(b, S, S, seed=44)
+    n_iter = 9000
+    high_thres = torch.ones(20) * 0.7            # thres_target = start in this test: the annealing is covered by the phase-B test
+    inputs_denorm = ref.imutils.denormalize_img2(inputs.clone())
+    hl, ml = [], []
+    for i in range(b):
+        t = torch.max(high_thres[torch.nonzero(cls_label[i]).squeeze(-1)])
+        hl.append(t)
+        ml.append(torch.ones((S, S)) * t)
+    high, high_mask = torch.stack(hl), torch.stack(ml).unsqueeze(1)
+    cams_1, aux_1 = ref.cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=(1.0, 0.5, 1.5), branch=1)
+    cams_2, aux_2 = ref.cam_helper.multi_scale_cam2_siamese(model, inputs=inputs, scales=(1.0, 0.5, 1.5), branch=2)
+    res = model(torch.cat([inputs, inputs_aug], dim=0), need_sp=True)
+    cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
+    cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
+    segs_1_aug, segs_2_aug = res["branch1_aug"], res["branch2_aug"]
+    cls_loss = sum(F.multilabel_soft_margin_loss(t, cls_label) for t in (cls_1, cls_aux_1, cls_2, cls_aux_2))
+    ptc = 0
+    for aux, fmap in ((aux_1, fmap_1), (aux_2, fmap_2)):
+        r = F.interpolate(aux, size=fmap.shape[2:], mode="bilinear", align_corners=False)
+        _, pl = ref.cam_helper.cam_to_label_dynamic_cls(r.detach(), cls_label=cls_label, img_box=img_box, ignore_mid=True,
+                                                        bkg_thre=0.5, high_thre=high, low_thre=0.25, ignore_index=255)
+        ptc = ptc + ref.losses.get_masked_ptc_loss(fmap, ref.cam_helper.label_to_aff_mask(pl))
+    rep = cls_label.unsqueeze(-1).unsqueeze(-1).repeat([1, 1, S, S])
+    kw = dict(cls_labels=cls_label, high_thre_map=high_mask, low_thre=0.25, ignore_index=255, img_box=img_box)
+    lab_1 = ref.cam_helper.refine_cams_with_dynamic_thres(par, inputs_denorm, cams=cams_1.detach() * rep, **kw)
+    lab_2 = ref.cam_helper.refine_cams_with_dynamic_thres(par, inputs_denorm, cams=cams_2.detach() * rep, **kw)
+    segs_1 = F.interpolate(segs_1, size=lab_1.shape[1:], mode="bilinear", align_corners=False)
+    segs_2 = F.interpolate(segs_2, size=lab_2.shape[1:], mode="bilinear", align_corners=False)
+    ce_criterion = nn.CrossEntropyLoss(ignore_index=255, reduction="none")
+    for segs, lab in ((segs_1, lab_1), (segs_2, lab_2)):                                      # :358-394
+        sl = ce_criterion(segs, lab.type(torch.long)).detach()
+        roi = (lab != 0).bool() & (lab != 255).bool()
+        for i in range(b):
+            m = sl[i][roi[i]]
+            if (m > 0.1).sum().item() > 1000:
+                gmm = GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4, random_state=0)
+                gmm.fit(m[m > 0.1].unsqueeze(-1).cpu().detach().numpy())
+                if abs(gmm.means_[0, 0] - gmm.means_[1, 0]) > 1.0:
+                    prob = gmm.predict_proba(sl[i].view(-1).unsqueeze(-1).cpu().detach().numpy())
+                    noise = torch.tensor(prob[:, gmm.means_.argmax()] > 0.95).reshape(S, S) & (lab[i] != 0).bool()
+                    lab[i][noise] = 255
+    seg_loss_1 = ref.losses.get_seg_loss(segs_1, lab_2.type(torch.long), ignore_index=255)
+    seg_loss_2 = ref.losses.get_seg_loss(segs_2, lab_1.type(torch.long), ignore_index=255)
+    seg = seg_loss_1 + seg_loss_2
+    segs_1_aug = F.interpolate(torch.flip(segs_1_aug, dims=[3]), size=(S, S), mode="bilinear", align_corners=False)   # :407-436
+    segs_2_aug = F.interpolate(torch.flip(segs_2_aug, dims=[3]), size=(S, S), mode="bilinear", align_corners=False)
+    ps1, ps2 = segs_1.detach().data.max(1)[1], segs_2.detach().data.max(1)[1]
+    cf1, cf2 = torch.softmax(segs_1.detach(), dim=1).max(1)[0], torch.softmax(segs_2.detach(), dim=1).max(1)[0]
+    um1, um2 = (lab_2 == 255).bool() & (cf1 > 0.9), (lab_1 == 255).bool() & (cf2 > 0.9)
+    ps1[~um1] = 255
+    ps2[~um2] = 255
+    r1, r2 = seg_loss_1 * 0.0, seg_loss_2 * 0.0
+    if um1.sum() > 0:
+        r1 = ce_criterion(segs_1_aug, ps1).sum() / um1.sum()
+    if um2.sum() > 0:
+        r2 = ce_criterion(segs_2_aug, ps2).sum() / um2.sum()
+    reg = r1 + r2
+    f1, f2 = fmap_1.view(b, 768, -1), fmap_2.view(b, 768, -1)
+    cos = nn.CosineSimilarity(dim=-1, eps=1e-6)
+    sim = (1 + cos(f1.detach(), f2).mean()) + (1 + cos(f2.detach(), f1).mean())
+    loss = 1.0 * cls_loss + 0.2 * ptc + 0.2 * seg + 0.1 * sim + 0.05 * reg
+    want = dict(cls_loss=cls_loss, ptc_loss=ptc, seg_loss=seg, sim_loss=sim, reg_loss=reg)
+    got_loss, got, labels = O.train_losses(P, inputs, cls_label, img_box, n_iter, O.VOC_CFG, inputs_aug=inputs_aug)
+    for k in want:
+        assert abs(got[k].item() - want[k].item()) < 1e-5 * max(1.0, abs(want[k].item())), k
+    assert abs(got_loss.item() - loss.item()) < 1e-5
+    assert torch.equal(labels[0], lab_1) and torch.equal(labels[1], lab_2)
