@@ -1,5 +1,7 @@
 // CAM post-processing and pseudo-label casts — HBM-bound, one pass over
 // the output, low-resolution sources staged in shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "resample.cuh"
 
@@ -26,7 +28,7 @@ constexpr int MSCAM_ROWS = 32;  // output rows per block
 constexpr int MSCAM_THREADS = 128;
 
 template <int PASS>
-__global__ void __launch_bounds__(MSCAM_THREADS) mscam_kernel(MscamParams p) {
+__global__ void __launch_bounds__(MSCAM_THREADS) mscam_generic_kernel(MscamParams p) {
   extern __shared__ float sm[];
   const int plane = blockIdx.x;  // img*K + k
   const int img = plane / p.K, k = plane % p.K;
@@ -107,6 +109,182 @@ __global__ void __launch_bounds__(MSCAM_THREADS) mscam_kernel(MscamParams p) {
       atomicMax(&p.minmax[2 * plane + 1], __float_as_uint(mx));
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Column-per-thread variant (NS = number of scales, 1..4; the reference uses 3).
+// A thread owns one output column of a (MSCAM_TILE_ROWS x blockDim.x) tile: its horizontal sampling
+// coordinates are loop invariants, and the horizontally interpolated values of the two source rows
+// (t0, t1 of bilerp4) only change when the source row index advances, i.e. every H/gh output rows.  The
+// inner loop is then one vertical blend per scale and twin: ~25 instructions per output pixel instead of
+// ~120, which is what moves this stage from LDS/ALU-bound towards the 64 MB store stream it should be.
+// Same arithmetic (same fma order) as bilerp4: results are bit-identical to the generic kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int MSCAM_TILE_ROWS = 64;
+
+struct MscamRow {  // vertical sampling of one output row for one scale, row indices relative to the staged window
+  int i0, i1;
+  float l0, l1;
+};
+
+// a / d correctly rounded for normal-range operands (Markstein): q0 = RN(a * RN(1/d)), r = a - q0*d (exact in fma),
+// q = RN(q0 + r * RN(1/d)).  The plain `/` costs ~15 instructions per pixel for its special-case handling; here
+// a is in [0, max] and d = max + 1e-5, far from overflow / denormals.
+__device__ __forceinline__ float div_rn_normal(float a, float d, float rcp_d) {
+  const float q0 = __fmul_rn(a, rcp_d);
+  const float r = __fmaf_rn(-q0, d, a);
+  return __fmaf_rn(r, rcp_d, q0);
+}
+
+template <int PASS, int NS>
+__global__ void __launch_bounds__(256) mscam_kernel(MscamParams p) {
+  extern __shared__ float sm[];
+  __shared__ int g_rlo[NS], g_nr[NS], g_clo[NS], g_nc[NS], g_off[NS + 1];
+  const int plane = blockIdx.x;  // img*K + k
+  const int img = plane / p.K, k = plane % p.K;
+  const int y_begin = blockIdx.y * MSCAM_TILE_ROWS;
+  const int y_end = min(y_begin + MSCAM_TILE_ROWS, p.H);
+  const int x_begin = blockIdx.z * blockDim.x;
+  const int x_last = min(x_begin + static_cast<int>(blockDim.x), p.W) - 1;
+
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int s = 0; s < NS; ++s) {
+      const int gh = p.gh[s], gw = p.gw[s];
+      const int rlo = lin_coord(y_begin, gh, static_cast<float>(gh) / p.H).i0;
+      const int rhi = lin_coord(y_end - 1, gh, static_cast<float>(gh) / p.H).i1;
+      const int clo = lin_coord(x_begin, gw, static_cast<float>(gw) / p.W).i0;
+      const int chi = lin_coord(x_last, gw, static_cast<float>(gw) / p.W).i1;
+      g_rlo[s] = rlo; g_nr[s] = rhi - rlo + 1; g_clo[s] = clo; g_nc[s] = chi - clo + 1;
+      g_off[s] = off;
+      off += 2 * g_nr[s] * g_nc[s];
+    }
+    g_off[NS] = off;
+  }
+  __syncthreads();
+  // Stage the window of the low-res planes of the image (A) and of its twin (B, stored pre-flipped along x, which
+  // commutes with the symmetric align_corners=False sampling grid).
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int gw = p.gw[s], n = p.gh[s] * gw;
+    const int nr = g_nr[s], nc = g_nc[s], rlo = g_rlo[s], clo = g_clo[s];
+    const float* a = p.lowres[s] + (static_cast<long>(img) * p.K + k) * n;
+    const float* bt = p.lowres[s] + (static_cast<long>(img + p.b) * p.K + k) * n;
+    float* A = sm + g_off[s];
+    float* B = A + nr * nc;
+    for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) {
+      const int r = i / nc, c = i - r * nc;
+      A[i] = __ldg(a + (rlo + r) * gw + clo + c);
+      B[i] = __ldg(bt + (rlo + r) * gw + (gw - 1 - (clo + c)));
+    }
+  }
+  MscamRow* rows = reinterpret_cast<MscamRow*>(sm + ((g_off[NS] + 3) & ~3));
+  float2* wts = reinterpret_cast<float2*>(rows + MSCAM_TILE_ROWS * NS);
+  int* flags = reinterpret_cast<int*>(wts + MSCAM_TILE_ROWS * NS);
+  for (int i = threadIdx.x; i < (y_end - y_begin) * NS; i += blockDim.x) {
+    const int r = i / NS, s = i - r * NS;
+    const Lin ly = lin_coord(y_begin + r, p.gh[s], static_cast<float>(p.gh[s]) / p.H);
+    rows[i] = MscamRow{ly.i0 - g_rlo[s], ly.i1 - g_rlo[s], ly.l0, ly.l1};
+    wts[i] = make_float2(ly.l0, ly.l1);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < y_end - y_begin; r += blockDim.x) {
+    int f = 0;
+    for (int s = 0; s < NS; ++s)
+      if (r == 0 || rows[r * NS + s].i0 != rows[(r - 1) * NS + s].i0 || rows[r * NS + s].i1 != rows[(r - 1) * NS + s].i1) f |= 1 << s;
+    flags[r] = f;
+  }
+  __syncthreads();
+
+  const int x = x_begin + threadIdx.x;
+  const bool active = x < p.W;
+  const int xc = min(x, p.W - 1);
+  int c0[NS], c1[NS], nc[NS];
+  float lx0[NS], lx1[NS], t0a[NS], t1a[NS], t0b[NS], t1b[NS];
+  const float* Ab[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const Lin lx = lin_coord(xc, p.gw[s], static_cast<float>(p.gw[s]) / p.W);
+    c0[s] = lx.i0 - g_clo[s]; c1[s] = lx.i1 - g_clo[s]; lx0[s] = lx.l0; lx1[s] = lx.l1;
+    nc[s] = g_nc[s];
+    Ab[s] = sm + g_off[s];
+    t0a[s] = t1a[s] = t0b[s] = t1b[s] = 0.0f;
+  }
+  float mn = INFINITY, mx = 0.0f, shift = 0.0f, denom = 1.0f, rcp = 1.0f;
+  if (PASS == 1) {
+    const float lo = __uint_as_float(p.minmax[2 * plane]);
+    const float hi = __uint_as_float(p.minmax[2 * plane + 1]);
+    shift = -lo;                       // cam + max(-cam)
+    denom = (hi + shift) + 1e-5f;      // max(cam) + 1e-5
+    rcp = __frcp_rn(denom);
+  }
+  float* o = p.out + (static_cast<long>(plane) * p.H + y_begin) * p.W + xc;
+  for (int r = 0; r < y_end - y_begin; ++r) {
+    const int changed = flags[r];      // bit s: the source rows of scale s differ from the previous output row's
+    if (changed != 0) {                // block-uniform and rare: every H/gh output rows
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if ((changed >> s) & 1) {
+          const MscamRow rw = rows[r * NS + s];
+          const float* A0 = Ab[s] + rw.i0 * nc[s];
+          const float* A1 = Ab[s] + rw.i1 * nc[s];
+          const float* B0 = A0 + g_nr[s] * nc[s];
+          const float* B1 = A1 + g_nr[s] * nc[s];
+          t0a[s] = __fmaf_rn(lx0[s], A0[c0[s]], __fmul_rn(lx1[s], A0[c1[s]]));
+          t1a[s] = __fmaf_rn(lx0[s], A1[c0[s]], __fmul_rn(lx1[s], A1[c1[s]]));
+          t0b[s] = __fmaf_rn(lx0[s], B0[c0[s]], __fmul_rn(lx1[s], B0[c1[s]]));
+          t1b[s] = __fmaf_rn(lx0[s], B1[c0[s]], __fmul_rn(lx1[s], B1[c1[s]]));
+        }
+      }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float2 l = wts[r * NS + s];
+      const float va = __fmaf_rn(l.x, t0a[s], __fmul_rn(l.y, t1a[s]));
+      const float vb = __fmaf_rn(l.x, t0b[s], __fmul_rn(l.y, t1b[s]));
+      acc += fmaxf(fmaxf(va, vb), 0.0f);
+    }
+    if (PASS == 0) {
+      mn = fminf(mn, acc);
+      mx = fmaxf(mx, acc);
+    } else if (active) {
+      __stcs(o + static_cast<long>(r) * p.W, div_rn_normal(acc + shift, denom, rcp));
+    }
+  }
+  if (PASS == 0) {
+    if (!active) { mn = INFINITY; mx = 0.0f; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) {  // values are >= 0 => unsigned bit patterns order like the floats
+      atomicMin(&p.minmax[2 * plane], __float_as_uint(mn));
+      atomicMax(&p.minmax[2 * plane + 1], __float_as_uint(mx));
+    }
+  }
+}
+
+template <int NS>
+static int launch_mscam_columns(const MscamParams& p, cudaStream_t st) {
+  const int bw = (p.W % 224 == 0) ? 224 : ((p.W >= 256) ? 256 : 128);
+  size_t floats = 0;
+  for (int s = 0; s < NS; ++s) {
+    const int nr = min(p.gh[s], cdiv(MSCAM_TILE_ROWS * p.gh[s], p.H) + 3);
+    const int nc = min(p.gw[s], cdiv(bw * p.gw[s], p.W) + 3);
+    floats += 2ull * nr * nc;
+  }
+  const size_t smem = (floats + 4) * sizeof(float) +
+                      static_cast<size_t>(MSCAM_TILE_ROWS) * (NS * (sizeof(MscamRow) + sizeof(float2)) + sizeof(int));
+  if (smem > 48 * 1024) return -1;  // unusual geometry: let the generic kernel handle it
+  dim3 grid(p.b * p.K, cdiv(p.H, MSCAM_TILE_ROWS), cdiv(p.W, bw));
+  mscam_kernel<0, NS><<<grid, bw, smem, st>>>(p);
+  DUPL_LAUNCH_OK();
+  mscam_kernel<1, NS><<<grid, bw, smem, st>>>(p);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
 }
 
 __global__ void mscam_init_minmax(unsigned int* mm, int planes) {
@@ -195,16 +373,29 @@ extern "C" int dupl_mscam_post(const dupl_mscam_args* a, void* stream) {
     p.lowres[s] = a->lowres[s]; p.gh[s] = a->gh[s]; p.gw[s] = a->gw[s];
     smem += 2ull * a->gh[s] * a->gw[s] * sizeof(float);
   }
-  DUPL_CHECK_ARG(smem <= 200 * 1024, "dupl_mscam_post: low-res maps need %zu B of shared memory", smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int planes_all = a->b * a->K;
+  if (a->nscale <= 4 && planes_all <= 65535 * 32 && getenv("DUPL_MSCAM_GENERIC") == nullptr) {
+    mscam_init_minmax<<<cdiv(planes_all, 256), 256, 0, st>>>(p.minmax, planes_all);
+    DUPL_LAUNCH_OK();
+    int rc = -1;
+    switch (a->nscale) {
+      case 1: rc = launch_mscam_columns<1>(p, st); break;
+      case 2: rc = launch_mscam_columns<2>(p, st); break;
+      case 3: rc = launch_mscam_columns<3>(p, st); break;
+      case 4: rc = launch_mscam_columns<4>(p, st); break;
+    }
+    if (rc >= 0) return rc;
+  }
+  DUPL_CHECK_ARG(smem <= 200 * 1024, "dupl_mscam_post: low-res maps need %zu B of shared memory", smem);
   static size_t smem_set0 = 0, smem_set1 = 0;
   if (smem > 48 * 1024) {
     if (smem > smem_set0) {
-      DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       smem_set0 = smem;
     }
     if (smem > smem_set1) {
-      DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       smem_set1 = smem;
     }
   }
@@ -212,9 +403,9 @@ extern "C" int dupl_mscam_post(const dupl_mscam_args* a, void* stream) {
   mscam_init_minmax<<<cdiv(planes, 256), 256, 0, st>>>(p.minmax, planes);
   DUPL_LAUNCH_OK();
   dim3 grid(planes, cdiv(a->H, MSCAM_ROWS));
-  mscam_kernel<0><<<grid, MSCAM_THREADS, smem, st>>>(p);
+  mscam_generic_kernel<0><<<grid, MSCAM_THREADS, smem, st>>>(p);
   DUPL_LAUNCH_OK();
-  mscam_kernel<1><<<grid, MSCAM_THREADS, smem, st>>>(p);
+  mscam_generic_kernel<1><<<grid, MSCAM_THREADS, smem, st>>>(p);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

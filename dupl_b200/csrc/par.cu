@@ -5,6 +5,7 @@
 // shared by every mask set that is propagated over that image, and all channel planes of all
 // images advance together in one launch per iteration.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "resample.cuh"
@@ -131,6 +132,157 @@ __global__ void __launch_bounds__(256) par_propagate_kernel(const float* __restr
 #pragma unroll
   for (int c = 0; c < CH; ++c)
     if (c < np) D[c * hw] = acc[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled propagation step: a CTA owns a PT_W x PT_H pixel tile of one image and up to PT_CH mask planes.
+// The planes' tile + halo (max dilation, replicate border baked in while loading) is staged in shared
+// memory, so the 48-neighbour gather is `LDS [tile + constant offset]` with no index clamping in the inner
+// loop, and the affinity (the only per-iteration stream that does not fit in shared memory) is read exactly
+// once per pixel and plane chunk with 128-byte coalesced loads.  Two CTAs fit on an SM (<= 5 planes x 20 KB),
+// so one CTA's staging overlaps the other's gather.  Same products and the same summation order as
+// par_propagate_kernel: results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int PT_W = 32, PT_H = 16, PT_CH = 5, PT_MAX_HALO = 24;
+
+template <int NDIL, int NP>
+__device__ __forceinline__ void par_tile_gather(const float* __restrict__ A, long hw, const float* tile, int pitch,
+                                                int plane_stride, int center, const ParGeom& g, float (&acc)[NP]) {
+#pragma unroll
+  for (int c = 0; c < NP; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int di = 0; di < NDIL; ++di) {
+    const int d = g.dil[di];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = __ldg(A + (di * 8 + j) * hw);
+      const float* q = tile + center + (c_par_dy[j] * d) * pitch + c_par_dx[j] * d;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) acc[c] = fmaf(a, q[c * plane_stride], acc[c]);
+    }
+  }
+}
+
+// The reference's only configuration (train_final_voc.py:160: dilations [1,2,4,8,12,24]): every neighbour offset inside the
+// staged tile is a compile-time constant, so the gather is `LDS [center + imm]` + FFMA and nothing else.
+constexpr int PS_HALO = 24, PS_PITCH = PT_W + 2 * PS_HALO, PS_ROWS = PT_H + 2 * PS_HALO, PS_PLANE = PS_PITCH * PS_ROWS;
+__host__ __device__ constexpr int ps_dil(int di) { return di == 0 ? 1 : di == 1 ? 2 : di == 2 ? 4 : di == 3 ? 8 : di == 4 ? 12 : 24; }
+__host__ __device__ constexpr int ps_dy(int j) { return j < 3 ? -1 : (j < 5 ? 0 : 1); }
+__host__ __device__ constexpr int ps_dx(int j) { return (j == 0 || j == 3 || j == 5) ? -1 : ((j == 1 || j == 6) ? 0 : 1); }
+
+template <int NP>
+__device__ __forceinline__ void par_std_gather(const float* __restrict__ A, long hw, const float* q0, float* __restrict__ D) {
+  float acc[NP];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int di = 0; di < 6; ++di) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = __ldg(A + (di * 8 + j) * hw);
+      const int off = (ps_dy(j) * ps_dil(di)) * PS_PITCH + ps_dx(j) * ps_dil(di);  // folds to an immediate after unrolling
+#pragma unroll
+      for (int c = 0; c < NP; ++c) acc[c] = fmaf(a, q0[c * PS_PLANE + off], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NP; ++c) D[c * hw] = acc[c];
+}
+
+__global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_std_kernel(const float* __restrict__ aff,
+                                                                            const float* __restrict__ src,
+                                                                            float* __restrict__ dst,
+                                                                            const int* __restrict__ nactive, int P,
+                                                                            int max_chunks, int h, int w) {
+  extern __shared__ float tile[];
+  const int b = blockIdx.z / max_chunks;
+  const int chunk = blockIdx.z % max_chunks;
+  const int live = nactive != nullptr ? min(__ldg(nactive + b), P) : P;
+  const int chunks = (live + PT_CH - 1) / PT_CH;
+  if (chunk >= chunks) return;
+  const int per = (live + chunks - 1) / chunks;
+  const int p0 = chunk * per;
+  const int np = min(per, live - p0);
+  if (np <= 0) return;
+  const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+  const long hw = static_cast<long>(h) * w;
+  const float* S = src + (static_cast<long>(b) * P + p0) * hw;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // stage rows wid, wid+16, ..: tile[c][r][cx] = plane_c[clamp(y0 - 24 + r)][clamp(x0 - 24 + cx)]
+  for (int r = wid; r < PS_ROWS; r += PT_H) {
+    const long row = static_cast<long>(min(max(y0 - PS_HALO + r, 0), h - 1)) * w;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int cx = lane + 32 * k;
+      if (cx < PS_PITCH) {
+        const long o = row + min(max(x0 - PS_HALO + cx, 0), w - 1);
+        for (int c = 0; c < np; ++c) tile[c * PS_PLANE + r * PS_PITCH + cx] = __ldg(S + c * hw + o);
+      }
+    }
+  }
+  __syncthreads();
+  const int x = x0 + lane, y = y0 + wid;
+  if (x >= w || y >= h) return;
+  const float* A = aff + static_cast<long>(b) * 48 * hw + static_cast<long>(y) * w + x;
+  const float* q0 = tile + (wid + PS_HALO) * PS_PITCH + lane + PS_HALO;
+  float* D = dst + (static_cast<long>(b) * P + p0) * hw + static_cast<long>(y) * w + x;
+  switch (np) {
+    case 1: par_std_gather<1>(A, hw, q0, D); break;
+    case 2: par_std_gather<2>(A, hw, q0, D); break;
+    case 3: par_std_gather<3>(A, hw, q0, D); break;
+    case 4: par_std_gather<4>(A, hw, q0, D); break;
+    case 5: par_std_gather<5>(A, hw, q0, D); break;
+  }
+}
+
+template <int NDIL>
+__global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tiled_kernel(const float* __restrict__ aff,
+                                                                              const float* __restrict__ src,
+                                                                              float* __restrict__ dst,
+                                                                              const int* __restrict__ nactive, int P,
+                                                                              int max_chunks, int h, int w, int halo,
+                                                                              ParGeom g) {
+  extern __shared__ float tile[];
+  constexpr int N = 8 * NDIL;
+  const int b = blockIdx.z / max_chunks;
+  const int chunk = blockIdx.z % max_chunks;
+  const int live = nactive != nullptr ? min(__ldg(nactive + b), P) : P;
+  const int chunks = (live + PT_CH - 1) / PT_CH;
+  if (chunk >= chunks) return;
+  const int per = (live + chunks - 1) / chunks;  // balanced split: 6 live planes -> 3 + 3, not 5 + 1
+  const int p0 = chunk * per;
+  const int np = min(per, live - p0);
+  if (np <= 0) return;
+  const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+  const int pitch = PT_W + 2 * halo, rows = PT_H + 2 * halo;
+  const int plane_stride = pitch * rows;
+  const long hw = static_cast<long>(h) * w;
+  const float* S = src + (static_cast<long>(b) * P + p0) * hw;
+  // stage: tile[c][r][cx] = plane_c[clamp(y0 - halo + r)][clamp(x0 - halo + cx)]
+  for (int i = threadIdx.x; i < plane_stride; i += PT_W * PT_H) {
+    const int r = i / pitch, cx = i - r * pitch;
+    const int gy = min(max(y0 - halo + r, 0), h - 1);
+    const int gx = min(max(x0 - halo + cx, 0), w - 1);
+    const long o = static_cast<long>(gy) * w + gx;
+    for (int c = 0; c < np; ++c) tile[c * plane_stride + i] = __ldg(S + c * hw + o);
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % PT_W, ty = threadIdx.x / PT_W;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= w || y >= h) return;
+  const float* A = aff + static_cast<long>(b) * N * hw + static_cast<long>(y) * w + x;
+  const int center = (ty + halo) * pitch + tx + halo;
+  float* D = dst + (static_cast<long>(b) * P + p0) * hw + static_cast<long>(y) * w + x;
+  switch (np) {
+#define PT_CASE(NP)                                                                 \
+  case NP: {                                                                        \
+    float acc[NP];                                                                  \
+    par_tile_gather<NDIL, NP>(A, hw, tile, pitch, plane_stride, center, g, acc);    \
+    _Pragma("unroll") for (int c = 0; c < NP; ++c) D[c * hw] = acc[c];              \
+  } break;
+    PT_CASE(1) PT_CASE(2) PT_CASE(3) PT_CASE(4) PT_CASE(5)
+#undef PT_CASE
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -337,12 +489,58 @@ extern "C" int dupl_par_propagate(const float* aff, float* masks, float* scratch
   ParGeom g;
   int rc = fill_geom(dilations_host, ndil, g);
   if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int halo = 0;
+  for (int i = 0; i < ndil; ++i) halo = g.dil[i] > halo ? g.dil[i] : halo;
+  const bool force_simple = getenv("DUPL_PAR_SIMPLE") != nullptr;  // A/B switch for tests and measurements
+  if (halo <= PT_MAX_HALO && !force_simple && static_cast<long>(B) * cdiv(P, PT_CH) <= 65535) {
+    const int max_chunks = cdiv(P, PT_CH);
+    const size_t smem = static_cast<size_t>(PT_CH) * (PT_W + 2 * halo) * (PT_H + 2 * halo) * sizeof(float);
+    dim3 tgrid(cdiv(w, PT_W), cdiv(h, PT_H), B * max_chunks), tblock(PT_W * PT_H);
+    float* tsrc = masks;
+    float* tdst = scratch;
+    const bool standard = ndil == 6 && g.dil[0] == 1 && g.dil[1] == 2 && g.dil[2] == 4 && g.dil[3] == 8 && g.dil[4] == 12 &&
+                          g.dil[5] == 24 && getenv("DUPL_PAR_GENERIC_TILE") == nullptr;
+    if (standard) {
+      static bool attr_std = false;
+      if (!attr_std) {
+        DUPL_CUDA_OK(cudaFuncSetAttribute(par_propagate_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          PT_CH * PS_PLANE * 4));
+        attr_std = true;
+      }
+    }
+    for (int it = 0; it < num_iter; ++it) {
+      if (standard) {
+        par_propagate_std_kernel<<<tgrid, tblock, PT_CH * PS_PLANE * sizeof(float), st>>>(aff, tsrc, tdst, nactive, P, max_chunks, h, w);
+        DUPL_LAUNCH_OK();
+        float* t = tsrc; tsrc = tdst; tdst = t;
+        continue;
+      }
+      switch (ndil) {
+#define TILED_CASE(ND)                                                                                                     \
+  case ND: {                                                                                                               \
+    static bool attr = false;                                                                                              \
+    if (!attr) {                                                                                                           \
+      DUPL_CUDA_OK(cudaFuncSetAttribute(par_propagate_tiled_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                        PT_CH * (PT_W + 2 * PT_MAX_HALO) * (PT_H + 2 * PT_MAX_HALO) * 4));                  \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    par_propagate_tiled_kernel<ND><<<tgrid, tblock, smem, st>>>(aff, tsrc, tdst, nactive, P, max_chunks, h, w, halo, g);   \
+  } break;
+        TILED_CASE(1) TILED_CASE(2) TILED_CASE(3) TILED_CASE(4) TILED_CASE(5) TILED_CASE(6) TILED_CASE(7) TILED_CASE(8)
+#undef TILED_CASE
+      }
+      DUPL_LAUNCH_OK();
+      float* t = tsrc; tsrc = tdst; tdst = t;
+    }
+    if (result_in_scratch_host != nullptr) *result_in_scratch_host = (tsrc == scratch) ? 1 : 0;
+    return DUPL_OK;
+  }
   constexpr int CH = 8;
   const int chunks = cdiv(P, CH);
   DUPL_CHECK_ARG(static_cast<long>(B) * chunks <= 65535, "dupl_par_propagate: B*chunks=%ld exceeds the launch grid",
                  static_cast<long>(B) * chunks);
   dim3 grid(cdiv(w, 32), cdiv(h, 8), B * chunks), block(32, 8);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* src = masks;
   float* dst = scratch;
   for (int it = 0; it < num_iter; ++it) {

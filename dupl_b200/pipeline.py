@@ -111,12 +111,12 @@ class CamParStep:
             n._keep_next = False
         if self.refine is None:
             return None, None, (cams_1, aux_1), (cams_2, aux_2)
-        kw = dict(cls_labels=cls_label, low_thre=self.low_thre, ignore_index=self.ignore_index, img_box=img_box)
+        # both students refine over the same images: one PAR affinity for the two calls (cam_helper.refine_cams_shared_affinity)
         if self.refine == "aux_scalar":
-            lab_1 = cam_helper.refine_cams_with_bkg_v2(self.par, inputs_denorm, cams=aux_1, high_thre=self.scalar_high_thre, **kw)
-            lab_2 = cam_helper.refine_cams_with_bkg_v2(self.par, inputs_denorm, cams=aux_2, high_thre=self.scalar_high_thre, **kw)
+            lab_1, lab_2 = cam_helper.refine_cams_shared_affinity(self.par, inputs_denorm, [aux_1, aux_2], cls_label,
+                                                                  float(self.scalar_high_thre), self.low_thre, self.ignore_index, img_box)
             return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)
         thr_map = high_thres.to(inputs.device, torch.float32).reshape(b, 1, 1, 1).expand(b, 1, h, w).contiguous()
-        lab_1 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_1, high_thre_map=thr_map, **kw)
-        lab_2 = cam_helper.refine_cams_with_dynamic_thres(self.par, inputs_denorm, cams=cams_2, high_thre_map=thr_map, **kw)
+        lab_1, lab_2 = cam_helper.refine_cams_shared_affinity(self.par, inputs_denorm, [cams_1, cams_2], cls_label, thr_map,
+                                                              self.low_thre, self.ignore_index, img_box)
         return lab_1, lab_2, (cams_1, aux_1), (cams_2, aux_2)

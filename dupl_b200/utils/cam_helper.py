@@ -93,6 +93,23 @@ def _refine(ref_mod, images, cams, cls_labels, bkg_h, low_thre, ignore_index, im
     return ops.refine_epilogue(masks, cls, img_box, h, w, ignore_index)
 
 
+def refine_cams_shared_affinity(ref_mod, images, cams_list, cls_labels, bkg_h, low_thre, ignore_index, img_box):
+    """refine_cams_with_dynamic_thres / _bkg_v2 for several CAM tensors over the SAME images (the two students of
+    train_final_voc.py:330-343): PAR's affinity depends on the images only (PAR.py:68-87), so it is computed once
+    instead of once per call (4x per image in the reference).  Returns one label map per entry."""
+    L.require_cuda(images, *cams_list)
+    b, _, h, w = images.shape
+    aff = None
+    out = []
+    for cams in cams_list:
+        images_ds, masks, nactive, cls = ops.refine_prologue(images, cams, cls_labels, bkg_h, low_thre)
+        if aff is None:
+            aff = ops.par_affinity(images_ds, ref_mod.dilations, ref_mod.w1, ref_mod.w2)
+        masks = ops.par_propagate(aff, masks, ref_mod.dilations, ref_mod.num_iter, nactive=nactive)
+        out.append(ops.refine_epilogue(masks, cls, img_box, h, w, ignore_index))
+    return out
+
+
 def refine_cams_with_bkg_v2(ref_mod=None, images=None, cams=None, cls_labels=None, high_thre=None, low_thre=None,
                             ignore_index=False, img_box=None, down_scale=2):
     """utils/cam_helper.py:338-383 (scalar high threshold) -> float32 [b,h,w] in {0..K, ignore}."""

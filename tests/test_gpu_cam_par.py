@@ -138,3 +138,39 @@ def test_refine_labels(dynamic):
             omasks[i, v * n:(v + 1) * n] = O.par_propagate(aff[i:i + 1], mm[i:i + 1, idx], DIL, 10)[0]
     lab, lh, ll = ops.refine_epilogue(omasks.cuda(), clsd, box, H, W, 255, want_parts=True)
     assert torch.equal(lh.cpu(), want_h) and torch.equal(ll.cpu(), want_l) and torch.equal(lab.cpu(), want)
+
+
+@pytest.mark.parametrize("b,K,H,W,grids", [(2, 20, 448, 448, [(28, 28), (14, 14), (42, 42)]), (1, 5, 64, 96, [(4, 6), (2, 3), (6, 9)]),
+                                           (3, 7, 100, 130, [(6, 8)]), (1, 3, 224, 224, [(14, 14), (7, 7)])])
+def test_mscam_column_kernel_is_bit_identical_to_the_generic_kernel(b, K, H, W, grids, monkeypatch):
+    """The column-per-thread kernel hoists the horizontal interpolation out of the row loop; same fma order => same bits."""
+    from dupl_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    lowres = [torch.randn(2 * b, K, gh, gw, generator=g).cuda() for gh, gw in grids]
+    fast = ops.mscam_post(lowres, b, H, W)
+    monkeypatch.setenv("DUPL_MSCAM_GENERIC", "1")
+    slow = ops.mscam_post(lowres, b, H, W)
+    torch.cuda.synchronize()
+    assert torch.isfinite(fast).all()
+    assert torch.equal(fast, slow)
+
+
+@pytest.mark.parametrize("B,P,h,w,live", [(4, 42, 224, 224, [4, 6, 8, 10]), (2, 7, 50, 70, None), (1, 3, 24, 33, None),
+                                          (3, 12, 64, 64, [12, 1, 5])])
+def test_par_tiled_propagation_is_bit_identical_to_the_per_pixel_kernel(B, P, h, w, live, monkeypatch):
+    """Shared-memory tile + halo (replicate border baked in) vs direct clamped gathers: same products, same order."""
+    from dupl_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    dil = [1, 2, 4, 8, 12, 24]
+    imgs = torch.rand(B, 3, h, w, generator=g).cuda()
+    aff = ops.par_affinity(imgs, dil)
+    masks = torch.rand(B, P, h, w, generator=g).cuda()
+    nact = None if live is None else torch.tensor(live, dtype=torch.int32).cuda()
+    fast = ops.par_propagate(aff, masks.clone(), dil, 10, nactive=nact)
+    monkeypatch.setenv("DUPL_PAR_SIMPLE", "1")
+    slow = ops.par_propagate(aff, masks.clone(), dil, 10, nactive=nact)
+    torch.cuda.synchronize()
+    for i in range(B):
+        n = P if live is None else live[i]
+        assert torch.isfinite(fast[i, :n]).all()
+        assert torch.equal(fast[i, :n], slow[i, :n])
