@@ -38,7 +38,7 @@ class GemmGroup(C.Structure):
 class GemmArgs(C.Structure):
     _fields_ = [("groups", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("lda", C.c_int32), ("ldo", C.c_int32), ("epilogue", C.c_int32), ("nseg", C.c_int32),
-                ("ldw", C.c_int32), ("max_ksplit", C.c_int32), ("f32_rows", C.c_int32), ("reserved", C.c_int32),
+                ("ldw", C.c_int32), ("max_ksplit", C.c_int32), ("f32_rows", C.c_int32), ("passes", C.c_int32),
                 ("seg", Segment * MAX_SEGMENTS), ("g", GemmGroup * MAX_GROUPS)]
 
 
@@ -138,6 +138,10 @@ _PROTOTYPES = {
     "dupl_seg_loss_up_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_int64, C.c_void_p, C.c_void_p]),
     "dupl_ptc_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "dupl_ptc_loss_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3),
+    "dupl_ptc_prepare": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 6),
+    "dupl_ptc_mask_reduce": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dupl_ptc_dg": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 3),
+    "dupl_ptc_norm_bwd_rows": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p] * 2),
     "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
                                   C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "dupl_crf_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

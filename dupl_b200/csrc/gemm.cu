@@ -50,6 +50,7 @@ struct GemmParamsDev {
   int ksplit;    // split-K factor: work item (group, k-split, tile); partial s lands at out_f32 + s*M*ldo (EPI_F32 only)
   int kper;      // k-blocks per split
   int f32_rows;  // GELU_SPLIT: rows below this get the fp32 pre-activation side output
+  int passes;    // 3: hi*hi + hi*lo + lo*hi;  4: + lo*lo (products whose SIGN is consumed downstream: PTC Gram)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -173,9 +174,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           const uint64_t a_hi = desc(s), a_lo = desc(s + Cfg::A_BYTES);
           const uint64_t b_hi = desc(s + 2 * Cfg::A_BYTES), b_lo = desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint64_t a = (pass == 2) ? a_lo : a_hi;
-            const uint64_t b = (pass == 1) ? b_lo : b_hi;
+          for (int pass = 0; pass < 4; ++pass) {
+            if (pass >= p.passes) break;
+            const uint64_t a = (pass >= 2) ? a_lo : a_hi;
+            const uint64_t b = (pass == 1 || pass == 3) ? b_lo : b_hi;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               tc_mma_f16_pair(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
@@ -417,6 +419,8 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   memset(&P, 0, sizeof(P));
   P.groups = a->groups; P.M = a->M; P.N = a->N; P.K = a->K; P.ldo = a->ldo; P.epilogue = a->epilogue;
   P.f32_rows = a->f32_rows > 0 ? a->f32_rows : a->M;
+  DUPL_CHECK_ARG(a->passes == 0 || a->passes == 3 || a->passes == 4, "dupl_gemm_bf16x3: passes=%d (3 or 4)", a->passes);
+  P.passes = a->passes == 4 ? 4 : 3;
   P.nseg = 0;
   if (a->epilogue == DUPL_EPI_PATCH) {
     DUPL_CHECK_ARG(a->nseg >= 1 && a->nseg <= DUPL_MAX_SEGMENTS, "dupl_gemm_bf16x3: nseg=%d", a->nseg);

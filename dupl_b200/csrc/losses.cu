@@ -4,6 +4,8 @@
 // Reductions are two-stage (per-block partials, then one block in a fixed order) so results are
 // bit-reproducible.  The Gram is computed in fp32 on the CUDA cores (0.94 GFLOP per image): exact
 // rather than fast; it is < 1 % of the step.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "resample.cuh"
 
@@ -412,6 +414,184 @@ __global__ void __launch_bounds__(256) ptc_bwd_norm_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PTC on the tensor cores: the two contractions of the loss (Gram x_hat x_hat^T per image and dX_hat = T x_hat) are
+// [784 x 768] x [768 x 784] / [784 x 784] x [784 x 768] GEMMs -> dupl_gemm_bf16x3 (split-bf16 operands, fp32 accumulate).
+// The kernels below only produce its operands and consume its results.
+// ------------------------------------------------------------------------------------------------
+// x [b][C][n] fp32, inv [b][n]  ->  x_hat = x * inv as split planes in both layouts:
+//   rows_* [b*n][C]      (token-major: A and W operand of the Gram)
+//   cm_*   [b][C][npad]  (channel-major, zero padded to npad = pad64(n): W operand of dX_hat = T x_hat)
+__global__ void __launch_bounds__(256) ptc_normalize_split_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                                  int C, int n, int npad, __nv_bfloat16* __restrict__ rows_hi,
+                                                                  __nv_bfloat16* __restrict__ rows_lo,
+                                                                  __nv_bfloat16* __restrict__ cm_hi,
+                                                                  __nv_bfloat16* __restrict__ cm_lo) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p = p0 + tx;
+  const float iv = p < n ? inv[b * n + p] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    float v = 0.0f;
+    if (c < C && p < n) v = __ldg(x + (static_cast<long>(b) * C + c) * n + p) * iv;
+    t[ty + 8 * k][tx] = v;
+    if (c < C && p < npad) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const long o = (static_cast<long>(b) * C + c) * npad + p;
+      cm_hi[o] = h;
+      cm_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pp = p0 + ty + 8 * k, c = c0 + tx;
+    if (pp < n && c < C) {
+      const float v = t[tx][ty + 8 * k];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const long o = (static_cast<long>(b) * n + pp) * C + c;
+      rows_hi[o] = h;
+      rows_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// masked sums of |G| -> 4 partials per block (same layout as ptc_gram_kernel's, finished by ptc_finish_kernel).
+// The backward consumes sign(G): cosines closer to zero than the split-bf16 operand rounding (2^-17 per element,
+// ~1e-6 on a 768-term sum) are recomputed here in fp32 from x and written back, so that near-orthogonal token pairs get
+// the sign an fp32 Gram would give them (about one pair per image otherwise flips and moves that image's gradient by 0.5 %).
+constexpr float PTC_RECOMPUTE_BELOW = 1e-5f;
+
+__global__ void __launch_bounds__(256) ptc_mask_reduce_kernel(float* __restrict__ G, const long long* __restrict__ mask,
+                                                              const float* __restrict__ x, const float* __restrict__ inv,
+                                                              int C, int n, long total, float* __restrict__ partials) {
+  __shared__ float sh[8];
+  float pos_sum = 0.0f, neg_sum = 0.0f, pos_cnt = 0.0f, neg_cnt = 0.0f;
+  const long nn = static_cast<long>(n) * n;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+    const long long m = mask[i];
+    float g = G[i];
+    if (fabsf(g) < PTC_RECOMPUTE_BELOW) {
+      const int b = static_cast<int>(i / nn);
+      const long r = i - b * nn;
+      const int p = static_cast<int>(r / n), q = static_cast<int>(r - static_cast<long>(p) * n);
+      const float* xb = x + static_cast<long>(b) * C * n;
+      float acc = 0.0f;
+      for (int c = 0; c < C; ++c) acc = fmaf(__ldg(xb + static_cast<long>(c) * n + p), __ldg(xb + static_cast<long>(c) * n + q), acc);
+      g = acc * inv[b * n + p] * inv[b * n + q];
+      G[i] = g;
+    }
+    g = fabsf(g);
+    if (m == 1) {
+      pos_sum += g;
+      pos_cnt += 1.0f;
+    } else if (m == 0) {
+      neg_sum += g;
+      neg_cnt += 1.0f;
+    }
+  }
+  float r;
+  r = block_sum(pos_sum, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 0] = r;
+  r = block_sum(neg_sum, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 1] = r;
+  r = block_sum(pos_cnt, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 2] = r;
+  r = block_sum(neg_cnt, sh); if (threadIdx.x == 0) partials[4 * blockIdx.x + 3] = r;
+}
+
+// T[p][q] = S[p][q] + S[q][p] (S as in ptc_bwd_gemm_kernel) as split planes [b*n][npad], pad columns zero.
+__global__ void __launch_bounds__(256) ptc_dg_split_kernel(const float* __restrict__ G, const long long* __restrict__ mask,
+                                                           const float* __restrict__ stats, const float* __restrict__ grad_out,
+                                                           int n, int npad, __nv_bfloat16* __restrict__ t_hi,
+                                                           __nv_bfloat16* __restrict__ t_lo) {
+  __shared__ float tr[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float g = grad_out[0];
+  const float wpos = -0.5f / (stats[2] + 1.0f) * g, wneg = 0.5f / (stats[3] + 1.0f) * g;
+  auto sfun = [&](int r, int c) -> float {
+    if (r >= n || c >= n) return 0.0f;
+    const long o = (static_cast<long>(b) * n + r) * n + c;
+    const long long m = mask[o];
+    if (m != 0 && m != 1) return 0.0f;
+    const float gs = G[o];
+    const float sg = gs > 0.0f ? 1.0f : (gs < 0.0f ? -1.0f : 0.0f);
+    return sg * (m == 1 ? wpos : wneg);
+  };
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tr[ty + 8 * k][tx] = sfun(q0 + ty + 8 * k, p0 + tx);  // S[q][p], coalesced over p
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pp = p0 + ty + 8 * k, q = q0 + tx;
+    if (pp < n && q < npad) {
+      const float v = sfun(pp, q) + tr[tx][ty + 8 * k];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const long o = (static_cast<long>(b) * n + pp) * npad + q;
+      t_hi[o] = h;
+      t_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// dxh rows [b*n][C] (token-major result of the GEMM) -> dx [b][C][n]:  dx = inv * (dxh - x_hat * <x_hat, dxh>)
+__global__ void __launch_bounds__(256) ptc_norm_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                                const float* __restrict__ dxh, int C, int n,
+                                                                float* __restrict__ dx) {
+  __shared__ float tr[32][33];
+  __shared__ float part[8][32];
+  __shared__ float dots[32];
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p = p0 + tx;
+  const float iv = p < n ? inv[b * n + p] : 0.0f;
+  float dot = 0.0f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // dxh tile, coalesced over c
+      const int pp = p0 + ty + 8 * k, c = c0 + tx;
+      tr[ty + 8 * k][tx] = (pp < n && c < C) ? __ldg(dxh + (static_cast<long>(b) * n + pp) * C + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k;
+      if (c < C && p < n) dot = fmaf(__ldg(x + (static_cast<long>(b) * C + c) * n + p) * iv, tr[tx][ty + 8 * k], dot);
+    }
+    __syncthreads();
+  }
+  part[ty][tx] = dot;
+  __syncthreads();
+  if (ty == 0) {
+    float d = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d += part[k][tx];
+    dots[tx] = d;
+  }
+  __syncthreads();
+  const float d = dots[tx];
+  const bool clamped = iv >= 1e8f;  // ||x|| <= eps
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pp = p0 + ty + 8 * k, c = c0 + tx;
+      tr[ty + 8 * k][tx] = (pp < n && c < C) ? __ldg(dxh + (static_cast<long>(b) * n + pp) * C + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k;
+      if (c < C && p < n) {
+        const long o = (static_cast<long>(b) * C + c) * n + p;
+        const float xh = __ldg(x + o) * iv;
+        dx[o] = iv * (tr[tx][ty + 8 * k] - (clamped ? 0.0f : xh * d));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace dupl
 
 using namespace dupl;
@@ -492,6 +672,51 @@ extern "C" int dupl_ptc_loss_bwd(const float* x, const int64_t* mask, const floa
   ptc_bwd_gemm_kernel<<<grid, 256, 0, st>>>(x, inv, reinterpret_cast<const long long*>(mask), Gs, stats, grad_out, C, n, dxh_scratch);
   DUPL_LAUNCH_OK();
   ptc_bwd_norm_kernel<<<cdiv(b * n, 256), 256, 0, st>>>(x, inv, dxh_scratch, C, n, b * n, dx);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_prepare(const float* x, int32_t b, int32_t C, int32_t n, int32_t npad, float* inv, void* rows_hi,
+                                void* rows_lo, void* cm_hi, void* cm_lo, void* stream) {
+  DUPL_CHECK_ARG(x && inv && rows_hi && rows_lo && cm_hi && cm_lo && b > 0 && C > 0 && n > 0 && npad >= n,
+                 "dupl_ptc_prepare: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ptc_invnorm_kernel<<<cdiv(b * n, 256), 256, 0, st>>>(x, C, n, b * n, inv);
+  DUPL_LAUNCH_OK();
+  ptc_normalize_split_kernel<<<dim3(cdiv(npad, 32), cdiv(C, 32), b), 256, 0, st>>>(
+      x, inv, C, n, npad, static_cast<__nv_bfloat16*>(rows_hi), static_cast<__nv_bfloat16*>(rows_lo),
+      static_cast<__nv_bfloat16*>(cm_hi), static_cast<__nv_bfloat16*>(cm_lo));
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_mask_reduce(float* G, const int64_t* mask, const float* x, const float* inv, int32_t b, int32_t C,
+                                    int32_t n, float* partials, int32_t nblocks, float* stats, void* stream) {
+  DUPL_CHECK_ARG(G && mask && x && inv && partials && stats && b > 0 && C > 0 && n > 0 && nblocks > 0,
+                 "dupl_ptc_mask_reduce: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ptc_mask_reduce_kernel<<<nblocks, 256, 0, st>>>(G, reinterpret_cast<const long long*>(mask), x, inv, C, n,
+                                                  static_cast<long>(b) * n * n, partials);
+  DUPL_LAUNCH_OK();
+  ptc_finish_kernel<<<1, 256, 0, st>>>(partials, nblocks, stats);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_dg(const float* G, const int64_t* mask, const float* stats, const float* grad_out, int32_t b,
+                           int32_t n, int32_t npad, void* t_hi, void* t_lo, void* stream) {
+  DUPL_CHECK_ARG(G && mask && stats && grad_out && t_hi && t_lo && b > 0 && n > 0 && npad >= n, "dupl_ptc_dg: bad arguments");
+  ptc_dg_split_kernel<<<dim3(cdiv(npad, 32), cdiv(n, 32), b), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      G, reinterpret_cast<const long long*>(mask), stats, grad_out, n, npad, static_cast<__nv_bfloat16*>(t_hi),
+      static_cast<__nv_bfloat16*>(t_lo));
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_ptc_norm_bwd_rows(const float* x, const float* inv, const float* dxh_rows, int32_t b, int32_t C, int32_t n,
+                                      float* dx, void* stream) {
+  DUPL_CHECK_ARG(x && inv && dxh_rows && dx && b > 0 && C > 0 && n > 0, "dupl_ptc_norm_bwd_rows: bad arguments");
+  ptc_norm_bwd_rows_kernel<<<dim3(cdiv(n, 32), b), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, inv, dxh_rows, C, n, dx);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

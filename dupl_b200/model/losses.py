@@ -6,6 +6,7 @@ script's autograd graph (`loss.backward()`) without a PyTorch re-implementation 
 import torch
 
 from .. import _lib as L
+from .. import ops
 
 
 class _SegLoss(torch.autograd.Function):
@@ -69,7 +70,9 @@ class _SegLossUp(torch.autograd.Function):
         return dpred, None, None
 
 
-class _PtcLoss(torch.autograd.Function):
+class _PtcLossSimt(torch.autograd.Function):
+    """fp32 CUDA-core variant (any shape; also the A/B reference of the tensor-core path in tests)."""
+
     @staticmethod
     def forward(ctx, inputs, mask):
         L.require_cuda(inputs, mask)
@@ -102,9 +105,75 @@ class _PtcLoss(torch.autograd.Function):
         return dx, None
 
 
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+class _PtcLoss(torch.autograd.Function):
+    """get_masked_ptc_loss with both contractions on the tensor cores (split-bf16 GEMM): forward G_i = x_hat_i x_hat_i^T per
+    image, backward dX_hat_i = (S_i + S_i^T) x_hat_i.  Shapes the GEMM cannot take (h*w not a multiple of 16, channels not a
+    multiple of 64) use the fp32 CUDA-core kernels (_PtcLossSimt)."""
+
+    @staticmethod
+    def forward(ctx, inputs, mask):
+        L.require_cuda(inputs, mask)
+        x = L.f32c(inputs.detach())
+        b, c, h, w = x.shape
+        n = h * w
+        mask = mask.to(torch.int64).contiguous()
+        if tuple(mask.shape) != (b, n, n):
+            raise ValueError(f"mask must be [b, h*w, h*w] = {(b, n, n)}, got {tuple(mask.shape)}")
+        dev = x.device
+        npad = _pad64(n)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        inv = torch.empty(b, n, dtype=torch.float32, device=dev)
+        rows = (torch.empty(b * n, c, **bf), torch.empty(b * n, c, **bf))
+        cm = (torch.empty(b, c, npad, **bf), torch.empty(b, c, npad, **bf))
+        st = L.stream_ptr(dev)
+        L.check(L.lib().dupl_ptc_prepare(L.ptr(x), b, c, n, npad, L.ptr(inv), L.ptr(rows[0]), L.ptr(rows[1]), L.ptr(cm[0]),
+                                         L.ptr(cm[1]), st), "dupl_ptc_prepare")
+        G = torch.empty(b, n, n, dtype=torch.float32, device=dev)
+        for i in range(0, b, L.MAX_GROUPS):
+            ops.gemm_bf16x3([dict(a=(rows[0][j * n:(j + 1) * n], rows[1][j * n:(j + 1) * n]),
+                                  w=(rows[0][j * n:(j + 1) * n], rows[1][j * n:(j + 1) * n]), out_f32=G[j])
+                             for j in range(i, min(i + L.MAX_GROUPS, b))], n, n, c, L.EPI_F32)
+        nblocks = 592
+        partials = torch.empty(4 * nblocks, dtype=torch.float32, device=dev)
+        stats = torch.empty(5, dtype=torch.float32, device=dev)
+        L.check(L.lib().dupl_ptc_mask_reduce(L.ptr(G), L.ptr(mask), L.ptr(x), L.ptr(inv), b, c, n, L.ptr(partials), nblocks, L.ptr(stats), st),
+                "dupl_ptc_mask_reduce")
+        ctx.save_for_backward(x, mask, inv, G, stats, cm[0], cm[1])
+        return stats[4].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, mask, inv, G, stats, cm_hi, cm_lo = ctx.saved_tensors
+        b, c, h, w = x.shape
+        n = h * w
+        npad = cm_hi.shape[2]
+        dev = x.device
+        st = L.stream_ptr(dev)
+        g = L.f32c(grad_out).reshape(1)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        t = (torch.empty(b * n, npad, **bf), torch.empty(b * n, npad, **bf))
+        L.check(L.lib().dupl_ptc_dg(L.ptr(G), L.ptr(mask), L.ptr(stats), L.ptr(g), b, n, npad, L.ptr(t[0]), L.ptr(t[1]), st),
+                "dupl_ptc_dg")
+        dxh = torch.empty(b * n, c, dtype=torch.float32, device=dev)
+        for i in range(0, b, L.MAX_GROUPS):
+            ops.gemm_bf16x3([dict(a=(t[0][j * n:(j + 1) * n], t[1][j * n:(j + 1) * n]), w=(cm_hi[j], cm_lo[j]),
+                                  out_f32=dxh[j * n:(j + 1) * n]) for j in range(i, min(i + L.MAX_GROUPS, b))],
+                            n, c, npad, L.EPI_F32)
+        dx = torch.empty_like(x)
+        L.check(L.lib().dupl_ptc_norm_bwd_rows(L.ptr(x), L.ptr(inv), L.ptr(dxh), b, c, n, L.ptr(dx), st), "dupl_ptc_norm_bwd_rows")
+        return dx, None
+
+
 def get_masked_ptc_loss(inputs, mask):
     """model/losses.py:6-21"""
-    return _PtcLoss.apply(inputs, mask)
+    n = inputs.shape[2] * inputs.shape[3]
+    if n % 16 == 0 and inputs.shape[1] % 64 == 0:
+        return _PtcLoss.apply(inputs, mask)
+    return _PtcLossSimt.apply(inputs, mask)
 
 
 def get_seg_loss(pred, label, ignore_index=255):

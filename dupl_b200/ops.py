@@ -40,7 +40,7 @@ def split_bf16(x, out=None):
     return hi, lo
 
 
-def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=None, ksplit=0, f32_rows=0):
+def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=None, ksplit=0, f32_rows=0, passes=3):
     """groups: list of dicts with keys a=(hi,lo), w=(hi,lo), bias, resid, out_f32, out=(hi,lo), pos=[...].
     ksplit > 1 lets the library split the contraction up to that many ways (plain F32 epilogue, no bias): the
     partial sums go through a workspace allocated here and are added in a fixed order."""
@@ -51,6 +51,7 @@ def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=No
     a.ldw = 0 if ldw is None else ldw
     a.max_ksplit = ksplit
     a.f32_rows = f32_rows
+    a.passes = passes
     a.epilogue = epilogue
     ws = []
     a.nseg = 0

@@ -102,7 +102,7 @@ typedef struct {
   int32_t ldw;                          /* row stride of the W planes in elements (0 = K) */
   int32_t max_ksplit;                   /* 0/1 = no split-K; else the workspace holds this many partials (F32 epilogue, no bias) */
   int32_t f32_rows;                     /* GELU_SPLIT: only rows < f32_rows get the out_f32 side output (0 = all rows) */
-  int32_t reserved;
+  int32_t passes;                       /* 0/3: hi*hi + hi*lo + lo*hi (error ~2^-16 of sum|a_i w_i|); 4: also lo*lo (fp32-level) */
   dupl_segment seg[DUPL_MAX_SEGMENTS];  /* PATCH only: patch row -> token row mapping */
   dupl_gemm_group g[DUPL_MAX_GROUPS];
 } dupl_gemm_args;
@@ -361,6 +361,21 @@ int dupl_ptc_loss_fwd(const float* x, const int64_t* mask, int32_t b, int32_t C,
                       float* partials, float* stats, void* stream);
 int dupl_ptc_loss_bwd(const float* x, const int64_t* mask, const float* inv, const float* Gs, const float* stats,
                       const float* grad_out, int32_t b, int32_t C, int32_t n, float* dxh_scratch, float* dx, void* stream);
+
+/* The same loss with its two contractions on the tensor cores (model/losses.py:6-21): the host sequences
+ *   dupl_ptc_prepare  ->  dupl_gemm_bf16x3 (G_i = x_hat_i x_hat_i^T per image)  ->  dupl_ptc_mask_reduce          (forward)
+ *   dupl_ptc_dg  ->  dupl_gemm_bf16x3 (dX_hat_i = T_i x_hat_i)  ->  dupl_ptc_norm_bwd_rows                          (backward)
+ * rows_*: split-bf16 x_hat [b*n, C] (token-major); cm_*: split-bf16 x_hat [b, C, npad] (channel-major, zero padded to
+ * npad = multiple of 64); G fp32 [b, n, n]; t_*: split-bf16 T = S + S^T [b*n, npad]; dxh_rows fp32 [b*n, C]. */
+int dupl_ptc_prepare(const float* x, int32_t b, int32_t C, int32_t n, int32_t npad, float* inv, void* rows_hi, void* rows_lo,
+                     void* cm_hi, void* cm_lo, void* stream);
+/* also re-derives in fp32 (from x, inv) the entries of G closer to zero than the split-bf16 rounding, in place */
+int dupl_ptc_mask_reduce(float* G, const int64_t* mask, const float* x, const float* inv, int32_t b, int32_t C, int32_t n,
+                         float* partials, int32_t nblocks, float* stats, void* stream);
+int dupl_ptc_dg(const float* G, const int64_t* mask, const float* stats, const float* grad_out, int32_t b, int32_t n,
+                int32_t npad, void* t_hi, void* t_lo, void* stream);
+int dupl_ptc_norm_bwd_rows(const float* x, const float* inv, const float* dxh_rows, int32_t b, int32_t C, int32_t n, float* dx,
+                           void* stream);
 
 /* GMM noise filter of the training loop (train_final_voc.py:358-394, sklearn GaussianMixture in the
  * reference): per image, 2-component 1-D mixture on loss[label not in {0, ignore} and loss > loss_min]; when more

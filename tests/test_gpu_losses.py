@@ -66,7 +66,7 @@ def test_seg_loss_without_foreground_or_background_is_finite():
     assert loss.item() == 0.0 and torch.count_nonzero(pred.grad) == 0
 
 
-@pytest.mark.parametrize("b,C,h,w", [(2, 768, 7, 9), (1, 96, 12, 11), (3, 768, 28, 28)])
+@pytest.mark.parametrize("b,C,h,w", [(2, 768, 7, 9), (1, 96, 12, 11), (3, 768, 28, 28), (2, 768, 4, 4), (4, 768, 28, 28), (1, 64, 8, 6)])
 def test_ptc_loss_value_and_gradient(b, C, h, w):
     from dupl_b200.model.losses import get_masked_ptc_loss
     from dupl_b200.utils import cam_helper
@@ -93,3 +93,22 @@ def test_losses_match_reference_golden_values():
     assert abs(ptc.item() - float(d["ptc"])) < 1e-5
     seg = get_seg_loss(d["pred"].float().cuda(), d["label"].long().cuda(), ignore_index=255)
     assert abs(seg.item() - float(d["seg"])) < 1e-4
+
+
+def test_ptc_tensor_core_path_agrees_with_the_fp32_simt_path():
+    """Same loss through the split-bf16 GEMM (Gram and dX_hat on tcgen05) and through the fp32 CUDA-core kernels."""
+    from dupl_b200.model.losses import _PtcLoss, _PtcLossSimt
+    from dupl_b200.utils import cam_helper
+    g = torch.Generator().manual_seed(3)
+    fmap = torch.randn(4, 768, 28, 28, generator=g).cuda()
+    lab = torch.randint(0, 5, (4, 28, 28), generator=g)
+    lab[lab == 4] = 255
+    aff = cam_helper.label_to_aff_mask(lab.cuda())
+    outs = []
+    for fn in (_PtcLoss, _PtcLossSimt):
+        f = fmap.clone().requires_grad_(True)
+        loss = fn.apply(f, aff)
+        (loss * 0.2).backward()
+        outs.append((loss.item(), f.grad.clone()))
+    assert abs(outs[0][0] - outs[1][0]) < 2e-6
+    assert rel_err(outs[0][1], outs[1][1]) < 1e-4
