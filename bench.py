@@ -330,7 +330,15 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     optim = make_optimizer(model)
     wrapped = model
     if h.world > 1:
-        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[h.local_rank], find_unused_parameters=True)
+        # train_final_voc.py:155 wraps with find_unused_parameters=True (encoder.head.* never receives a gradient).  The
+        # fused driver knows the graph is the same every step: static_graph lets the reducer skip the per-step traversal,
+        # bucket views avoid the copy back.  DUPL_DDP=reference restores the script's exact construction for A/B runs.
+        if os.environ.get("DUPL_DDP", "") == "reference":
+            kw = dict(find_unused_parameters=True)
+        else:
+            kw = dict(find_unused_parameters=True, static_graph=True, gradient_as_bucket_view=True,
+                      bucket_cap_mb=int(os.environ.get("DUPL_DDP_BUCKET_MB", "64")))
+        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[h.local_rank], **kw)
     targs = Args if K == 20 else Args.coco()
     step = PhaseBStep(wrapped, optim, args=targs, device=h.dev)
     x, cls, box, _ = make_inputs(h.rank, K)
