@@ -16,6 +16,8 @@
 // independent of summation order: bit-reproducible run to run although the build uses atomics.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dupl {
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(256) crf_neighbors_kernel(CrfWs ws, const int*
 // Gather-splat: each warp walks CRF_CHUNK consecutive csr positions (sorted by vertex), lanes = classes.
 template <int CPL>
 __global__ void __launch_bounds__(256) crf_splat_kernel(CrfWs ws, const float* __restrict__ Q, int C, int use_norm,
-                                                        long long* __restrict__ acc) {
+                                                        long long* __restrict__ acc, int k0, int ldc) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long start = static_cast<long>(warp) * CRF_CHUNK;
@@ -396,9 +398,9 @@ __global__ void __launch_bounds__(256) crf_splat_kernel(CrfWs ws, const float* _
         if (cur >= 0) {
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
-            const int k = lane + 32 * c;
+            const int k = k0 + lane + 32 * c;
             if (k < C && a[c] != 0)
-              atomicAdd(reinterpret_cast<unsigned long long*>(acc + static_cast<long>(cur) * C + k),
+              atomicAdd(reinterpret_cast<unsigned long long*>(acc + static_cast<long>(cur) * ldc + k),
                         static_cast<unsigned long long>(a[c]));
             a[c] = 0;
           }
@@ -407,9 +409,9 @@ __global__ void __launch_bounds__(256) crf_splat_kernel(CrfWs ws, const float* _
       }
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        const int k = lane + 32 * c;
+        const int k = k0 + lane + 32 * c;
         if (k < C) {
-          const float q = Q != nullptr ? __ldg(Q + static_cast<long>(pi) * C + k) : 1.0f;
+          const float q = Q != nullptr ? __ldg(Q + static_cast<long>(pi) * ldc + k) : 1.0f;
           a[c] += __float2ll_rn(wi * q * CRF_FIX);
         }
       }
@@ -418,9 +420,9 @@ __global__ void __launch_bounds__(256) crf_splat_kernel(CrfWs ws, const float* _
   if (cur >= 0) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      const int k = lane + 32 * c;
+      const int k = k0 + lane + 32 * c;
       if (k < C && a[c] != 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + static_cast<long>(cur) * C + k),
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + static_cast<long>(cur) * ldc + k),
                   static_cast<unsigned long long>(a[c]));
     }
   }
@@ -600,7 +602,7 @@ static int build_one(const CrfWs& ws, const unsigned char* img, int W, int H, fl
   // norm = 1/sqrt(K 1 + 1e-20): the filter applied to a vector of ones (C = 1), M read on the device
   DUPL_CUDA_OK(cudaMemsetAsync(ws.acc1, 0, sizeof(long long) * ws.E, st));
   const int warps = cdiv(ws.E, CRF_CHUNK);
-  crf_splat_kernel<1><<<cdiv(warps, 8), 256, 0, st>>>(ws, nullptr, 1, 0, ws.acc1);
+  crf_splat_kernel<1><<<cdiv(warps, 8), 256, 0, st>>>(ws, nullptr, 1, 0, ws.acc1, 0, 1);
   DUPL_LAUNCH_OK();
   float* a = ws.val_a;
   float* b = ws.val_b;
@@ -650,8 +652,20 @@ static int infer_impl(const dupl_crf_args* a, const CrfLayout& L, const int* M, 
       const CrfWs& ws = L.k[k];
       const size_t mc = static_cast<size_t>(M[k]) * C;
       DUPL_CUDA_OK(cudaMemsetAsync(acc[k], 0, mc * sizeof(long long), st));
-      crf_splat_kernel<CPL><<<cdiv(cdiv(ws.E, CRF_CHUNK), 8), 256, 0, st>>>(ws, Q, C, 1, acc[k]);
-      DUPL_LAUNCH_OK();
+      // The gather reads every pixel's Q row once per lattice vertex it touches (d+1 times, in vertex order = random
+      // in pixel order).  With C > 32 the [N][C] matrix (100 MB at 640x480x81) does not stay in L2 and every one of those
+      // reads went to DRAM (ncu: 624 MB per launch against 153 MB algorithmic).  32 classes at a time, the 128-byte
+      // slices of all rows (39 MB) are L2-resident across the d+1 visits.  (DUPL_CRF_SPLAT_WIDE=1: single wide pass.)
+      static const bool wide = getenv("DUPL_CRF_SPLAT_WIDE") != nullptr;
+      if (CPL > 1 && !wide) {
+        for (int k0 = 0; k0 < C; k0 += 32) {
+          crf_splat_kernel<1><<<cdiv(cdiv(ws.E, CRF_CHUNK), 8), 256, 0, st>>>(ws, Q, min(C, k0 + 32), 1, acc[k], k0, C);
+          DUPL_LAUNCH_OK();
+        }
+      } else {
+        crf_splat_kernel<CPL><<<cdiv(cdiv(ws.E, CRF_CHUNK), 8), 256, 0, st>>>(ws, Q, C, 1, acc[k], 0, C);
+        DUPL_LAUNCH_OK();
+      }
       float* x = va[k];
       float* y = vb[k];
       const int blocks = static_cast<int>((mc + 255) / 256);
