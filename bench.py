@@ -309,7 +309,9 @@ def gemm_roofline(timer, peaks, peak_kind, step_tflops, timed_in):
             "step_tflops": step_tflops}
 
 
-TRAFFIC_GEMM_BYTES = None  # filled from the committed ncu capture (profiles/); None until one exists for this build
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three captured M = 21 976 encoder launches (qkv 294.6 MB,
+# proj 225.1 MB, fc2 422.6 MB; algorithmic 277 / 205 / 414 MB) of `ncu --set full` on this command: profiles/r01_summary.md
+TRAFFIC_GEMM_BYTES = 314.1e6
 
 
 def build_model(K, dev, train=False):
