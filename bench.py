@@ -329,7 +329,10 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     from dupl_b200 import _lib as L
     from dupl_b200.train_step import PhaseBStep, make_optimizer, Args
     model, P = build_model(K, h.dev, train=True)
-    optim = make_optimizer(model)
+    # one process per model: the whole iteration is one CUDA graph (DUPL_TRAIN_CAPTURE=0 switches it off); under DDP the
+    # reducer's hooks need the eager autograd pass
+    capture = h.world == 1 and os.environ.get("DUPL_TRAIN_CAPTURE", "1") != "0"
+    optim = make_optimizer(model, capturable=capture)
     wrapped = model
     if h.world > 1:
         # train_final_voc.py:155 wraps with find_unused_parameters=True (encoder.head.* never receives a gradient).  The
@@ -342,42 +345,55 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
                       bucket_cap_mb=int(os.environ.get("DUPL_DDP_BUCKET_MB", "64")))
         wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[h.local_rank], **kw)
     targs = Args if K == 20 else Args.coco()
-    step = PhaseBStep(wrapped, optim, args=targs, device=h.dev)
+    step = PhaseBStep(wrapped, optim, args=targs, device=h.dev, capture=capture)
     x, cls, box, _ = make_inputs(h.rank, K)
+    if K == 80:
+        cls = cls.to(torch.uint8)           # COCO labels are uint8 (datasets/coco.py)
+    phase_c = getattr(args, "phase", "B") == "C"
+    # phase B: cam_iters <= n_iter < gmm_iters; phase C adds the augmented view (synthetic: another seeded batch), GMM, consistency
+    it = [(targs.gmm_iters + 1000) if phase_c else (targs.cam_iters + targs.gmm_iters) // 2]
+    if K == 80 and not phase_c:
+        it = [20000]                        # past the cams_aux window (n_iter <= 12000), before gmm_iters = 32000
+    from helpers import synth_images
+    x_aug = synth_images(BATCH, SIZE, SIZE, seed=100 + h.rank) if phase_c else None
     x_pin, cls_pin = x.pin_memory(), cls.pin_memory()
     x_dev, cls_dev = x.to(h.dev), cls.to(h.dev)
-    it = [3000]
+    aug_pin = x_aug.pin_memory() if phase_c else None
+    aug_dev = x_aug.to(h.dev) if phase_c else None
     last = {}
 
     def device_step():
-        last["loss"], _ = step(x_dev, cls_dev, box, it[0])
+        last["loss"], _ = step(x_dev, cls_dev, box, it[0], aug_dev)
         it[0] += 1
 
     def e2e_step():
         xi = x_pin.to(h.dev, non_blocking=True)
         ci = cls_pin.to(h.dev, non_blocking=True)
-        loss, _ = step(xi, ci, box, it[0])
+        ai = aug_pin.to(h.dev, non_blocking=True) if phase_c else None
+        loss, _ = step(xi, ci, box, it[0], ai)
         it[0] += 1
         last["loss_host"] = loss.item()   # device -> host read of the step's result
 
     for _ in range(warmup):
         device_step()
     ms = h.time_device(device_step, steps)
-    out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 + cls_pin.numel() * 4), d2h=4, P=P, inputs=(x, cls, box))
+    out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 * (2 if phase_c else 1) + cls_pin.numel() * cls_pin.element_size()), d2h=4, P=P,
+               inputs=(x, cls, box), n_iter=it[0])
     timer = None
     if want_roofline:
-        eager = PhaseBStep(wrapped, optim, args=targs, device=h.dev, graph=False)
-        eager(x_dev, cls_dev, box, it[0])
+        eager = PhaseBStep(wrapped, make_optimizer(model) if capture else optim, args=targs, device=h.dev, graph=False)
+        eager(x_dev, cls_dev, box, it[0], aug_dev)
         launches0 = L.lib().dupl_launch_count()
         with GemmTimer(h.stream) as timer:
             h.barrier()
             for _ in range(steps):
-                eager(x_dev, cls_dev, box, it[0])
+                eager(x_dev, cls_dev, box, it[0], aug_dev)
             h.barrier()
         out["launches"] = int(L.lib().dupl_launch_count() - launches0)
     e2e_step()
     out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps
     out["timer"] = timer
+    out["capture"] = capture
     out["loss"] = float(last["loss"].item())
     out["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
     return out
@@ -522,10 +538,12 @@ def run_train(h, args):
             "metric": "train_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{args.dataset}{K + 1}_dual_student_phaseB_step_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
+            "config": {"workload": f"{args.dataset}{K + 1}_dual_student_phase{args.phase}_step_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
+                       "n_iter": t["n_iter"],
                        "classes": K + 1, "parallelism": f"ddp{h.world} (NCCL all-reduce of 732.7 MB fp32 grads per step)" if h.world > 1 else "single GPU",
                        "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush",
-                       "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images"},
+                       "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images",
+                       "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half only (DDP reducer needs eager autograd)"},
             "e2e": {"value": imgs / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
                     "ms_per_step": e2e_ms},
             "gpu_launches": t.get("launches"), "clocks": clocks, "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
@@ -630,6 +648,7 @@ def main():
     ap.add_argument("--impl", default="dupl_b200", choices=["dupl_b200", "reference"])
     ap.add_argument("--workload", default="cam_par", choices=["cam_par", "train", "crf_sweep"])
     ap.add_argument("--dataset", default="voc", choices=["voc", "coco"], help="train workload: class count / loss weights")
+    ap.add_argument("--phase", default="B", choices=["B", "C"], help="train workload: B = CAM+PAR+seg (default), C = + aug view, GMM filter, consistency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="cam_par: skip the secondary training-step measurement")
     ap.add_argument("--fuse-students", action="store_true", help="both students per grouped GEMM launch")

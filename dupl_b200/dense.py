@@ -39,6 +39,14 @@ class DecoderPlanes:
         return hit[1]
 
 
+def _invalidate(self):
+    for name, (key, planes) in list(self._cache.items()):
+        self._cache[name] = ((0, -1), planes)
+
+
+DecoderPlanes.invalidate = _invalidate
+
+
 def _get_t(self, name):
     """Transposed implicit-GEMM weight planes [9*Cin, Cout] (B operand of the conv dgrad GEMM)."""
     conv = getattr(self.net.decoder, name)

@@ -62,6 +62,12 @@ class StudentPlanes:
             self._planes[name] = hit
         return hit[1]
 
+    def invalidate(self):
+        """Marks every cached plane stale (keeps the buffers): used after a CUDA-graph replay changed the parameters
+        without bumping their `_version`."""
+        for name, (key, planes) in list(self._planes.items()):
+            self._planes[name] = ((0, -1), planes)
+
     def refresh_all(self):
         """Re-splits every GEMM weight into its (persistent) planes unconditionally.  Called inside a CUDA-graph
         capture so that each replay picks up the weights the optimizer wrote since the previous one."""

@@ -102,16 +102,25 @@ def cosine_descent(max_thres, min_thres, step, num_steps):
 
 
 class PolyWarmupAdamW(torch.optim.AdamW):
-    """utils/optimizer.py:38-68: AdamW whose step() first sets the warm-up / polynomial learning rate."""
+    """utils/optimizer.py:38-68: AdamW whose step() first sets the warm-up / polynomial learning rate.
+    capturable=True keeps the learning rates and step counters in device tensors so that step() can be part of a CUDA
+    graph (TrainStep(capture=True)); the schedule is then advanced by advance_schedule() before each replay."""
 
     def __init__(self, params, lr, weight_decay, betas, warmup_iter=None, max_iter=None, warmup_ratio=None, power=None,
-                 fused=None):
-        super().__init__(params, lr=lr, betas=betas, weight_decay=weight_decay, eps=1e-8, fused=fused)
+                 fused=None, capturable=False):
+        params = list(params)
+        self._init_lr = [g["lr"] for g in params]
+        if capturable:
+            dev = params[0]["params"][0].device
+            for g in params:
+                g["lr"] = torch.tensor(g["lr"], dtype=torch.float32, device=dev)
+            lr = torch.tensor(lr, dtype=torch.float32, device=dev)
+        super().__init__(params, lr=lr, betas=betas, weight_decay=weight_decay, eps=1e-8, fused=fused, capturable=capturable)
         self.global_step = 0
         self.warmup_iter, self.warmup_ratio, self.max_iter, self.power = warmup_iter, warmup_ratio, max_iter, power
-        self._init_lr = [g["lr"] for g in self.param_groups]
 
-    def step(self, closure=None):
+    def advance_schedule(self):
+        """Sets this step's learning rates (utils/optimizer.py:52-66) and counts the step."""
         if self.global_step < self.warmup_iter:
             m = 1 - (1 - self.global_step / self.warmup_iter) * (1 - self.warmup_ratio)
         elif self.global_step < self.max_iter:
@@ -120,12 +129,22 @@ class PolyWarmupAdamW(torch.optim.AdamW):
             m = None
         if m is not None:
             for g, lr0 in zip(self.param_groups, self._init_lr):
-                g["lr"] = lr0 * m
-        super().step(closure)
+                if torch.is_tensor(g["lr"]):
+                    g["lr"].fill_(lr0 * m)
+                else:
+                    g["lr"] = lr0 * m
         self.global_step += 1
 
+    def step(self, closure=None):
+        self.advance_schedule()
+        super().step(closure)
 
-def make_optimizer(model, args=Args):
+    def step_captured(self, closure=None):
+        """The parameter update alone (what a CUDA graph captures); the caller advances the schedule."""
+        super().step(closure)
+
+
+def make_optimizer(model, args=Args, capturable=False):
     """utils/train_helper.py:21-87 (get_optimizer): 4 groups, heads and decoders at 10x learning rate."""
     g = model.get_param_groups()
     on_gpu = all(p.is_cuda for grp in g for p in grp)  # torch's single-kernel-per-chunk AdamW (same update rule)
@@ -135,17 +154,23 @@ def make_optimizer(model, args=Args):
                 {"params": g[2], "lr": args.lr * 10, "weight_decay": args.wt_decay},
                 {"params": g[3], "lr": args.lr * 10, "weight_decay": args.wt_decay}],
         lr=args.lr, weight_decay=args.wt_decay, betas=args.betas, warmup_iter=args.warmup_iters, max_iter=args.max_iters,
-        warmup_ratio=args.warmup_lr, power=args.power, fused=True if on_gpu else None)
+        warmup_ratio=args.warmup_lr, power=args.power, fused=True if on_gpu else None, capturable=capturable and on_gpu)
 
 
 class TrainStep:
     """One iteration of the training loop for any n_iter (phases A / B / C of train_final_voc.py:186-472 and
     train_final_coco.py:182-464).  `PhaseBStep` is the historical name of the same class."""
 
-    def __init__(self, model, optim=None, args=Args, device=None, graph=True, reuse_forward=True):
+    def __init__(self, model, optim=None, args=Args, device=None, graph=True, reuse_forward=True, capture=False):
+        """capture=True: the WHOLE iteration (MS-CAM, PAR, forward heads, losses, backward, AdamW) is captured once per phase
+        as one CUDA graph and replayed; ~1500 kernel launches per step otherwise keep the host as busy as the GPU.  Needs a
+        capturable optimizer (make_optimizer(..., capturable=True)) and a single process per model (no DDP reducer)."""
         self.model = model          # siamese_network or DistributedDataParallel(siamese_network)
         self.optim = optim
         self.args = args
+        self.capture = capture
+        self._graphs = {}
+        self._sched = None          # static device scalars of the threshold schedule while capturing / replaying
         dev = device or next(model.parameters()).device
         self.par = PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24]).to(dev)
         # reuse_forward: `model(inputs)` of train_final_voc.py:287 recomputes what the MS-CAM pass has just computed for
@@ -163,6 +188,9 @@ class TrainStep:
                                    keep_activations=self.reuse_forward, refine="aux_scalar", scalar_high_thre=args.high_thre)
         for st in (self._cam_only, self._cam_aux):
             st.par = self.par
+        if capture:                 # one graph for everything: the CAM half is captured inline, not replayed as a sub-graph
+            for st in (self.pseudo, self._cam_only, self._cam_aux):
+                st.graph = False
         K = args.num_classes - 1
         self.thres_start = torch.ones(K, device=dev) * args.high_thre
         self.thres_target = torch.tensor(args.high_thres_target, dtype=torch.float32, device=dev)
@@ -203,7 +231,11 @@ class TrainStep:
             high_thres = a.high_thre
         else:
             # per-image high threshold = max over the present classes of the cosine-annealed class thresholds
-            thres = cosine_descent(self.thres_start, self.thres_target, n_iter - a.thres_anneal_from, a.max_iters - a.thres_anneal_from)
+            if self._sched is not None:   # captured: same expression with the two host scalars read from device memory
+                omc, done = self._sched
+                thres = torch.where(done, self.thres_target, self.thres_start + (self.thres_target - self.thres_start) * omc / 2)
+            else:
+                thres = cosine_descent(self.thres_start, self.thres_target, n_iter - a.thres_anneal_from, a.max_iters - a.thres_anneal_from)
             high_thres = torch.where(cls_f > 0, thres[None, :], thres.new_full((), -math.inf)).amax(1)
             # multi_scale_cam2_siamese x2 and refine_cams_with_* x2 (train_final_voc.py:279-284, 330-343; coco :312-333).
             # cams * cls_label_rep of the script is the identity on the channels the refine kernels read (one-hot labels).
@@ -267,11 +299,100 @@ class TrainStep:
         return loss, dict(cls_loss=cls_loss, ptc_loss=ptc_loss, seg_loss=seg_loss, sim_loss=sim_loss, reg_loss=reg_loss), labels
 
     def __call__(self, inputs, cls_label, img_box, n_iter, inputs_aug=None):
+        if self.capture:
+            return self._replay(inputs, cls_label, img_box, n_iter, inputs_aug)
         loss, parts, _ = self.losses(inputs, cls_label, img_box, n_iter, inputs_aug)
         self.optim.zero_grad()
         loss.backward()
         self.optim.step()
         return loss.detach(), {k: v.detach() for k, v in parts.items()}
+
+    # ------------------------------------------------------------------ whole-iteration CUDA graph
+    def _phase_key(self, n_iter, inputs, cls_label, inputs_aug):
+        a = self.args
+        w = a.loss_weights(n_iter)
+        return (n_iter < a.cam_iters, a.aux_refine_until is not None and n_iter <= a.aux_refine_until, n_iter >= a.gmm_iters,
+                tuple(sorted(w.items())), tuple(inputs.shape), tuple(cls_label.shape), cls_label.dtype, inputs_aug is not None)
+
+    def _set_schedule(self, st, n_iter):
+        a = self.args
+        step, num = n_iter - a.thres_anneal_from, a.max_iters - a.thres_anneal_from
+        if step < 0:
+            omc, done = 0.0, False
+        elif step >= num:
+            omc, done = 0.0, True
+        else:
+            omc, done = float(1 - np.cos(np.pi * (step / (num - 1)))), False
+        st["omc"].fill_(omc)
+        st["done"].fill_(done)
+
+    def _replay(self, inputs, cls_label, img_box, n_iter, inputs_aug):
+        if hasattr(self.model, "module"):
+            raise RuntimeError("TrainStep(capture=True) drives one process per model; use capture=False under DistributedDataParallel")
+        dev = inputs.device
+        key = self._phase_key(n_iter, inputs, cls_label, inputs_aug)
+        st = self._graphs.get(key)
+        first = st is None
+        if first:
+            st = dict(x=torch.empty_like(inputs), cls=torch.empty_like(cls_label),
+                      box=torch.empty(inputs.shape[0], 4, dtype=torch.int32, device=dev),
+                      aug=None if inputs_aug is None else torch.empty_like(inputs_aug),
+                      omc=torch.zeros((), dtype=torch.float32, device=dev), done=torch.zeros((), dtype=torch.bool, device=dev))
+            self._graphs[key] = st
+        st["x"].copy_(inputs, non_blocking=True)
+        st["cls"].copy_(cls_label, non_blocking=True)
+        st["box"].copy_(torch.as_tensor(img_box).to(torch.int32), non_blocking=True)
+        if inputs_aug is not None:
+            st["aug"].copy_(inputs_aug, non_blocking=True)
+        self._set_schedule(st, n_iter)
+        self._sched = (st["omc"], st["done"])
+        try:
+            if first:
+                # warm-up outside capture (lazy caches, optimizer state tensors, allocator pools); parameters, optimizer
+                # state and schedule are put back afterwards, so the first captured call is ONE training step like any other
+                params = [p for g in self.optim.param_groups for p in g["params"]]
+                saved_p = [p.detach().clone() for p in params]
+                saved_s = {p: {k: v.clone() for k, v in s.items() if torch.is_tensor(v)} for p, s in self.optim.state.items()}
+                saved_step = self.optim.global_step
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
+                        self.optim.zero_grad(set_to_none=True)
+                        loss.backward()
+                        self.optim.step_captured()
+                    with torch.no_grad():
+                        for p, q in zip(params, saved_p):
+                            p.copy_(q)
+                        for p, s in self.optim.state.items():
+                            for k, v in s.items():
+                                if torch.is_tensor(v):
+                                    if p in saved_s and k in saved_s[p]:
+                                        v.copy_(saved_s[p][k])
+                                    else:
+                                        v.zero_()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                self.optim.global_step = saved_step
+                del saved_p, saved_s
+                self.optim.zero_grad(set_to_none=True)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
+                    loss.backward()
+                    self.optim.step_captured()
+                st["graph"], st["loss"], st["parts"] = graph, loss.detach(), {k: v.detach() for k, v in parts.items()}
+            self.optim.advance_schedule()
+            st["graph"].replay()
+            # the replay updated the parameters without bumping `_version`: eager users of the weight planes must re-split
+            net = self.model
+            for b in (net.branch1, net.branch2):
+                b.planes().invalidate()
+                if getattr(b, "_dec_planes", None) is not None:
+                    b._dec_planes.invalidate()
+        finally:
+            self._sched = None
+        return st["loss"], st["parts"]
 
 
 PhaseBStep = TrainStep
