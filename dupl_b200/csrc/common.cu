@@ -68,6 +68,31 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return DUPL_OK;
 }
 
+int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                     uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return DUPL_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (d0 * 4) % 16 != 0) {
+    set_error("TMA operand must be 16-byte aligned (base %p, row of %llu floats)", base, static_cast<unsigned long long>(d0));
+    return DUPL_ERR_INVALID_ARGUMENT;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {d0 * 4, d0 * d1 * 4};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D fp32) failed with CUresult %d", static_cast<int>(r));
+    return DUPL_ERR_CUDA;
+  }
+  return DUPL_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

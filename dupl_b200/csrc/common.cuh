@@ -46,6 +46,11 @@ void count_launch();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols = 64);
 
+// 3-D fp32 tensor map over a dense [d2][d1][d0] array (d0 innermost), box = b2 x b1 x b0, no swizzle; out-of-bounds
+// elements read as zero.  d0 must be a multiple of 4 (16-byte global strides).
+int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                     uint32_t b2);
+
 int sm_count();
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

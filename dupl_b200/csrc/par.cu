@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 #include "resample.cuh"
 
 namespace dupl {
@@ -232,6 +233,123 @@ __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_std_kernel(const
     case 3: par_std_gather<3>(A, hw, q0, D); break;
     case 4: par_std_gather<4>(A, hw, q0, D); break;
     case 5: par_std_gather<5>(A, hw, q0, D); break;
+  }
+}
+
+// Same tile kernel with the affinity stream staged by TMA: the per-pixel affinity loads were the exposed latency of
+// par_propagate_std_kernel (ncu: issue slots 45 % busy, L1 hit rate 5 %).  Thread 0 keeps PA_STAGES box loads in flight
+// (3-D tensor map over [B*48][h][w], box = 3 neighbour planes x 16 rows x 32 pixels = 6 KB) behind an mbarrier ring;
+// the gather then reads affinity AND masks from shared memory.  <= 4 planes x 20 KB + 24 KB ring: two CTAs per SM.
+constexpr int PA_CH = 4, PA_NG = 3, PA_STAGES = 4, PA_GROUPS = 48 / PA_NG;
+constexpr int PA_STAGE_FLOATS = PA_NG * PT_H * PT_W;
+constexpr int PA_SMEM_BYTES = (PA_CH * PS_PLANE + PA_STAGES * PA_STAGE_FLOATS) * 4 + PA_STAGES * 8;
+
+template <int NP>
+__device__ __forceinline__ void par_tma_gather(const float* q0, const float* ring, uint64_t* full, const CUtensorMap* tm,
+                                               int x0, int y0, int plane0, int lane, int wid, bool issuer, float* __restrict__ D,
+                                               long hw, bool store) {
+  float acc[NP];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int g = 0; g < PA_GROUPS; ++g) {
+    const int s = g % PA_STAGES;
+    mbar_wait(&full[s], (g / PA_STAGES) & 1);
+    const float* a_s = ring + s * PA_STAGE_FLOATS + wid * PT_W + lane;
+#pragma unroll
+    for (int jj = 0; jj < PA_NG; ++jj) {
+      const int n = g * PA_NG + jj, di = n / 8, j = n % 8;
+      const float a = a_s[jj * PT_H * PT_W];
+      const int off = (ps_dy(j) * ps_dil(di)) * PS_PITCH + ps_dx(j) * ps_dil(di);
+#pragma unroll
+      for (int c = 0; c < NP; ++c) acc[c] = fmaf(a, q0[c * PS_PLANE + off], acc[c]);
+    }
+    if (g + PA_STAGES < PA_GROUPS) {
+      __syncthreads();  // every thread is done with ring stage s
+      if (issuer) {
+        mbar_arrive_expect_tx(&full[s], PA_STAGE_FLOATS * 4);
+        tma_load_3d(const_cast<float*>(ring) + s * PA_STAGE_FLOATS, tm, &full[s], x0, y0, plane0 + (g + PA_STAGES) * PA_NG);
+      }
+    }
+  }
+  if (store) {
+#pragma unroll
+    for (int c = 0; c < NP; ++c) D[c * hw] = acc[c];
+  }
+}
+
+// Persistent: 2 CTAs per SM walk the list of live work items (image, plane chunk, tile).  The number of live planes per
+// image is only known on the device (nactive, written by the refine prologue: no host sync), so a plain grid would have to
+// cover all ceil(P / 4) = 11 chunks of every image and ~85 % of its CTAs would exit at once; scheduling those empty CTAs
+// (each reserving 106 KB of shared memory) cost more than the work itself.
+__global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tma_kernel(const __grid_constant__ CUtensorMap tm_aff,
+                                                                            const float* __restrict__ src,
+                                                                            float* __restrict__ dst,
+                                                                            const int* __restrict__ nactive, int P, int B,
+                                                                            int h, int w, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) float tile[];
+  float* ring = tile + PA_CH * PS_PLANE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + PA_STAGES * PA_STAGE_FLOATS);
+  const long hw = static_cast<long>(h) * w;
+  const bool issuer = threadIdx.x == 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tiles = tiles_x * tiles_y;
+  if (issuer) {
+    for (int s = 0; s < PA_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  int total = 0;
+  for (int i = 0; i < B; ++i) {
+    const int live = nactive != nullptr ? min(__ldg(nactive + i), P) : P;
+    total += ((live + PA_CH - 1) / PA_CH) * tiles;
+  }
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    // decode item -> (image b, plane chunk, tile); every stage of the ring completes an even number of phases per item,
+    // so the barrier parities of par_tma_gather repeat from item to item
+    int b = 0, rem = item, live = 0, chunks = 0;
+    for (; b < B; ++b) {
+      live = nactive != nullptr ? min(__ldg(nactive + b), P) : P;
+      chunks = (live + PA_CH - 1) / PA_CH;
+      if (rem < chunks * tiles) break;
+      rem -= chunks * tiles;
+    }
+    const int chunk = rem / tiles, t = rem - chunk * tiles;
+    const int per = (live + chunks - 1) / chunks;  // balanced split: 6 live planes -> 3 + 3
+    const int p0 = chunk * per;
+    const int np = min(per, live - p0);
+    const int x0 = (t % tiles_x) * PT_W, y0 = (t / tiles_x) * PT_H;
+    if (issuer) {
+      for (int s = 0; s < PA_STAGES; ++s) {
+        mbar_arrive_expect_tx(&full[s], PA_STAGE_FLOATS * 4);
+        tma_load_3d(ring + s * PA_STAGE_FLOATS, &tm_aff, &full[s], x0, y0, b * 48 + s * PA_NG);
+      }
+    }
+    const float* S = src + (static_cast<long>(b) * P + p0) * hw;
+    for (int r = wid; r < PS_ROWS; r += PT_H) {
+      const long row = static_cast<long>(min(max(y0 - PS_HALO + r, 0), h - 1)) * w;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int cx = lane + 32 * k;
+        if (cx < PS_PITCH) {
+          const long o = row + min(max(x0 - PS_HALO + cx, 0), w - 1);
+          for (int c = 0; c < np; ++c) tile[c * PS_PLANE + r * PS_PITCH + cx] = __ldg(S + c * hw + o);
+        }
+      }
+    }
+    __syncthreads();  // tiles staged
+    const int x = x0 + lane, y = y0 + wid;
+    const bool store = x < w && y < h && np > 0;
+    const float* q0 = tile + (wid + PS_HALO) * PS_PITCH + lane + PS_HALO;
+    float* D = dst + (static_cast<long>(b) * P + p0) * hw + static_cast<long>(min(y, h - 1)) * w + min(x, w - 1);
+    switch (np) {
+      case 1: par_tma_gather<1>(q0, ring, full, &tm_aff, x0, y0, b * 48, lane, wid, issuer, D, hw, store); break;
+      case 2: par_tma_gather<2>(q0, ring, full, &tm_aff, x0, y0, b * 48, lane, wid, issuer, D, hw, store); break;
+      case 3: par_tma_gather<3>(q0, ring, full, &tm_aff, x0, y0, b * 48, lane, wid, issuer, D, hw, store); break;
+      default: par_tma_gather<4>(q0, ring, full, &tm_aff, x0, y0, b * 48, lane, wid, issuer, D, hw, store); break;
+    }
+    __syncthreads();  // everyone is done with the tiles and the ring before the next item overwrites them
   }
 }
 
@@ -499,6 +617,28 @@ extern "C" int dupl_par_propagate(const float* aff, float* masks, float* scratch
     dim3 tgrid(cdiv(w, PT_W), cdiv(h, PT_H), B * max_chunks), tblock(PT_W * PT_H);
     float* tsrc = masks;
     float* tdst = scratch;
+    // standard dilations + 16-byte aligned rows: affinity staged by TMA (DUPL_PAR_NO_TMA=1: plain loads, for A/B runs)
+    if (ndil == 6 && g.dil[0] == 1 && g.dil[1] == 2 && g.dil[2] == 4 && g.dil[3] == 8 && g.dil[4] == 12 && g.dil[5] == 24 &&
+        w % 4 == 0 && getenv("DUPL_PAR_NO_TMA") == nullptr && getenv("DUPL_PAR_GENERIC_TILE") == nullptr) {
+      CUtensorMap tm;
+      int rc2 = make_tmap_f32_3d(&tm, aff, w, h, static_cast<uint64_t>(B) * 48, PT_W, PT_H, PA_NG);
+      if (rc2) return rc2;
+      static bool attr_tma = false;
+      if (!attr_tma) {
+        DUPL_CUDA_OK(cudaFuncSetAttribute(par_propagate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM_BYTES));
+        attr_tma = true;
+      }
+      const int tiles_x = cdiv(w, PT_W), tiles_y = cdiv(h, PT_H);
+      const long max_items = static_cast<long>(B) * cdiv(P, PA_CH) * tiles_x * tiles_y;
+      const int ctas = static_cast<int>(max_items < 2L * sm_count() ? max_items : 2L * sm_count());
+      for (int it = 0; it < num_iter; ++it) {
+        par_propagate_tma_kernel<<<ctas, tblock, PA_SMEM_BYTES, st>>>(tm, tsrc, tdst, nactive, P, B, h, w, tiles_x, tiles_y);
+        DUPL_LAUNCH_OK();
+        float* t = tsrc; tsrc = tdst; tdst = t;
+      }
+      if (result_in_scratch_host != nullptr) *result_in_scratch_host = (tsrc == scratch) ? 1 : 0;
+      return DUPL_OK;
+    }
     const bool standard = ndil == 6 && g.dil[0] == 1 && g.dil[1] == 2 && g.dil[2] == 4 && g.dil[3] == 8 && g.dil[4] == 12 &&
                           g.dil[5] == 24 && getenv("DUPL_PAR_GENERIC_TILE") == nullptr;
     if (standard) {

@@ -55,6 +55,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D tiled load (innermost coordinate first).
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // shared::cluster address of `p` (a shared-memory location of the calling CTA) in CTA `rank` of the cluster.
 __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // dres[row] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // partial[blk][0][c] = sum_rows dy * xhat, partial[blk][1][c] = sum_rows dy   (rows of this block)
 // ------------------------------------------------------------------------------------------------
-constexpr int LNB_ROWS = 32;
+constexpr int LNB_ROWS = 16;  // 3140 training rows -> 197 blocks (32 rows gave 99 blocks on 148 SMs)
 template <int V>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, float* __restrict__ dres,

@@ -62,7 +62,7 @@ def colsum(x, R, Cc, tokens=0, np_=0, first=0):
 def layernorm_bwd(dy, x, gamma, dres):
     rows, cols = x.shape
     dev = x.device
-    partial = torch.empty(2 * cols * ((rows + 31) // 32), dtype=torch.float32, device=dev)
+    partial = torch.empty(2 * cols * ((rows + 15) // 16), dtype=torch.float32, device=dev)
     dg, db = torch.empty(cols, dtype=torch.float32, device=dev), torch.empty(cols, dtype=torch.float32, device=dev)
     L.check(L.lib().dupl_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(dres), L.ptr(partial), L.ptr(dg), L.ptr(db),
                                        rows, cols, E.LN_EPS, _st(dev)), "dupl_layernorm_bwd")
