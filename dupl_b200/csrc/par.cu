@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_std_kernel(const
 // the gather then reads affinity AND masks from shared memory.  <= 4 planes x 20 KB + 24 KB ring: two CTAs per SM.
 constexpr int PA_CH = 4, PA_NG = 3, PA_STAGES = 4, PA_GROUPS = 48 / PA_NG;
 constexpr int PA_STAGE_FLOATS = PA_NG * PT_H * PT_W;
-constexpr int PA_SMEM_BYTES = (PA_CH * PS_PLANE + PA_STAGES * PA_STAGE_FLOATS) * 4 + PA_STAGES * 8;
+constexpr int PA_SMEM_BYTES = (PA_CH * PS_PLANE + PA_STAGES * PA_STAGE_FLOATS) * 4 + (PA_STAGES + 1) * 8;
 
 template <int NP>
 __device__ __forceinline__ void par_tma_gather(const float* q0, const float* ring, uint64_t* full, const CUtensorMap* tm,
@@ -280,9 +280,12 @@ __device__ __forceinline__ void par_tma_gather(const float* q0, const float* rin
 
 // Persistent: 2 CTAs per SM walk the list of live work items (image, plane chunk, tile).  The number of live planes per
 // image is only known on the device (nactive, written by the refine prologue: no host sync), so a plain grid would have to
-// cover all ceil(P / 4) = 11 chunks of every image and ~85 % of its CTAs would exit at once; scheduling those empty CTAs
-// (each reserving 106 KB of shared memory) cost more than the work itself.
+// cover all ceil(P / 4) = 11 chunks of every image and ~85 % of its CTAs would exit at once.
+// The mask tiles (+ halo) are TMA box loads as well: out-of-image cells arrive as zeros and only those cells are then
+// overwritten with the replicate-border values by the threads (interior tiles: no staging instructions at all; the
+// register-staged version spent as many instructions on staging as on the gather).
 __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tma_kernel(const __grid_constant__ CUtensorMap tm_aff,
+                                                                            const __grid_constant__ CUtensorMap tm_src,
                                                                             const float* __restrict__ src,
                                                                             float* __restrict__ dst,
                                                                             const int* __restrict__ nactive, int P, int B,
@@ -290,12 +293,14 @@ __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tma_kernel(const
   extern __shared__ __align__(128) float tile[];
   float* ring = tile + PA_CH * PS_PLANE;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + PA_STAGES * PA_STAGE_FLOATS);
+  uint64_t* tile_full = full + PA_STAGES;
   const long hw = static_cast<long>(h) * w;
   const bool issuer = threadIdx.x == 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tiles = tiles_x * tiles_y;
   if (issuer) {
     for (int s = 0; s < PA_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init(tile_full, 1);
     fence_mbar_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -305,9 +310,10 @@ __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tma_kernel(const
     const int live = nactive != nullptr ? min(__ldg(nactive + i), P) : P;
     total += ((live + PA_CH - 1) / PA_CH) * tiles;
   }
+  uint32_t tile_parity = 0;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    // decode item -> (image b, plane chunk, tile); every stage of the ring completes an even number of phases per item,
-    // so the barrier parities of par_tma_gather repeat from item to item
+    // decode item -> (image b, plane chunk, tile); every stage of the affinity ring completes an even number of phases per
+    // item, so the barrier parities of par_tma_gather repeat from item to item
     int b = 0, rem = item, live = 0, chunks = 0;
     for (; b < B; ++b) {
       live = nactive != nullptr ? min(__ldg(nactive + b), P) : P;
@@ -321,24 +327,33 @@ __global__ void __launch_bounds__(PT_W * PT_H, 2) par_propagate_tma_kernel(const
     const int np = min(per, live - p0);
     const int x0 = (t % tiles_x) * PT_W, y0 = (t / tiles_x) * PT_H;
     if (issuer) {
+      mbar_arrive_expect_tx(tile_full, np * PS_PLANE * 4);
+      for (int c = 0; c < np; ++c) tma_load_3d(tile + c * PS_PLANE, &tm_src, tile_full, x0 - PS_HALO, y0 - PS_HALO, b * P + p0 + c);
       for (int s = 0; s < PA_STAGES; ++s) {
         mbar_arrive_expect_tx(&full[s], PA_STAGE_FLOATS * 4);
         tma_load_3d(ring + s * PA_STAGE_FLOATS, &tm_aff, &full[s], x0, y0, b * 48 + s * PA_NG);
       }
     }
-    const float* S = src + (static_cast<long>(b) * P + p0) * hw;
-    for (int r = wid; r < PS_ROWS; r += PT_H) {
-      const long row = static_cast<long>(min(max(y0 - PS_HALO + r, 0), h - 1)) * w;
+    mbar_wait(tile_full, tile_parity);
+    tile_parity ^= 1;
+    // replicate border: cells whose source coordinate lies outside the image (TMA wrote zeros there)
+    if (x0 < PS_HALO || y0 < PS_HALO || x0 + PT_W + PS_HALO > w || y0 + PT_H + PS_HALO > h) {
+      const float* S = src + (static_cast<long>(b) * P + p0) * hw;
+      for (int r = wid; r < PS_ROWS; r += PT_H) {
+        const int sy = y0 - PS_HALO + r;
+        const int gy = min(max(sy, 0), h - 1);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int cx = lane + 32 * k;
-        if (cx < PS_PITCH) {
-          const long o = row + min(max(x0 - PS_HALO + cx, 0), w - 1);
-          for (int c = 0; c < np; ++c) tile[c * PS_PLANE + r * PS_PITCH + cx] = __ldg(S + c * hw + o);
+        for (int k = 0; k < 3; ++k) {
+          const int cx = lane + 32 * k;
+          const int sx = x0 - PS_HALO + cx;
+          if (cx < PS_PITCH && (sy != gy || sx < 0 || sx >= w)) {
+            const long o = static_cast<long>(gy) * w + min(max(sx, 0), w - 1);
+            for (int c = 0; c < np; ++c) tile[c * PS_PLANE + r * PS_PITCH + cx] = __ldg(S + c * hw + o);
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();  // tiles staged
     const int x = x0 + lane, y = y0 + wid;
     const bool store = x < w && y < h && np > 0;
     const float* q0 = tile + (wid + PS_HALO) * PS_PITCH + lane + PS_HALO;
@@ -620,9 +635,11 @@ extern "C" int dupl_par_propagate(const float* aff, float* masks, float* scratch
     // standard dilations + 16-byte aligned rows: affinity staged by TMA (DUPL_PAR_NO_TMA=1: plain loads, for A/B runs)
     if (ndil == 6 && g.dil[0] == 1 && g.dil[1] == 2 && g.dil[2] == 4 && g.dil[3] == 8 && g.dil[4] == 12 && g.dil[5] == 24 &&
         w % 4 == 0 && getenv("DUPL_PAR_NO_TMA") == nullptr && getenv("DUPL_PAR_GENERIC_TILE") == nullptr) {
-      CUtensorMap tm;
+      CUtensorMap tm, tm_a, tm_b;  // affinity; the two mask buffers the iterations ping-pong between
       int rc2 = make_tmap_f32_3d(&tm, aff, w, h, static_cast<uint64_t>(B) * 48, PT_W, PT_H, PA_NG);
       if (rc2) return rc2;
+      if ((rc2 = make_tmap_f32_3d(&tm_a, masks, w, h, static_cast<uint64_t>(B) * P, PS_PITCH, PS_ROWS, 1))) return rc2;
+      if ((rc2 = make_tmap_f32_3d(&tm_b, scratch, w, h, static_cast<uint64_t>(B) * P, PS_PITCH, PS_ROWS, 1))) return rc2;
       static bool attr_tma = false;
       if (!attr_tma) {
         DUPL_CUDA_OK(cudaFuncSetAttribute(par_propagate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM_BYTES));
@@ -632,7 +649,8 @@ extern "C" int dupl_par_propagate(const float* aff, float* masks, float* scratch
       const long max_items = static_cast<long>(B) * cdiv(P, PA_CH) * tiles_x * tiles_y;
       const int ctas = static_cast<int>(max_items < 2L * sm_count() ? max_items : 2L * sm_count());
       for (int it = 0; it < num_iter; ++it) {
-        par_propagate_tma_kernel<<<ctas, tblock, PA_SMEM_BYTES, st>>>(tm, tsrc, tdst, nactive, P, B, h, w, tiles_x, tiles_y);
+        par_propagate_tma_kernel<<<ctas, tblock, PA_SMEM_BYTES, st>>>(tm, tsrc == masks ? tm_a : tm_b, tsrc, tdst, nactive, P, B, h, w,
+                                                                      tiles_x, tiles_y);
         DUPL_LAUNCH_OK();
         float* t = tsrc; tsrc = tdst; tdst = t;
       }
