@@ -61,10 +61,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * BK * 2;  // one plane
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the W tile, one plane
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // per epilogue warp: 32 x 33 fp32 tile for the residual rows
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
 template <int BN, int BK>
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stage_buf = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,8 +208,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       const int m0 = (2 * (r / n_tiles) + rank) * GEMM_BM;
       const int n0 = (r % n_tiles) * BN;
       const GemmGroupDev& G = p.g[g];
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
 
@@ -226,12 +226,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         pos_row = G.pos[si] + static_cast<long>(1 + pidx) * p.N;
       }
 
+      // RESID: the accumulator comes out of TMEM one row per thread, so a thread-per-row read of the residual touches 32
+      // rows (16 B each) per instruction with 8 loads in flight: measured, that read doubled the N = 768, K = 768 launches
+      // (proj 129 us vs 67 us without the residual).  The rows are therefore read with lane = column (32 independent
+      // 128-byte loads per thread in flight) and transposed through a per-warp shared-memory tile.
+      float* stg = stage_buf + (warp - 2) * (32 * 33);
+      const int rows_here = min(32, p.M - (m0 + q * 32));  // warp-uniform; <= 0 when the quadrant is padding
+      float rv[32];  // residual rows of the chunk being fetched (software pipeline: chunk c+1 loads while chunk c is written)
+      auto fetch_resid = [&](int c0n) {
+        const int coln = n0 + c0n;
+        if (coln < p.N && rows_here > 0) {
+          const float* rbase = G.resid + static_cast<long>(m0 + q * 32) * p.ldo + coln + lane;
+          const bool lane_ok = lane < p.N - coln;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) rv[rr] = (rr < rows_here && lane_ok) ? rbase[static_cast<long>(rr) * p.ldo] : 0.0f;
+        }
+      };
+      if (p.epilogue == DUPL_EPI_RESID) fetch_resid(0);  // in flight while the MMAs of this tile finish
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
-        tc_wait_ld();
         const int col0 = n0 + c0;
+        if (p.epilogue == DUPL_EPI_RESID) {
+          __syncwarp();
+          if (col0 < p.N && rows_here > 0) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) stg[rr * 33 + lane] = rv[rr];
+          }
+          __syncwarp();
+          if (c0 + 32 < BN) fetch_resid(c0 + 32);
+        }
+        tc_wait_ld();
         if (row_ok && col0 < p.N) {
           float f[32];
 #pragma unroll
@@ -247,13 +275,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           if (p.epilogue == DUPL_EPI_F32 || p.epilogue == DUPL_EPI_RESID || p.epilogue == DUPL_EPI_PATCH) {
             float* o = G.out_f32 + (static_cast<long>(ks) * p.M + out_row) * p.ldo + col0;
             const float* add = nullptr;
-            if (p.epilogue == DUPL_EPI_RESID) add = G.resid + static_cast<long>(row) * p.ldo + col0;
             if (p.epilogue == DUPL_EPI_PATCH) add = pos_row + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (j < ncols) {
                 float4 o4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (add != nullptr) {
+                if (p.epilogue == DUPL_EPI_RESID) {
+                  const float* sr = stg + lane * 33 + j;
+                  o4.x += sr[0]; o4.y += sr[1]; o4.z += sr[2]; o4.w += sr[3];
+                } else if (add != nullptr) {
                   const float4 a4 = *reinterpret_cast<const float4*>(add + j);
                   o4.x += a4.x; o4.y += a4.y; o4.z += a4.z; o4.w += a4.w;
                 }

@@ -348,6 +348,9 @@ class TrainStep:
         self._sched = (st["omc"], st["done"])
         try:
             if first:
+                # the warm-up runs on a side stream on purpose: torch's stream-mismatch warning for AccumulateGrad nodes is noise here
+                if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
                 # warm-up outside capture (lazy caches, optimizer state tensors, allocator pools); parameters, optimizer
                 # state and schedule are put back afterwards, so the first captured call is ONE training step like any other
                 params = [p for g in self.optim.param_groups for p in g["params"]]
