@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from .gmm import gmm_noise_filter
-from .model.losses import get_masked_ptc_loss, get_seg_loss_upsampled
+from .model.losses import ce_sum_upsampled, get_masked_ptc_loss, get_seg_loss_upsampled
 from .model.PAR import PAR
 from .pipeline import CamParStep, denormalize_img2
 from .utils import cam_helper
@@ -283,10 +283,9 @@ class TrainStep:
                         conf, pseudo_seg = torch.softmax(up, dim=1).max(1)
                         uncertain = (other_label == a.ignore_index) & (conf > 0.9)
                         target = torch.where(uncertain, pseudo_seg, torch.full_like(pseudo_seg, a.ignore_index))
-                    aug_up = F.interpolate(torch.flip(aug, dims=[3]), size=size, mode="bilinear", align_corners=False)
-                    ce = F.cross_entropy(aug_up, target, ignore_index=a.ignore_index, reduction="none")
-                    # `if uncertain.sum() > 0` of the script without the host sync: an empty mask gives 0 / 1 = 0
-                    regs.append(ce.sum() / uncertain.sum().clamp_min(1))
+                    # F.interpolate + ce_criterion(...).sum() / uncertain.sum() fused; `if uncertain.sum() > 0` of the script
+                    # without the host sync: an empty mask gives 0 / 1 = 0
+                    regs.append(ce_sum_upsampled(torch.flip(aug, dims=[3]), target, a.ignore_index))
                 reg_loss = regs[0] + regs[1]
 
         f1 = fmap_1.view(fmap_1.shape[0], fmap_1.shape[1], -1)

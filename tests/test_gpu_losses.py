@@ -112,3 +112,27 @@ def test_ptc_tensor_core_path_agrees_with_the_fp32_simt_path():
         outs.append((loss.item(), f.grad.clone()))
     assert abs(outs[0][0] - outs[1][0]) < 2e-6
     assert rel_err(outs[0][1], outs[1][1]) < 1e-4
+
+
+@pytest.mark.parametrize("b,C,h,w,H,W,frac", [(2, 21, 21, 21, 448, 448, 0.3), (1, 81, 14, 14, 224, 224, 0.05), (2, 21, 7, 9, 64, 80, 0.0)])
+def test_consistency_ce_sum_upsampled_matches_torch(b, C, h, w, H, W, frac):
+    """ce_criterion(F.interpolate(aug), pseudo_seg).sum() / mask.sum() of train_final_voc.py:407-436 (0 for an empty mask)."""
+    import torch.nn.functional as F
+    from dupl_b200.model.losses import ce_sum_upsampled
+    g = torch.Generator().manual_seed(C + h)
+    pred = torch.randn(b, C, h, w, generator=g) * 3
+    target = torch.randint(0, C, (b, H, W), generator=g)
+    target[torch.rand(b, H, W, generator=g) >= frac] = 255
+    p_ref = pred.clone().requires_grad_(True)
+    up = F.interpolate(p_ref, size=(H, W), mode="bilinear", align_corners=False)
+    n = (target != 255).sum()
+    want = F.cross_entropy(up, target, ignore_index=255, reduction="none").sum() / n if n > 0 else up.sum() * 0.0
+    (want * 0.05).backward()
+    p_gpu = pred.cuda().requires_grad_(True)
+    got = ce_sum_upsampled(p_gpu, target.cuda(), 255)
+    (got * 0.05).backward()
+    assert abs(got.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    if n > 0:
+        assert rel_err(p_gpu.grad, p_ref.grad) < 1e-4
+    else:
+        assert torch.count_nonzero(p_gpu.grad) == 0
