@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .utils import cam_helper
 from .utils.dcrf import DenseCRF
+from .utils.evaluate import ConfusionMatrix
 
 
 def shard_indices(n_items, rank, world):
@@ -118,3 +119,20 @@ class SegCrfSweep:
             out["crf_pred"].append(self.crf_prob(images_u8[i], seg[i:i + 1]).argmax(0))
         out["cam_label"] = self.cam_label(inputs, cls_label, label_size, branch)
         return out
+
+    @torch.no_grad()
+    def validate(self, samples, num_classes, rank=0, world=1, branch=1):
+        """validate_siamase(_coco) + crf_proc over a list of samples (utils/train_helper.py:90-283, tools/eval_seg_*.py): every
+        rank takes images rank, rank + world, ... (tools/eval_seg_coco_ddp.py:241), accumulates three confusion matrices on
+        its device (seg arg-max, CRF arg-max, CAM pseudo-labels) and ONE C x C all-reduce per matrix merges them.
+        samples[i] = (image_u8 [H,W,3] uint8, inputs [1,3,h,w] normalised, cls_label [1,K], label [H,W] int).
+        Returns {"seg": scores, "crf": scores, "cam": scores} (utils/evaluate.py:17-60 semantics)."""
+        dev = next(self.model.parameters()).device
+        cms = {k: ConfusionMatrix(num_classes, dev) for k in ("seg", "crf", "cam")}
+        for i in shard_indices(len(samples), rank, world):
+            img, x, cls, gt = (t.to(dev, non_blocking=True) for t in samples[i])
+            out = self([img], x, cls, branch=branch)
+            cms["seg"].update(gt, out["seg_pred"][0])
+            cms["crf"].update(gt, out["crf_pred"][0])
+            cms["cam"].update(gt, out["cam_label"][0], pseudo=True)
+        return {k: cm.all_reduce().scores() for k, cm in cms.items()}

@@ -68,3 +68,27 @@ def test_sweep_call_returns_device_label_maps():
         assert a.shape == b.shape == (64, 64) and a.is_cuda and b.dtype == torch.int64
         assert int(a.max()) <= 20 and int(b.max()) <= 20
     assert out["cam_label"].shape == (2, 64, 64) and out["cam_label"].dtype == torch.int64
+
+
+def test_validate_accumulates_device_side_confusion_matrices():
+    """validate_siamase + crf_proc as one sharded sweep: scores equal utils/evaluate.py applied to the per-image outputs."""
+    from dupl_b200.eval_sweep import SegCrfSweep
+    from dupl_b200.utils import evaluate
+    m, _ = _model(21)
+    sweep = SegCrfSweep(m, flavour="coco", crop_size=64)
+    samples, segs, crfs, gts = [], [], [], []
+    g = torch.Generator().manual_seed(9)
+    for i in range(3):
+        x = synth_images(1, 64, 64, seed=40 + i)
+        gt = torch.randint(0, 21, (64, 64), generator=g)
+        gt[torch.rand(64, 64, generator=g) < 0.1] = 255
+        samples.append((_u8_image(x), x, synth_cls_labels(1, 20, seed=40 + i), gt))
+    got = sweep.validate(samples, 21)
+    for img, x, cls, gt in samples:
+        out = sweep([img.cuda()], x.cuda(), cls.cuda(), branch=1)
+        segs.append(out["seg_pred"][0].cpu().numpy())
+        crfs.append(out["crf_pred"][0].cpu().numpy())
+        gts.append(gt.numpy())
+    assert got["seg"]["miou"] == evaluate.scores(gts, segs, 21)["miou"]
+    assert got["crf"]["pAcc"] == evaluate.scores(gts, crfs, 21)["pAcc"]
+    assert set(got) == {"seg", "crf", "cam"}
