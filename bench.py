@@ -303,9 +303,11 @@ def gemm_roofline(timer, peaks, peak_kind, step_tflops, timed_in):
             # ncu --set full capture of this command, profiles/r01_summary.md
             "traffic": TRAFFIC_GEMM_BYTES,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})",
+            "issued_tflops": 3.0 * achieved, "frac_issued": 3.0 * achieved / peak_tf if peak_tf else None,
             "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "timed_in": timed_in,
             "note": "achieved = algorithmic fp32-GEMM FLOPs (2MNK) / CUDA-event time; the kernel issues 3 bf16 MMAs per "
-                    "product (split operands), so the tensor pipe does 3x this figure and frac is capped at 1/3",
+                    "product (split operands: the 1e-3 fp32 parity bar rules out single-pass bf16/fp16/tf32, DESIGN.md section 2), so the "
+                    "tensor pipe does 3x this figure (issued_tflops / frac_issued) and frac is capped at 1/3",
             "step_tflops": step_tflops}
 
 
