@@ -653,7 +653,8 @@ def main():
     ap.add_argument("--phase", default="B", choices=["B", "C"], help="train workload: B = CAM+PAR+seg (default), C = + aug view, GMM filter, consistency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="cam_par: skip the secondary training-step measurement")
-    ap.add_argument("--fuse-students", action="store_true", help="both students per grouped GEMM launch")
+    ap.add_argument("--no-fuse-students", dest="fuse_students", action="store_false",
+                    help="one encoder pass per student instead of both students per grouped GEMM launch")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
     args = ap.parse_args()

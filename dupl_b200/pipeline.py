@@ -27,13 +27,15 @@ class CamParStep:
     """multi_scale_cam2_siamese for both students + refine_cams_with_dynamic_thres for both students."""
 
     def __init__(self, model, cam_scales=(1.0, 0.5, 1.5), low_thre=0.25, ignore_index=255,
-                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=False, graph=False, keep_activations=False,
+                 dilations=(1, 2, 4, 8, 12, 24), num_iter=10, fuse_students=True, graph=False, keep_activations=False,
                  refine="dynamic", scalar_high_thre=None):
         self.model = model
         self.scales = tuple(cam_scales)
         self.low_thre = low_thre
         self.ignore_index = ignore_index
         self.par = PAR(num_iter=num_iter, dilations=list(dilations))  # train_final_voc.py:160
+        # both students per grouped GEMM launch (one encoder pass over [student][segment] groups): 3 % faster than two passes
+        # on B200 (402 vs 376 TFLOP/s over the GEMM launches: twice the tiles per launch fill the 74 CTA pairs better)
         self.fuse_students = fuse_students
         self.graph = graph      # replay the whole step as ONE CUDA graph (the ~220 launches cost the host nothing)
         # keep the encoder activations of the un-flipped scale-1.0 images on each student (network._kept) so that the
