@@ -333,10 +333,12 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     model, P = build_model(K, h.dev, train=True)
     # one process per model: the whole iteration is one CUDA graph (DUPL_TRAIN_CAPTURE=0 switches it off); under DDP the
     # reducer's hooks need the eager autograd pass
-    capture = h.world == 1 and os.environ.get("DUPL_TRAIN_CAPTURE", "1") != "0"
+    # with several ranks the captured step all-reduces the flattened gradients itself (one NCCL call inside the graph);
+    # DUPL_TRAIN_CAPTURE=0 or DUPL_TRAIN_CAPTURE_DDP=0 fall back to the eager autograd half under DistributedDataParallel
+    capture = os.environ.get("DUPL_TRAIN_CAPTURE", "1") != "0" and (h.world == 1 or os.environ.get("DUPL_TRAIN_CAPTURE_DDP", "1") == "1")
     optim = make_optimizer(model, capturable=capture)
     wrapped = model
-    if h.world > 1:
+    if h.world > 1 and not capture:
         # train_final_voc.py:155 wraps with find_unused_parameters=True (encoder.head.* never receives a gradient).  The
         # fused driver knows the graph is the same every step: static_graph lets the reducer skip the per-step traversal,
         # bucket views avoid the copy back.  DUPL_DDP=reference restores the script's exact construction for A/B runs.
@@ -383,19 +385,32 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
                inputs=(x, cls, box), n_iter=it[0])
     timer = None
     if want_roofline:
-        eager = PhaseBStep(wrapped, make_optimizer(model) if capture else optim, args=targs, device=h.dev, graph=False)
-        eager(x_dev, cls_dev, box, it[0], aug_dev)
+        eager = PhaseBStep(wrapped, None, args=targs, device=h.dev, graph=False)
+
+        def eager_iter():   # losses + backward launched kernel by kernel; no optimizer step (the parameters stay as they are)
+            model.zero_grad(set_to_none=True)
+            loss, _, _ = eager.losses(x_dev, cls_dev, box, it[0], aug_dev)
+            loss.backward()
+
+        eager_iter()
         launches0 = L.lib().dupl_launch_count()
         with GemmTimer(h.stream) as timer:
             h.barrier()
             for _ in range(steps):
-                eager(x_dev, cls_dev, box, it[0], aug_dev)
+                eager_iter()
             h.barrier()
         out["launches"] = int(L.lib().dupl_launch_count() - launches0)
     e2e_step()
     out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps
     out["timer"] = timer
     out["capture"] = capture
+    # replicas must hold bit-identical parameters after the run (same updates on every rank)
+    chk = torch.stack([p.detach().double().sum() for p in list(model.parameters())[:64]]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    if h.dist is not None:
+        h.dist.all_reduce(lo, op=h.dist.ReduceOp.MIN)
+        h.dist.all_reduce(hi, op=h.dist.ReduceOp.MAX)
+    out["ranks_in_sync"] = bool((lo == hi).item())
     out["loss"] = float(last["loss"].item())
     out["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
     return out
@@ -492,8 +507,9 @@ def run_cam_par(h, args):
         train = {"metric": "train_images_per_sec", "value": imgs / (tms / 1000.0), "unit": UNIT, "ms_per_step": tms,
                  "e2e": {"value": imgs / (te2e / 1000.0), "unit": UNIT, "ms_per_step": te2e},
                  "workload": "voc21_dual_student_phaseB_step_448_bs4 (MS-CAM + PAR labels + fwd/bwd of both students + losses + AdamW"
-                             + (", DDP all-reduce)" if h.world > 1 else ")"),
-                 "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2)}
+                             + (", gradient all-reduce over NCCL)" if h.world > 1 else ")"),
+                 "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2), "ranks_in_sync": t["ranks_in_sync"],
+                 "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half"}
 
     if h.rank == 0:
         peaks, peak_kind = load_peaks()
@@ -542,13 +558,15 @@ def run_train(h, args):
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"{args.dataset}{K + 1}_dual_student_phase{args.phase}_step_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
                        "n_iter": t["n_iter"],
-                       "classes": K + 1, "parallelism": f"ddp{h.world} (NCCL all-reduce of 732.7 MB fp32 grads per step)" if h.world > 1 else "single GPU",
+                       "classes": K + 1, "parallelism": (f"dp{h.world} (one NCCL all-reduce of the 732.7 MB fp32 gradients per step, " +
+                                       ("inside the captured graph)" if t.get("capture") else "DistributedDataParallel reducer)")) if h.world > 1 else "single GPU",
                        "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush",
                        "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images",
                        "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half only (DDP reducer needs eager autograd)"},
             "e2e": {"value": imgs / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
                     "ms_per_step": e2e_ms},
             "gpu_launches": t.get("launches"), "clocks": clocks, "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
+            "ranks_in_sync": t["ranks_in_sync"],
             "roofline": gemm_roofline(t["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_TRAIN * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
                                       "the same K steps with the CAM half launched eagerly (no graph) right after the timed region"),
         }

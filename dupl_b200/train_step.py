@@ -164,7 +164,8 @@ class TrainStep:
     def __init__(self, model, optim=None, args=Args, device=None, graph=True, reuse_forward=True, capture=False):
         """capture=True: the WHOLE iteration (MS-CAM, PAR, forward heads, losses, backward, AdamW) is captured once per phase
         as one CUDA graph and replayed; ~1500 kernel launches per step otherwise keep the host as busy as the GPU.  Needs a
-        capturable optimizer (make_optimizer(..., capturable=True)) and a single process per model (no DDP reducer)."""
+        capturable optimizer (make_optimizer(..., capturable=True)) and the bare model: with several ranks the gradients are
+        averaged by one NCCL all-reduce inside the graph instead of by DistributedDataParallel's hooks."""
         self.model = model          # siamese_network or DistributedDataParallel(siamese_network)
         self.optim = optim
         self.args = args
@@ -306,6 +307,23 @@ class TrainStep:
         self.optim.step()
         return loss.detach(), {k: v.detach() for k, v in parts.items()}
 
+    # ------------------------------------------------------------------ data parallel without the DDP reducer
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _all_reduce_grads(self):
+        """train_final_voc.py:155,470: DistributedDataParallel averages the gradients over the ranks.  Same result here with ONE
+        NCCL all-reduce of the flattened gradients (732.7 MB fp32), issued on the current stream so that it can be captured
+        into the iteration's CUDA graph.  Every rank starts from the same parameters (same seed, as in the script)."""
+        import torch.distributed as dist
+        grads = [p.grad for g in self.optim.param_groups for p in g["params"] if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
     # ------------------------------------------------------------------ whole-iteration CUDA graph
     def _phase_key(self, n_iter, inputs, cls_label, inputs_aug):
         a = self.args
@@ -327,7 +345,8 @@ class TrainStep:
 
     def _replay(self, inputs, cls_label, img_box, n_iter, inputs_aug):
         if hasattr(self.model, "module"):
-            raise RuntimeError("TrainStep(capture=True) drives one process per model; use capture=False under DistributedDataParallel")
+            raise RuntimeError("TrainStep(capture=True) takes the bare siamese_network: with several ranks it all-reduces the "
+                               "gradients itself inside the graph (DistributedDataParallel's hooks need the eager autograd pass)")
         dev = inputs.device
         key = self._phase_key(n_iter, inputs, cls_label, inputs_aug)
         st = self._graphs.get(key)
@@ -363,6 +382,8 @@ class TrainStep:
                         loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
                         self.optim.zero_grad(set_to_none=True)
                         loss.backward()
+                        if self._world() > 1:
+                            self._all_reduce_grads()
                         self.optim.step_captured()
                     with torch.no_grad():
                         for p, q in zip(params, saved_p):
@@ -379,9 +400,12 @@ class TrainStep:
                 del saved_p, saved_s
                 self.optim.zero_grad(set_to_none=True)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                multi = self._world() > 1
+                with torch.cuda.graph(graph, **(dict(capture_error_mode="thread_local") if multi else {})):
                     loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
                     loss.backward()
+                    if multi:
+                        self._all_reduce_grads()
                     self.optim.step_captured()
                 st["graph"], st["loss"], st["parts"] = graph, loss.detach(), {k: v.detach() for k, v in parts.items()}
             self.optim.advance_schedule()

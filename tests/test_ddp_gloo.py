@@ -58,3 +58,43 @@ def test_student_function_under_ddp_world_size_2():
         mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
         assert out[0][0] and out[1][0], dict(out)
         assert out[0][1:] == out[1][1:]  # identical averaged gradients on both ranks
+
+
+def _worker_allreduce(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dupl_b200.train_step import TrainStep
+    ps = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    ps[0].grad = torch.full((3, 5), float(rank + 1))
+    ps[1].grad = torch.arange(7.0) * (rank + 1)
+    # ps[2] never received a gradient (like encoder.head.*): it must be skipped, not break the flattening
+
+    class _Opt:
+        param_groups = [{"params": ps[:2]}, {"params": ps[2:]}]
+
+    step = TrainStep.__new__(TrainStep)
+    step.optim = _Opt()
+    orig = dist.all_reduce
+
+    def avg_all_reduce(t, op=None):           # gloo has no AVG: emulate it (NCCL provides it natively)
+        orig(t, op=dist.ReduceOp.SUM)
+        t.div_(world)
+    dist.all_reduce = avg_all_reduce
+    step._all_reduce_grads()
+    out[rank] = (ps[0].grad.tolist(), ps[1].grad.tolist(), ps[2].grad is None)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_in_graph_gradient_all_reduce_averages_over_ranks():
+    """TrainStep._all_reduce_grads (what the captured multi-rank step does instead of DDP's reducer): mean over ranks,
+    parameters without a gradient are skipped."""
+    port = 29900 + os.getpid() % 90
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_allreduce, args=(2, port, out), nprocs=2, join=True)
+        assert out[0] == out[1]
+        g0, g1, none2 = out[0]
+        assert none2 and all(abs(v - 1.5) < 1e-6 for row in g0 for v in row)
+        assert all(abs(v - 1.5 * i) < 1e-6 for i, v in enumerate(g1))
