@@ -413,6 +413,20 @@ static void choose_tiling(int M, int N, int k_blocks, int groups, int max_split,
 
 }  // namespace dupl
 
+extern "C" int dupl_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t groups, int32_t max_ksplit, int32_t* tile_n,
+                              int32_t* ksplit, int32_t* work_items) {
+  using namespace dupl;
+  DUPL_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 64 == 0 && groups >= 1 && tile_n && ksplit && work_items,
+                 "dupl_gemm_plan: bad arguments");
+  int bn, ks = 1, kper = K / 64;
+  if (N < 256) bn = (N > 64) ? 128 : 64;
+  else choose_tiling(M, N, K / 64, groups, max_ksplit > 1 ? max_ksplit : 1, true, bn, ks, kper);
+  *tile_n = bn;
+  *ksplit = ks;
+  *work_items = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, bn) * groups * ks;
+  return DUPL_OK;
+}
+
 extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   using namespace dupl;
   DUPL_CHECK_ARG(a != nullptr, "dupl_gemm_bf16x3: args is NULL");

@@ -108,6 +108,10 @@ typedef struct {
 } dupl_gemm_args;
 
 int dupl_gemm_bf16x3(const dupl_gemm_args* args, void* stream);
+/* Host-only: the tile width (columns per CTA pair), split-K factor and number of work items dupl_gemm_bf16x3 would use for
+ * this shape on the current device (148 SMs assumed without a device).  No launch. */
+int dupl_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t groups, int32_t max_ksplit, int32_t* tile_n, int32_t* ksplit,
+                   int32_t* work_items);
 
 /* LayerNorm over the last dim (biased variance, eps inside the sqrt; vit.py:146,152,256 with
  * eps=1e-6 from deit.py:100) of x[rows, cols] -> split bf16 planes and/or fp32 (either output may be

@@ -105,3 +105,27 @@ def test_eval_sweep_shards_images_like_the_reference_tool():
         parts = [shard_indices(n, r, world) for r in range(world)]
         assert sorted(i for p in parts for i in p) == list(range(n))
         assert all(p == list(range(r, n, world)) for r, p in enumerate(parts))
+
+
+def test_gemm_plan_fills_the_74_cta_pairs_for_the_training_shapes():
+    """Host-side tiling choice (no GPU needed): 148 SMs = 74 CTA pairs; the M = 3140 training shapes must not be left on a
+    fraction of them, wgrad shapes (few output tiles, K = 3200) must split K, the big MS-CAM shapes keep 256-wide tiles."""
+    import ctypes as C
+    from dupl_b200 import _lib as L
+
+    def plan(M, N, K, groups=1, max_ksplit=0):
+        bn, ks, items = C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(L.lib().dupl_gemm_plan(M, N, K, groups, max_ksplit, C.byref(bn), C.byref(ks), C.byref(items)), "dupl_gemm_plan")
+        return bn.value, ks.value, items.value
+
+    assert plan(21976, 3072, 768)[:2] == (256, 1)               # fc1 of the MS-CAM pass: 1032 tiles, 14 waves
+    bn, ks, items = plan(3140, 768, 768)                          # proj of the training pass: 39 tiles of 256 would use 53 %
+    assert bn < 256 and ks == 1 and items > 39
+    bn, ks, items = plan(768, 768, 3200, max_ksplit=8)            # wgrad of proj: 9 output tiles
+    assert ks > 1 and 37 <= items <= 148
+    assert plan(768, 768, 3200, max_ksplit=0)[1] == 1             # split-K only when a workspace was offered
+    bn, ks, items = plan(3072, 768, 3200, max_ksplit=8)           # wgrad of fc1
+    assert items >= 70
+    assert plan(200, 32, 768)[0] == 64 and plan(260, 128, 256)[0] == 128   # narrow heads keep the narrow instantiations
+    with __import__("pytest").raises(RuntimeError):
+        plan(16, 16, 60)
