@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""Benchmarks of the DuPL hot path on B200 (BASELINE.json configs).
+"""Benchmarks of the DuPL hot path on B200 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cam_par|train|crf_sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload train|cam_par|crf_sweep]
 
-Workloads ("step" = one pass of the path over one synthetic batch):
-  cam_par    (default; BASELINE.json configs[1]) VOC, b=4 per GPU, 448x448: multi_scale_cam2_siamese (scales 1.0/0.5/1.5 +
-             flip) for both students, then refine_cams_with_dynamic_thres (PAR, 10 iterations, 48 neighbours) for both.
-             The line also carries `train_step`: the full dual-student training step measured in the same run.
-  train      (configs[2]/[3]) the full phase-B training step (MS-CAM + PAR pseudo-labels + both students'
-             forward/backward + all losses + AdamW); DDP over NCCL when launched under torchrun.  --dataset voc|coco.
-  crf_sweep  (configs[4]) COCO eval sweep per image: MS-CAM labels (one student) + multi-scale/flip seg logits (both
-             students) + DenseCRF mean-field (10 iterations, 640x480x81) on the GPU; images strided over ranks.
-Prints ONE JSON line on rank 0 (contract in the task statement; keys explained in DESIGN.md §Measurement).
+BASELINE.json's metric is "train images/sec (dual-student step) at 1/2/4/8 B200; CAM+PAR+CRF ms/img".  The default
+workload is therefore `train`: the full phase-B dual-student step (train_final_voc.py:186-472: MS-CAM of both students,
+PAR pseudo-labels, forward / backward of both students with all losses, gradient average over the ranks, AdamW) on a
+synthetic VOC batch, b = 4 per GPU, 448x448.  Its line carries `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches` and three secondary objects measured in the same run (rank 0, N = 1 only for the last two):
+  `cam_par`        BASELINE.json configs[1]: MS-CAM + PAR refine of both students (images/s, ms/img, HBM-roofline fractions
+                   of the PAR propagation and MS-CAM post-processing kernels);
+  `crf`            DenseCRF mean-field ms/img at 640x480x81, T = 10, device-resident and through the numpy API, next to the
+                   1-thread C restatement of pydensecrf;
+  `reference_gpu`  the UNMODIFIED reference (baseline/_ref, its own modules on stock PyTorch: fp32, cudnn.deterministic)
+                   executing the same loop body on the same GPU and batch — the north_star's ">= 5x" comparator.
+Other workloads: `cam_par` alone, `crf_sweep` (configs[4]: COCO eval sweep per image, images strided over ranks),
+`--dataset coco`, `--phase C`.
+
+`--impl reference` times the reference's CPU path on the host cores (the unmodified reference from baseline/_ref when it
+is there, else the oracle port), one 448x448 image per step, all host threads; rank 0 only under torchrun.  On a box with
+a GPU its line also carries `reference_gpu`.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -100,7 +108,7 @@ class ClockSampler:
         return out
 
 
-# ======================================================================================= CPU arms (oracle port)
+# ======================================================================================= CPU arms / reference arms
 def cpu_cam_par(P, x, cls, box, thr, n_images, students=(1, 2)):
     """cam_par on the host cores through the CPU oracle (reference restatement), on `n_images` images.  Seconds."""
     from oracle import dupl_oracle as O
@@ -116,17 +124,79 @@ def cpu_cam_par(P, x, cls, box, thr, n_images, students=(1, 2)):
     return time.perf_counter() - t0
 
 
-def cpu_train(P, x, cls, box, size):
-    """one image of the phase-B step (losses + backward) through the CPU oracle at a reduced resolution `size`
-    (the full 448^2 step costs minutes per image on the host).  Seconds."""
-    from oracle import dupl_oracle as O
-    xs = torch.nn.functional.interpolate(x[:1], size=(size, size), mode="bilinear", align_corners=False)
-    bx = torch.tensor([[0, size, 0, size]], dtype=torch.int16)
-    Pg = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
-    t0 = time.perf_counter()
-    loss, _, _ = O.phase_b_losses(Pg, xs, cls[:1], bx, 3000)
-    loss.backward()
-    return time.perf_counter() - t0
+def reference_available():
+    try:
+        from baseline import compat
+        return compat.available()
+    except Exception:
+        return False
+
+
+class CpuTrainArm:
+    """The phase-B step on the host cores, ONE 448x448 image per step (b = 1; both students, MS-CAM + PAR labels + losses +
+    backward + AdamW): the unmodified reference's own modules from baseline/_ref (kind "reference") when that tree is
+    present, else the oracle port (kind "port": losses + backward, no optimizer)."""
+
+    def __init__(self, P, K):
+        self.K = K
+        self.kind = "reference" if (reference_available() and K == 20) else "port"
+        if self.kind == "reference":
+            from baseline.ref_step import ReferenceStep
+            self.step = ReferenceStep(torch.device("cpu"), state_dict=P, samples_per_gpu=1)
+            self.sample = ("1 image per step (b=1, 448x448) through the unmodified reference loop body on CPU: MS-CAM x2 students, PAR "
+                           "refine, fwd/bwd of both students, all losses, AdamW (baseline/ref_step.py over baseline/_ref)")
+        else:
+            self.P = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+            self.sample = ("1 image per step (b=1, 448x448) through the oracle port (oracle/dupl_oracle.py train_losses + backward; "
+                           "no optimizer step)")
+
+    def __call__(self, x, cls, box, n_iter):
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.step(x[:1], cls[:1], box[:1], n_iter)
+        else:
+            from oracle import dupl_oracle as O
+            for v in self.P.values():
+                v.grad = None
+            cfg = O.VOC_CFG if self.K == 20 else O.COCO_CFG
+            loss, _, _ = O.train_losses(self.P, x[:1], cls[:1], box[:1], n_iter, cfg)
+            loss.backward()
+        return time.perf_counter() - t0
+
+
+def measure_reference_gpu(dev, P, x, cls, box, n_iter, steps, warmup, local_rank=0, ddp=False, strong_aug=False):
+    """The unmodified reference on the GPU (stock PyTorch, fp32, cudnn.benchmark=False / deterministic=True as
+    train_final_voc.py:95-102), same batch, same loop body, CUDA-event timed.  -> dict or None when baseline/_ref is absent."""
+    if not reference_available():
+        return None
+    from baseline.ref_step import ReferenceStep
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    step = ReferenceStep(dev, state_dict=P, samples_per_gpu=x.shape[0], ddp=ddp, local_rank=local_rank, strong_aug=strong_aug)
+    it = n_iter
+    for _ in range(warmup):
+        step(x, cls, box, it)
+        it += 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss, parts = step(x, cls, box, it)
+        it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - w0) * 1000.0 / steps
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": x.shape[0] / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "wall_ms_per_step": wall, "steps": steps,
+           "warmup": warmup, "loss": float(loss), "torch": torch.__version__,
+           "what": "UNMODIFIED reference modules (baseline/_ref: model_dupl, cam_helper, PAR, losses, optimizer) on stock PyTorch, "
+                   "loop body of train_final_voc.py:186-472 incl. its host syncs, AdamW; fp32 matmul "
+                   f"(allow_tf32 matmul={tf32[0]}, cudnn={tf32[1]}: torch defaults, as the script leaves them), cudnn.deterministic; "
+                   + ("with" if strong_aug else "without") + " the PIL RandAugment round trip (:191)",
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+    del step
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_crf(img_u8, prob, iters=10):
@@ -152,37 +222,65 @@ def normalise_u8(img_u8):
     return x
 
 
+def train_workload(dataset, K, phase):
+    return f"{dataset}{K + 1}_dual_student_phase{phase}_step_448_bs4"
+
+
+def train_n_iter(K, phase_c):
+    from dupl_b200.train_step import Args
+    targs = Args if K == 20 else Args.coco()
+    if phase_c:
+        return targs.gmm_iters + 1000
+    return 20000 if K == 80 else (targs.cam_iters + targs.gmm_iters) // 2
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The reference is pure Python/PyTorch (no compiled code of its own)
-    and /root/reference does not exist on the GPU box, so its CPU restatement (oracle/, pinned against the reference
-    in tests/) is timed with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (one process, all threads;
+    rank 0 alone under torchrun).  /root/reference does not exist on the GPU box: the unmodified tree travels as
+    baseline/_ref (baseline/install_ref.sh); without it the CPU restatement in oracle/ is timed instead."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from helpers import init_state_dict
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)                       # torchrun exports OMP_NUM_THREADS=1
     K = 80 if (args.dataset == "coco" or args.workload == "crf_sweep") else 20
     cores = torch.get_num_threads()
     times = []
+    extra = {}
+    kind = "port"
     if args.workload == "cam_par":
         P = init_state_dict(K + 1)
         x, cls, box, thr = make_inputs(0, K)
-        sample = "1 of 4 images; MS-CAM + PAR refine for student 1, time doubled for the two students"
+        sample = "1 of 4 images per step; MS-CAM + PAR refine for both students through the oracle port"
         for i in range(args.warmup + args.steps):
-            t = cpu_cam_par(P, x, cls, box, thr, 1, students=(1,)) * 2.0
+            t = cpu_cam_par(P, x, cls, box, thr, 1)
             if i >= args.warmup:
                 times.append(t)
-        metric, workload = "cam_par_refine_images_per_sec", "voc21_dual_student_cam_par_refine_448_bs4"
+        metric, config, imgs = "cam_par_refine_images_per_sec", {"workload": "voc21_dual_student_cam_par_refine_448_bs4"}, 1.0
     elif args.workload == "train":
         P = init_state_dict(K + 1)
         x, cls, box, thr = make_inputs(0, K)
-        size = 224
-        sample = (f"1 image at {size}x{size} (full phase-B losses + backward of both students), time scaled by the "
-                  f"algorithmic FLOP ratio of 448^2 to {size}^2 (x4.47)")
-        for i in range(args.warmup + args.steps):
-            t = cpu_train(P, x, cls, box, size) * 4.47
-            if i >= args.warmup:
-                times.append(t)
-        metric, workload = "train_images_per_sec", f"{args.dataset}_dual_student_phaseB_step_448_bs4"
+        if K == 80:
+            cls = cls.to(torch.uint8)
+        arm = CpuTrainArm(P, K)
+        kind, sample = arm.kind, arm.sample
+        n_iter = train_n_iter(K, False)
+        xs = torch.nn.functional.interpolate(x, size=(64, 64), mode="bilinear", align_corners=False)
+        bs = torch.tensor([[0, 64, 0, 64]] * x.shape[0], dtype=torch.int16)
+        for i in range(args.warmup):                  # warm-up = thread pools / allocator only: tiny images, untimed
+            arm(xs, cls, bs, n_iter)
+        for i in range(args.steps):
+            times.append(arm(x, cls, box, n_iter + i))
+        metric, imgs = "train_images_per_sec", 1.0
+        config = {"workload": train_workload(args.dataset, K, "B"), "per_gpu_batch": BATCH, "image": SIZE, "classes": K + 1}
+        if torch.cuda.is_available() and K == 20 and not args.no_reference_gpu:
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            torch.cuda.set_device(dev)
+            try:
+                extra["reference_gpu"] = measure_reference_gpu(dev, P, x, cls, box, n_iter, steps=min(args.steps, 10), warmup=3)
+            except Exception as exc:
+                extra["reference_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     else:
         img = synth_coco_image(0)
         g = torch.Generator().manual_seed(0)
@@ -194,14 +292,15 @@ def run_reference(args):
             t = cpu_crf(img.numpy(), prob)
             if i >= args.warmup:
                 times.append(t)
-        metric, workload = "crf_sweep_images_per_sec", "coco81_mscam_mscseg_densecrf_640x480"
+        metric, config, imgs = "crf_sweep_images_per_sec", {"workload": "coco81_mscam_mscseg_densecrf_640x480"}, 1.0
     ms = 1000.0 * sum(times) / len(times)
-    val = 1.0 / (ms / 1000.0)
+    val = imgs / (ms / 1000.0)
     line = {"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra)
     print(json.dumps(line))
 
 
@@ -258,39 +357,85 @@ class Harness:
             self.dist.destroy_process_group()
 
 
-class GemmTimer:
-    """Per-launch CUDA-event timing of the dominant kernel (the tcgen05 GEMM) on the launching stream."""
+class OpTimer:
+    """Per-launch CUDA-event timing of selected ops wrappers (dupl_b200.ops.*) on the launching stream: the tcgen05 GEMM
+    (dominant kernel, tensor roofline) and the HBM-bound PAR / MS-CAM kernels."""
+    NAMES = ("gemm_bf16x3", "attention_fwd", "attention_bwd", "par_propagate", "par_affinity", "mscam_post")
 
     def __init__(self, stream):
         from dupl_b200 import ops
-        import dupl_b200.encoder as enc_mod
-        import dupl_b200.train as train_mod
-        import dupl_b200.dense as dense_mod
-        self.ops, self.mods, self.stream = ops, (ops, enc_mod.ops, train_mod.ops, dense_mod.ops), stream
-        self.orig = ops.gemm_bf16x3
-        self.events = []
+        self.ops, self.stream = ops, stream
+        self.orig = {n: getattr(ops, n) for n in self.NAMES}
+        self.events = {n: [] for n in self.NAMES}
+        self.meta = {n: [] for n in self.NAMES}
 
-    def __enter__(self):
-        orig, events, stream = self.orig, self.events, self.stream
+    def _wrap(self, name):
+        orig, events, meta, stream = self.orig[name], self.events[name], self.meta[name], self.stream
 
-        def timed(groups, M, N, K, epilogue, **kw):
+        def timed(*a, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            orig(groups, M, N, K, epilogue, **kw)
+            r = orig(*a, **kw)
             e1.record(stream)
-            events.append((e0, e1, 2.0 * M * N * K * len(groups)))
-        for m in self.mods:
-            m.gemm_bf16x3 = timed
+            events.append((e0, e1))
+            if name == "gemm_bf16x3":
+                groups, M, N, K = a[0], a[1], a[2], a[3]
+                meta.append(2.0 * M * N * K * len(groups))
+            elif name == "par_propagate":
+                meta.append((tuple(a[1].shape), kw.get("nactive", a[4] if len(a) > 4 else None), a[3]))
+            elif name == "mscam_post":
+                meta.append(float(r.numel() * 4))
+            else:
+                meta.append(None)
+            return r
+        return timed
+
+    def __enter__(self):
+        for n in self.NAMES:   # every module of the package calls these through the `ops` module attribute
+            setattr(self.ops, n, self._wrap(n))
         return self
 
     def __exit__(self, *exc):
-        for m in self.mods:
-            m.gemm_bf16x3 = self.orig
+        for n in self.NAMES:
+            setattr(self.ops, n, self.orig[n])
+
+    def ms(self, name):
+        return sum(a.elapsed_time(b) for a, b in self.events[name])
 
     def summary(self):
-        ms = sum(a.elapsed_time(b) for a, b, _ in self.events)
-        flop = sum(f for _, _, f in self.events)
-        return ms, flop, len(self.events)
+        return self.ms("gemm_bf16x3"), sum(self.meta["gemm_bf16x3"]), len(self.events["gemm_bf16x3"])
+
+    def hbm_kernels(self, peaks):
+        """Effective-model HBM fractions of the PAR propagation and MS-CAM post-processing launches:
+        PAR per call = T * sum_i 4*h*w*(48 + 2*P_i) bytes (affinity once per image and iteration, P_i live mask planes
+        read + written); MS-CAM post = bytes of the [b,K,H,W] fp32 tensor it writes."""
+        out = {}
+        pk = peaks["hbm_gbs"]
+        n = len(self.events["par_propagate"])
+        if n:
+            total = 0.0
+            for (shape, nactive, iters) in self.meta["par_propagate"]:
+                B, P, hh, ww = shape
+                live = nactive.tolist() if nactive is not None else [P] * B
+                total += iters * sum(4.0 * hh * ww * (48 + 2 * p) for p in live)
+            ms = self.ms("par_propagate")
+            out["par_propagate"] = {"calls": n, "ms_per_call": ms / n, "effective_gbs": total / (ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": total / (ms * 1e-3) / 1e9 / pk,
+                                    "model": "T x sum_i 4hw(48 + 2 P_i) B per call (affinity streamed once per image and iteration)"}
+        n = len(self.events["par_affinity"])
+        if n:
+            out["par_affinity"] = {"calls": n, "ms_per_call": self.ms("par_affinity") / n}
+        n = len(self.events["mscam_post"])
+        if n:
+            ms, total = self.ms("mscam_post"), sum(self.meta["mscam_post"])
+            out["mscam_post"] = {"calls": n, "ms_per_call": ms / n, "effective_gbs": total / (ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": total / (ms * 1e-3) / 1e9 / pk,
+                                 "model": "bytes of the normalised [b,K,448,448] fp32 CAM tensor written once (both passes timed)"}
+        for k in ("attention_fwd", "attention_bwd"):
+            n = len(self.events[k])
+            if n:
+                out[k] = {"calls": n, "ms_per_call": self.ms(k) / n}
+        return out
 
 
 def gemm_roofline(timer, peaks, peak_kind, step_tflops, timed_in):
@@ -299,21 +444,16 @@ def gemm_roofline(timer, peaks, peak_kind, step_tflops, timed_in):
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     return {"bound": "tensor", "kernel": "gemm_bf16x3_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved / peak_tf if peak_tf else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fc1-shaped launch (M=21976, N=3072, K=768),
-            # ncu --set full capture of this command, profiles/r01_summary.md
-            "traffic": TRAFFIC_GEMM_BYTES,
+            # launches of many shapes are timed here (CAM half M = 21 976 x 2 students, training half M = 3140): there is no
+            # single per-launch DRAM figure for the mix; the ncu --set full captures per shape are in profiles/ (r02_summary.md)
+            "traffic": None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})",
             "issued_tflops": 3.0 * achieved, "frac_issued": 3.0 * achieved / peak_tf if peak_tf else None,
             "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "timed_in": timed_in,
             "note": "achieved = algorithmic fp32-GEMM FLOPs (2MNK) / CUDA-event time; the kernel issues 3 bf16 MMAs per "
-                    "product (split operands: the 1e-3 fp32 parity bar rules out single-pass bf16/fp16/tf32, DESIGN.md section 2), so the "
+                    "product (split operands: the 1e-3 fp32 parity bar, profiles/r02_precision_table.md), so the "
                     "tensor pipe does 3x this figure (issued_tflops / frac_issued) and frac is capped at 1/3",
             "step_tflops": step_tflops}
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three captured M = 21 976 encoder launches (qkv 294.6 MB,
-# proj 225.1 MB, fc2 422.6 MB; algorithmic 277 / 205 / 414 MB) of `ncu --set full` on this command: profiles/r01_summary.md
-TRAFFIC_GEMM_BYTES = 314.1e6
 
 
 def build_model(K, dev, train=False):
@@ -326,15 +466,19 @@ def build_model(K, dev, train=False):
     return (model.train() if train else model.eval()), P
 
 
+def params_checksum(model):
+    """One int64 per parameter tensor: the wrap-around sum of its fp32 bit patterns (bit-level, order-independent)."""
+    return torch.stack([p.detach().contiguous().view(torch.int32).to(torch.int64).sum() for p in model.parameters()])
+
+
 def measure_train(h, args, K, steps, warmup, want_roofline):
-    """Full phase-B step.  Returns dict(ms, e2e_ms, launches, timer, h2d, d2h, loss)."""
+    """Full training step.  Returns dict(ms, e2e_ms, launches, timer, h2d, d2h, loss, ...)."""
     from dupl_b200 import _lib as L
     from dupl_b200.train_step import PhaseBStep, make_optimizer, Args
     model, P = build_model(K, h.dev, train=True)
-    # one process per model: the whole iteration is one CUDA graph (DUPL_TRAIN_CAPTURE=0 switches it off); under DDP the
-    # reducer's hooks need the eager autograd pass
-    # with several ranks the captured step all-reduces the flattened gradients itself (one NCCL call inside the graph);
-    # DUPL_TRAIN_CAPTURE=0 or DUPL_TRAIN_CAPTURE_DDP=0 fall back to the eager autograd half under DistributedDataParallel
+    # one process per model: the whole iteration is one CUDA graph; with several ranks the captured step averages the
+    # gradients itself (NCCL inside the graph).  DUPL_TRAIN_CAPTURE=0 or DUPL_TRAIN_CAPTURE_DDP=0 fall back to the eager
+    # autograd half under DistributedDataParallel (the reducer's hooks need the eager autograd pass)
     capture = os.environ.get("DUPL_TRAIN_CAPTURE", "1") != "0" and (h.world == 1 or os.environ.get("DUPL_TRAIN_CAPTURE_DDP", "1") == "1")
     optim = make_optimizer(model, capturable=capture)
     wrapped = model
@@ -355,9 +499,7 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
         cls = cls.to(torch.uint8)           # COCO labels are uint8 (datasets/coco.py)
     phase_c = getattr(args, "phase", "B") == "C"
     # phase B: cam_iters <= n_iter < gmm_iters; phase C adds the augmented view (synthetic: another seeded batch), GMM, consistency
-    it = [(targs.gmm_iters + 1000) if phase_c else (targs.cam_iters + targs.gmm_iters) // 2]
-    if K == 80 and not phase_c:
-        it = [20000]                        # past the cams_aux window (n_iter <= 12000), before gmm_iters = 32000
+    it = [train_n_iter(K, phase_c)]
     from helpers import synth_images
     x_aug = synth_images(BATCH, SIZE, SIZE, seed=100 + h.rank) if phase_c else None
     x_pin, cls_pin = x.pin_memory(), cls.pin_memory()
@@ -380,9 +522,15 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
 
     for _ in range(warmup):
         device_step()
+    sampler = ClockSampler(h.local_rank)
+    if h.rank == 0:
+        sampler.start()
     ms = h.time_device(device_step, steps)
     out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 * (2 if phase_c else 1) + cls_pin.numel() * cls_pin.element_size()), d2h=4, P=P,
                inputs=(x, cls, box), n_iter=it[0])
+    e2e_step()
+    out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps
+    out["clocks"] = sampler.stop() if h.rank == 0 else None
     timer = None
     if want_roofline:
         eager = PhaseBStep(wrapped, None, args=targs, device=h.dev, graph=False)
@@ -394,29 +542,33 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
 
         eager_iter()
         launches0 = L.lib().dupl_launch_count()
-        with GemmTimer(h.stream) as timer:
+        with OpTimer(h.stream) as timer:
             h.barrier()
             for _ in range(steps):
                 eager_iter()
             h.barrier()
         out["launches"] = int(L.lib().dupl_launch_count() - launches0)
-    e2e_step()
-    out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps
+        del eager
     out["timer"] = timer
     out["capture"] = capture
-    # replicas must hold bit-identical parameters after the run (same updates on every rank)
-    chk = torch.stack([p.detach().double().sum() for p in list(model.parameters())[:64]]).sum().reshape(1)
+    # replicas must hold bit-identical parameters after the run (same updates on every rank): EVERY parameter tensor
+    chk = params_checksum(model)
     lo, hi = chk.clone(), chk.clone()
     if h.dist is not None:
         h.dist.all_reduce(lo, op=h.dist.ReduceOp.MIN)
         h.dist.all_reduce(hi, op=h.dist.ReduceOp.MAX)
-    out["ranks_in_sync"] = bool((lo == hi).item())
+    out["ranks_in_sync"] = bool((lo == hi).all().item())
+    out["params_checked"] = int(chk.numel())
     out["loss"] = float(last["loss"].item())
     out["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
+    model.zero_grad(set_to_none=True)
+    del step, optim, wrapped, model
+    torch.cuda.empty_cache()
     return out
 
 
-def run_cam_par(h, args):
+def measure_cam_par(h, args, steps, warmup, want_breakdown=False):
+    """BASELINE.json configs[1]: MS-CAM (3 scales + flips) of both students + PAR refine of both students, b = 4."""
     from dupl_b200 import _lib as L, ops
     from dupl_b200.pipeline import CamParStep
     K = 20
@@ -441,31 +593,31 @@ def run_cam_par(h, args):
         out_pin[1].copy_(l2, non_blocking=True)
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
     h.barrier()
     sampler = ClockSampler(h.local_rank)
     if h.rank == 0:
         sampler.start()
     # ---- timed region 1: inputs resident in HBM (the step is replayed as one CUDA graph unless --no-graph)
-    ms_total = h.time_device(device_step, args.steps)
-    # ---- same K steps launched kernel by kernel with CUDA events around every GEMM launch (roofline of the dominant
-    #      kernel) and the library's launch counter (kernels per step)
+    ms_total = h.time_device(device_step, steps)
+    # ---- same K steps launched kernel by kernel with CUDA events around the GEMM / PAR / MS-CAM launches and the
+    #      library's launch counter (kernels per step)
     eager(x_dev, cls_dev, box, thr_dev)
     launches0 = L.lib().dupl_launch_count()
-    with GemmTimer(h.stream) as timer:
+    with OpTimer(h.stream) as timer:
         h.barrier()
-        for _ in range(args.steps):
+        for _ in range(steps):
             eager(x_dev, cls_dev, box, thr_dev)
         h.barrier()
     launches = L.lib().dupl_launch_count() - launches0
     # ---- timed region 2: end to end through the public API with host buffers
     e2e_step()
-    e2e_ms_total = h.time_wall(e2e_step, args.steps)
+    e2e_ms_total = h.time_wall(e2e_step, steps)
     clocks = sampler.stop() if h.rank == 0 else None
 
     breakdown = None
-    if args.breakdown and h.rank == 0:
+    if want_breakdown and h.rank == 0:
         recs = []
         names = ["gemm_bf16x3", "attention_fwd", "layernorm_split", "patchify", "cls_rows", "cam_contract", "mscam_post",
                  "par_affinity", "par_propagate", "refine_prologue", "refine_epilogue", "split_bf16", "pos_embed_resize"]
@@ -493,94 +645,168 @@ def run_cam_par(h, args):
         for n, e0, e1 in recs:
             breakdown[n] = breakdown.get(n, 0.0) + e0.elapsed_time(e1)
         breakdown = {k: round(v, 3) for k, v in breakdown.items()}
+    ms_step, e2e_ms_step = [v / steps for v in h.max_over_ranks(ms_total, e2e_ms_total)]
+    res = dict(ms=ms_step, e2e_ms=e2e_ms_step, launches=int(launches), clocks=clocks, timer=timer, breakdown=breakdown, P=P,
+               inputs=(x, cls, box, thr), h2d=int(x_pin.numel() * 4 + cls_pin.numel() * 4 + thr_pin.numel() * 4),
+               d2h=int(out_pin.numel() * 4))
+    del step, eager, model
+    torch.cuda.empty_cache()
+    return res
 
-    ms_step, e2e_ms_step = [v / args.steps for v in h.max_over_ranks(ms_total, e2e_ms_total)]
+
+def cam_par_config(h, args):
+    return {"workload": "voc21_dual_student_cam_par_refine_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
+            "classes": 21, "cam_scales": list(SCALES), "par_iters": 10,
+            "parallelism": f"dp{h.world} (independent batches, no collective on this path)",
+            "l2_policy": "per-step working set ~1.5 GB per student >> 126 MB L2; no explicit flush",
+            "fuse_students": bool(args.fuse_students), "cuda_graph": not args.no_graph}
+
+
+def run_cam_par(h, args):
+    c = measure_cam_par(h, args, args.steps, args.warmup, want_breakdown=args.breakdown)
     imgs = BATCH * h.world
-
-    # ---- secondary figure: the full dual-student training step (configs[2] per-GPU shape) in the same run
-    train = None
-    if not args.no_train_step:
-        del step, eager
-        torch.cuda.empty_cache()
-        try:
-            t = measure_train(h, args, K, steps=max(5, args.steps // 2), warmup=3, want_roofline=False)
-        except Exception as exc:  # the secondary figure must never take the headline line down with it
-            t = None
-            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    if not args.no_train_step and t is not None:
-        tms, te2e = h.max_over_ranks(t["ms"], t["e2e_ms"])
-        train = {"metric": "train_images_per_sec", "value": imgs / (tms / 1000.0), "unit": UNIT, "ms_per_step": tms,
-                 "e2e": {"value": imgs / (te2e / 1000.0), "unit": UNIT, "ms_per_step": te2e},
-                 "workload": "voc21_dual_student_phaseB_step_448_bs4 (MS-CAM + PAR labels + fwd/bwd of both students + losses + AdamW"
-                             + (", gradient all-reduce over NCCL)" if h.world > 1 else ")"),
-                 "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2), "ranks_in_sync": t["ranks_in_sync"],
-                 "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half"}
-
     if h.rank == 0:
         peaks, peak_kind = load_peaks()
         line = {
-            "metric": "cam_par_refine_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "cam_par_refine_images_per_sec", "value": imgs / (c["ms"] / 1000.0), "unit": UNIT, "n_gpus": h.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": c["ms"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "voc21_dual_student_cam_par_refine_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
-                       "classes": K + 1, "cam_scales": list(SCALES), "par_iters": 10,
-                       "parallelism": f"dp{h.world} (independent batches, no collective on this path)",
-                       "l2_policy": "per-step working set ~1.5 GB per student >> 126 MB L2; no explicit flush",
-                       "fuse_students": bool(args.fuse_students), "cuda_graph": not args.no_graph},
-            "e2e": {"value": imgs / (e2e_ms_step / 1000.0), "unit": UNIT,
-                    "h2d_bytes_per_step": int(x_pin.numel() * 4 + cls_pin.numel() * 4 + thr_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": e2e_ms_step},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": gemm_roofline(timer, peaks, peak_kind, GFLOP_PER_IMAGE_CAM * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
+            "config": cam_par_config(h, args),
+            "e2e": {"value": imgs / (c["e2e_ms"] / 1000.0), "unit": UNIT, "h2d_bytes_per_step": c["h2d"],
+                    "d2h_bytes_per_step": c["d2h"], "ms_per_step": c["e2e_ms"]},
+            "gpu_launches": c["launches"], "clocks": c["clocks"],
+            "roofline": gemm_roofline(c["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_CAM * 1e9 * BATCH / (c["ms"] * 1e-3) / 1e12,
                                       "the same K steps launched eagerly right after the (graph-replayed) timed region"),
+            "hbm_kernels": c["timer"].hbm_kernels(peaks),
         }
-        if train is not None:
-            line["train_step"] = train
-        if breakdown is not None:
-            line["breakdown_ms"] = breakdown
+        if c["breakdown"] is not None:
+            line["breakdown_ms"] = c["breakdown"]
         if h.world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            secs = cpu_cam_par(P, x, cls, box, thr, 1, students=(1,)) * 2.0
+            x, cls, box, thr = c["inputs"]
+            secs = cpu_cam_par(c["P"], x, cls, box, thr, 1)
             line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "1 of 4 images; MS-CAM + PAR refine for student 1 timed once, doubled for the two students"}
+                                    "sample": "1 of 4 images; MS-CAM + PAR refine for both students through the oracle port, timed once"}
         print(json.dumps(line))
+
+
+def measure_crf(h, steps):
+    """DenseCRF mean-field at COCO size (640x480x81, T = 10, tools/eval_seg_coco_ddp.py:156-188 parameters): device-resident
+    ms/img, the same through the reference's numpy interface (utils/dcrf.py:42-69: numpy in, numpy out), and the 1-thread C
+    restatement of pydensecrf on the host."""
+    from dupl_b200 import ops
+    from dupl_b200.utils.dcrf import DenseCRF
+    H, W, Cn = 480, 640, 81
+    imgs = [synth_coco_image(i) for i in range(4)]
+    g = torch.Generator().manual_seed(0)
+    probs = []
+    for _ in imgs:
+        lg = torch.randn(1, Cn, 28, 28, generator=g) * 2.0
+        probs.append(torch.softmax(torch.nn.functional.interpolate(lg, size=(H, W), mode="bilinear", align_corners=False), 1)[0].contiguous())
+    crf = DenseCRF(10, 1, 1, 4, 121, 5)
+    dev_in = [(a.to(h.dev), p.to(h.dev)) for a, p in zip(imgs, probs)]
+    np_in = [(a.numpy(), p.numpy()) for a, p in zip(imgs, probs)]
+    k = [0]
+
+    def device_step():
+        a, p = dev_in[k[0] % len(dev_in)]
+        k[0] += 1
+        return crf(a, p)
+
+    def numpy_step():
+        a, p = np_in[k[0] % len(np_in)]
+        k[0] += 1
+        return crf(a, p)
+
+    for _ in range(3):
+        device_step()
+    ms = h.time_device(device_step, steps) / steps
+    numpy_step()
+    e2e = h.time_wall(numpy_step, steps) / steps
+    m2, m5 = ops.last_crf_lattice_sizes()
+    N, T = H * W, 10
+    per_iter = 0
+    for d, M in ((2, m2), (5, m5)):   # SURVEY §8(d): splat + (d+1) blurs + slice
+        per_iter += (N * Cn * 4 + N * (d + 1) * 8 + M * Cn * 4) + (d + 1) * (2 * M * Cn * 4 + M * 8) + (N * (d + 1) * 8 + M * Cn * 4 + N * Cn * 4)
+    per_iter += 2 * N * Cn * 4
+    peaks, _ = load_peaks()
+    out = {"ms_per_image": ms, "e2e_numpy_ms_per_image": e2e, "size": "640x480x81, T=10, (pos_w 1, sxy 1), (bi_w 4, sxy 121, srgb 5)",
+           "lattice_vertices": {"gaussian_d2": m2, "bilateral_d5": m5},
+           "effective_gbs": per_iter * T / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": per_iter * T / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+           "e2e_bytes": {"h2d": int(H * W * 3 + Cn * H * W * 4), "d2h": int(Cn * H * W * 4)}}
+    return out, np_in[0]
 
 
 def run_train(h, args):
     K = 80 if args.dataset == "coco" else 20
-    sampler = ClockSampler(h.local_rank)
-    if h.rank == 0:
-        sampler.start()
     t = measure_train(h, args, K, args.steps, args.warmup, want_roofline=True)
-    clocks = sampler.stop() if h.rank == 0 else None
     ms_step, e2e_ms = h.max_over_ranks(t["ms"], t["e2e_ms"])
     imgs = BATCH * h.world
+    peaks, peak_kind = load_peaks()
+    secondary = {}
+    if not args.no_secondary:
+        # ---- CAM + PAR half alone (configs[1]) — every rank takes part (max over ranks inside)
+        try:
+            c = measure_cam_par(h, args, max(5, args.steps // 2), 3)
+            secondary["cam_par"] = {"metric": "cam_par_refine_images_per_sec", "value": imgs / (c["ms"] / 1000.0), "unit": UNIT,
+                                    "ms_per_step": c["ms"], "ms_per_image": c["ms"] / BATCH,
+                                    "e2e": {"value": imgs / (c["e2e_ms"] / 1000.0), "unit": UNIT, "ms_per_step": c["e2e_ms"]},
+                                    "workload": "voc21_dual_student_cam_par_refine_448_bs4 (BASELINE.json configs[1])",
+                                    "hbm_kernels": c["timer"].hbm_kernels(peaks)}
+        except Exception as exc:      # a secondary figure must never take the headline line down with it
+            secondary["cam_par"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if h.world == 1:
+            try:
+                crf, crf_np = measure_crf(h, max(5, args.steps // 2))
+                if not args.no_cpu_baseline:
+                    secs = cpu_crf(*crf_np)
+                    crf["cpu_1_thread_ms_per_image"] = secs * 1000.0
+                    crf["speedup_vs_cpu_1_thread"] = secs * 1000.0 / crf["ms_per_image"]
+                    crf["cpu_kind"] = "C restatement of the permutohedral mean-field (oracle/densecrf_ref.c), not pydensecrf"
+                secondary["crf"] = crf
+            except Exception as exc:
+                secondary["crf"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            if K == 20 and not args.no_reference_gpu and args.phase == "B":
+                try:
+                    x, cls, box = t["inputs"]
+                    r = measure_reference_gpu(h.dev, t["P"], x, cls, box, train_n_iter(K, False), steps=min(args.steps, 10), warmup=3)
+                    if r is not None:
+                        r["speedup"] = (imgs / (ms_step / 1000.0)) / r["value"]
+                        r["speedup_e2e"] = (imgs / (e2e_ms / 1000.0)) / r["value"]
+                        r["target"] = ">= 5x (BASELINE.json north_star)"
+                    else:
+                        r = {"unavailable": "baseline/_ref absent (run baseline/install_ref.sh where /root/reference is mounted)"}
+                    secondary["reference_gpu"] = r
+                except Exception as exc:
+                    secondary["reference_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if h.rank == 0:
-        peaks, peak_kind = load_peaks()
         line = {
             "metric": "train_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{args.dataset}{K + 1}_dual_student_phase{args.phase}_step_448_bs4", "per_gpu_batch": BATCH, "image": SIZE,
-                       "n_iter": t["n_iter"],
-                       "classes": K + 1, "parallelism": (f"dp{h.world} (one NCCL all-reduce of the 732.7 MB fp32 gradients per step, " +
-                                       ("inside the captured graph)" if t.get("capture") else "DistributedDataParallel reducer)")) if h.world > 1 else "single GPU",
+            "config": {"workload": train_workload(args.dataset, K, args.phase), "per_gpu_batch": BATCH, "image": SIZE,
+                       "classes": K + 1, "n_iter": t["n_iter"],
+                       "parallelism": (f"dp{h.world} (gradients averaged over NCCL " +
+                                       ("inside the captured graph)" if t.get("capture") else "by the DistributedDataParallel reducer)")) if h.world > 1 else "single GPU",
                        "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush",
                        "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images",
                        "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half only (DDP reducer needs eager autograd)"},
             "e2e": {"value": imgs / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
                     "ms_per_step": e2e_ms},
-            "gpu_launches": t.get("launches"), "clocks": clocks, "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
-            "ranks_in_sync": t["ranks_in_sync"],
+            "gpu_launches": t.get("launches"), "clocks": t["clocks"], "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
+            "ranks_in_sync": t["ranks_in_sync"], "params_checked": t["params_checked"],
             "roofline": gemm_roofline(t["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_TRAIN * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
-                                      "the same K steps with the CAM half launched eagerly (no graph) right after the timed region"),
+                                      "the same K steps launched eagerly (no graph, no optimizer step) right after the timed region"),
+            "hbm_kernels": t["timer"].hbm_kernels(peaks),
         }
+        line.update(secondary)
         if h.world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             x, cls, box = t["inputs"]
-            secs = cpu_train(t["P"], x, cls, box, 224) * 4.47
-            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "1 image at 224x224 through the oracle's phase-B losses + backward, scaled by the FLOP ratio 4.47 to 448x448"}
+            arm = CpuTrainArm(t["P"], K)
+            secs = arm(x, cls, box, train_n_iter(K, False))
+            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": arm.kind,
+                                    "sample": arm.sample + "; timed once"}
         print(json.dumps(line))
 
 
@@ -671,11 +897,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dupl_b200", choices=["dupl_b200", "reference"])
-    ap.add_argument("--workload", default="cam_par", choices=["cam_par", "train", "crf_sweep"])
+    ap.add_argument("--workload", default="train", choices=["train", "cam_par", "crf_sweep"])
     ap.add_argument("--dataset", default="voc", choices=["voc", "coco"], help="train workload: class count / loss weights")
     ap.add_argument("--phase", default="B", choices=["B", "C"], help="train workload: B = CAM+PAR+seg (default), C = + aug view, GMM filter, consistency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train-step", action="store_true", help="cam_par: skip the secondary training-step measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="train: skip the secondary cam_par / crf / reference_gpu measurements")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the unmodified reference on the GPU")
     ap.add_argument("--no-fuse-students", dest="fuse_students", action="store_false",
                     help="one encoder pass per student instead of both students per grouped GEMM launch")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdupl.so")
+# DUPL_LIB: an alternative build of the same library (tools/precision_table.py loads the TF32-emulation experiment builds)
+LIB_PATH = os.environ.get("DUPL_LIB") or os.path.join(_HERE, "libdupl.so")
 
 MAX_SEGMENTS = 8
 MAX_GROUPS = 2

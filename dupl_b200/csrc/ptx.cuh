@@ -240,12 +240,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, in
 
 // ---------------------------------------------------------------- split-bf16 helpers
 // x = hi + lo + O(2^-17 |x|): two bf16 planes carry ~16 mantissa bits through the tensor core.
+// Experiment builds only (make emu, tools/precision_table.py): -DDUPL_EMU_TF32 rounds every value to TF32 (10 explicit
+// mantissa bits, cvt.rna) BEFORE it is split, so that the 3-pass product of the planes equals a single-pass kind::tf32 MMA
+// on RN-rounded operands to 2^-17.  The product library is built without it.
+__device__ __forceinline__ float emu_operand(float x) {
+#ifdef DUPL_EMU_TF32
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+#else
+  return x;
+#endif
+}
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  x = emu_operand(x);
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 // Two values at once: one cvt.rn.bf16x2.f32 per plane.  Element a goes to the low half (lower address).
 __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = emu_operand(a);
+  b = emu_operand(b);
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);

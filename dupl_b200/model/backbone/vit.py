@@ -84,13 +84,23 @@ class VisionTransformer(nn.Module):
         raise RuntimeError("the encoder is driven by dupl_b200.encoder (CUDA kernels), not by nn.Module.forward")
 
 
+DEIT_BASE_URL = "https://dl.fbaipublicfiles.com/deit/deit_base_patch16_224-b5f2ef4d.pth"
+
+
 def deit_base_patch16_224(pretrained=False, **kwargs):
+    """model/backbone/deit.py:97-109: with pretrained=True (the scripts' default, train_final_voc.py:54) the DeiT-B
+    checkpoint comes through torch.hub exactly as in the reference — from the hub cache `./pretrained/` when the file is
+    there (no network needed), else torch.hub tries to download it and raises what the reference would raise offline."""
+    model = VisionTransformer(**kwargs)
     if pretrained:
-        raise RuntimeError("no network access: load the DeiT checkpoint with load_state_dict instead of pretrained=True")
-    return VisionTransformer(**kwargs)
+        checkpoint = torch.hub.load_state_dict_from_url(url=DEIT_BASE_URL, model_dir="./pretrained", map_location="cpu",
+                                                        check_hash=True)["model"]
+        model.load_state_dict(checkpoint)
+    return model
 
 
 def vit_base_patch16_224(pretrained=False, **kwargs):
     if pretrained:
-        raise RuntimeError("no network access: load the ViT checkpoint with load_state_dict instead of pretrained=True")
+        raise RuntimeError("vit_base_patch16_224(pretrained=True) goes through timm's load_pretrained in the reference "
+                           "(vit.py:1069-1080), which this image lacks: load the checkpoint with load_state_dict instead")
     return VisionTransformer(**kwargs)

@@ -122,6 +122,23 @@ def attention_fwd(qkv_hi, qkv_lo, out_hi, out_lo, segs, heads, scale, lse=None):
     L.check(L.lib().dupl_attention_fwd(C.byref(a), L.stream_ptr(qkv_hi.device)), "dupl_attention_fwd")
 
 
+def attention_bwd(qkv, att, d_att, lse, batch, tokens, heads, scale, row_offset=0):
+    """Backward of softmax(Q K^T * scale) V per (image, head) (autograd of vit.py:120-135) for `batch` images of `tokens`
+    rows starting at `row_offset`.  qkv / att / d_att are (hi, lo) split-bf16 plane pairs [M, 3D] / [M, D] / [M, D], lse the
+    forward's log-sum-exp [M, heads].  -> d_qkv fp32 [M, 3D]."""
+    M, D = att[0].shape
+    dev = att[0].device
+    d_qkv = torch.empty(M, 3 * D, dtype=torch.float32, device=dev)
+    dvec = torch.empty(M, heads, dtype=torch.float32, device=dev)
+    a = L.AttentionBwdArgs()
+    a.qkv_hi, a.qkv_lo, a.o_hi, a.o_lo = qkv[0].data_ptr(), qkv[1].data_ptr(), att[0].data_ptr(), att[1].data_ptr()
+    a.do_hi, a.do_lo = d_att[0].data_ptr(), d_att[1].data_ptr()
+    a.lse, a.Dvec, a.dqkv = lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
+    a.M, a.batch, a.tokens, a.row_offset, a.heads, a.scale = M, batch, tokens, row_offset, heads, scale
+    L.check(L.lib().dupl_attention_bwd(C.byref(a), L.stream_ptr(dev)), "dupl_attention_bwd")
+    return d_qkv
+
+
 def patchify(images, seg, size, flip_twin, out_hi, out_lo):
     """size = (hs, ws): the resolution the images are resized to before the 16x16 patch grid is cut."""
     b, _, H, W = images.shape

@@ -77,10 +77,16 @@ class CamParStep:
                     b.planes().refresh_all()    # replays see the weights of the moment
                 st["out"] = self._run(st["x"], st["cls"], st["box"], st["thr"])
             st["graph"] = graph
+            # the kept activations this graph writes: several CamParStep graphs can share one model (TrainStep owns three),
+            # so every replay must re-point the students at ITS buffers, not at those of the graph captured last
+            st["kept"] = (net.branch1._kept, net.branch2._kept)
             self._g = st
         st = self._g
         self._stage(st, inputs, cls_label, img_box, high_thres)
         st["graph"].replay()
+        if self.keep_activations:
+            net = self.model.module if hasattr(self.model, "module") else self.model
+            net.branch1._kept, net.branch2._kept = st["kept"]
         return st["out"]
 
     @staticmethod

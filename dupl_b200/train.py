@@ -276,14 +276,7 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
         bfk = dict(dtype=torch.bfloat16, device=dev)
         d_att = (torch.empty(M, D, **bfk), torch.empty(M, D, **bfk))     # dO as split planes: operand of the attention backward
         ops.gemm_bf16x3([dict(a=dpl, w=pl.plane_t(bp + "attn.proj.weight"), out=d_att)], M, D, D, L.EPI_SPLIT)
-        d_qkv = torch.empty(M, 3 * D, **f32)
-        a = L.AttentionBwdArgs()
-        a.qkv_hi, a.qkv_lo, a.o_hi, a.o_lo = b.qkv[0].data_ptr(), b.qkv[1].data_ptr(), b.att[0].data_ptr(), b.att[1].data_ptr()
-        a.do_hi, a.do_lo = d_att[0].data_ptr(), d_att[1].data_ptr()
-        dvec = torch.empty(M, E.HEADS, **f32)
-        a.lse, a.Dvec, a.dqkv = b.lse.data_ptr(), dvec.data_ptr(), d_qkv.data_ptr()
-        a.M, a.batch, a.tokens, a.row_offset, a.heads, a.scale = M, B, N, 0, E.HEADS, scale
-        L.check(L.lib().dupl_attention_bwd(C.byref(a), _st(dev)), "dupl_attention_bwd")
+        d_qkv = ops.attention_bwd(b.qkv, b.att, d_att, b.lse, B, N, E.HEADS, scale)
         dpl, dt, grads["encoder." + bp + "attn.qkv.bias"] = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
         grads["encoder." + bp + "attn.qkv.weight"] = wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad)
         d_xn1 = dgrad(dpl, pl.plane_t(bp + "attn.qkv.weight"), M, D, 3 * D)

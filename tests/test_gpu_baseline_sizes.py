@@ -1,0 +1,93 @@
+"""GPU: CUDA path vs the CPU oracle AT BASELINE.json's SIZES: 448x448 inputs, token counts
+N = 197 / 442 / 785 / 1765 (multi-tile attention forward AND backward), the grouped two-student MS-CAM pass, the phase-B
+losses with all 2 x 154 parameter gradients, VOC (K = 20) and COCO (K = 80).  Tolerances are the north_star's:
+CAM / logits / loss within 1e-3 relative of fp32; pseudo-label maps may differ where a CAM value sits within that
+tolerance of a threshold (mismatch fraction asserted and printed).
+
+The measurements live in tests/fullsize_checks.py (shared with tools/precision_table.py)."""
+import json
+
+import pytest
+
+import fullsize_checks as FC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,gh,gw", [(2, 14, 14), (2, 21, 21), (2, 28, 28), (1, 42, 42)])
+def test_attention_forward_and_backward_match_fp64_autograd(B, gh, gw):
+    """N = 197 (224^2), 442 (336^2, the phase-C view), 785 (448^2), 1765 (672^2): 2..14 key tiles of 128, a partial last
+    tile everywhere.  dQ / dK / dV accumulate in TMEM across all key / query tiles (attention_bwd.cu)."""
+    r = FC.attention_errors(B, gh, gw, seed=gh)
+    print("attention", json.dumps(r))
+    assert r["tokens"] == 1 + gh * gw
+    assert r["fwd"] < 1e-4, r
+    for k in ("dq", "dk", "dv"):
+        assert r[k] < 2e-4, r
+
+
+@pytest.fixture(scope="module")
+def voc_model():
+    return FC.build_model(21, -3)[0]
+
+
+def test_mscam_pair_and_refine_labels_at_448_match_oracle(voc_model):
+    """multi_scale_cam2_siamese for both students in the grouped pass (N = 785 + 197 + 1765 per image and flip) and the
+    refine step on top, one 448x448 image: cam_helper.py:164-204, 338-440."""
+    r = FC.mscam_errors(voc_model, 21, -3, b=1, S=448, seed=3, pair=True)
+    print("mscam448", json.dumps(r))
+    for br in (1, 2):
+        assert r[f"cam{br}"] < 1e-3 and r[f"aux{br}"] < 1e-3, r
+        assert r[f"cam{br}_raw_well"] < 1e-3, r
+        assert r[f"label{br}_mismatch"] < 1e-3, r
+    assert r["label1_mismatch_isolated"] < 1e-5, r      # same CAM in: the refine kernels alone (PAR 1e-6 off an arg-max tie at most)
+
+
+def test_mscam_batch4_single_student_path_at_448(voc_model):
+    """b = 4 as in configs[1] (M = 21 976 token rows per student) through the one-student entry point."""
+    r = FC.mscam_errors(voc_model, 21, -3, b=4, S=448, seed=5, pair=False)
+    print("mscam448_b4", json.dumps(r))
+    for br in (1, 2):
+        assert r[f"cam{br}"] < 1e-3 and r[f"aux{br}"] < 1e-3, r
+        assert r[f"label{br}_mismatch"] < 1e-3, r
+
+
+def test_phase_b_losses_and_all_gradients_at_448_match_oracle_autograd():
+    """train_final_voc.py:260-456 on one 448x448 image: every loss part, the refined labels and the gradient of the total
+    loss w.r.t. all 308 parameter tensors (N = 785: 7 query/key tiles in the attention backward, M = 785 rows in every
+    dgrad / wgrad GEMM incl. split-K)."""
+    r = FC.train_step_errors(21, b=1, S=448, seed=40, n_iter=3000)
+    print("train448", json.dumps(r))
+    assert r["grads_checked"] == 308
+    for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
+        assert r[k] < 1e-3, r
+    assert r["label_mismatch"] < 1e-3, r
+    assert r["grad_worst"] < 2e-3, r
+    assert r["grad_median"] < 1e-3, r
+
+
+def test_phase_b_batch2_at_448_matches_oracle_autograd():
+    """b = 2: M = 1570 rows (not a multiple of 64), two images per attention launch, batch-wide loss normalisers."""
+    r = FC.train_step_errors(21, b=2, S=448, seed=44, n_iter=5000)
+    print("train448_b2", json.dumps(r))
+    for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
+        assert r[k] < 1e-3, r
+    assert r["label_mismatch"] < 1e-3, r
+    assert r["grad_worst"] < 2e-3, r
+
+
+def test_coco_mscam_and_phase_b_at_448_match_oracle():
+    """K = 80, uint8 labels, aux_layer = 9, the dynamic-threshold window (train_final_coco.py:323-333, n_iter > 12000)."""
+    m = FC.build_model(81, 9)[0]
+    r = FC.mscam_errors(m, 81, 9, b=1, S=448, seed=9, pair=True)
+    print("coco_mscam448", json.dumps(r))
+    for br in (1, 2):
+        assert r[f"cam{br}"] < 1e-3 and r[f"aux{br}"] < 1e-3, r
+        assert r[f"label{br}_mismatch"] < 1e-3, r
+    del m
+    t = FC.train_step_errors(81, b=1, S=448, seed=48, n_iter=20000, coco=True)
+    print("coco_train448", json.dumps(t))
+    for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
+        assert t[k] < 1e-3, t
+    assert t["label_mismatch"] < 1e-3, t
+    assert t["grad_worst"] < 2e-3, t

@@ -237,3 +237,31 @@ def test_captured_iteration_matches_the_eager_iteration():
     assert abs(losses[0][0] - losses[1][0]) < 1e-6 and abs(losses[0][1] - losses[1][1]) < 2e-6   # before any sizeable update: identical
     worst = max(_nrel(finals[1][n], finals[0][n]) for n in finals[0])
     assert worst < 1e-4, worst
+
+
+def test_alternating_phases_with_graph_replay_use_their_own_kept_activations():
+    """TrainStep owns three graph-replayed CamParStep variants on ONE model; each replay must hand the training forward
+    the activations IT wrote.  Phase B -> A -> B with other images each time (graph=True, forward reuse on) must give the
+    same losses and gradients as a fresh eager step without reuse on the same inputs."""
+    from dupl_b200.train_step import TrainStep
+    from helpers import synth_boxes, synth_cls_labels
+    b, S = 2, 64
+    m, _ = _models()
+    step = TrainStep(m, None, graph=True, reuse_forward=True)
+    plain_m, _ = _models()
+    plain = TrainStep(plain_m, None, graph=False, reuse_forward=False)
+    seq = [(3000, 81), (500, 82), (3001, 83), (501, 84), (3002, 85)]
+    for n_iter, seed in seq:
+        x = synth_images(b, S, S, seed=seed).cuda()
+        cls = synth_cls_labels(b, 20, seed=seed).cuda()
+        box = synth_boxes(b, S, S, seed=seed)
+        outs = []
+        for st, mod in ((step, m), (plain, plain_m)):
+            mod.zero_grad(set_to_none=True)
+            loss, parts, _ = st.losses(x, cls, box, n_iter)
+            loss.backward()
+            torch.cuda.synchronize()
+            outs.append((loss.detach().clone(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}))
+        assert torch.equal(outs[0][0], outs[1][0]), (n_iter, outs[0][0].item(), outs[1][0].item())
+        for n in outs[1][1]:
+            assert torch.equal(outs[0][1][n], outs[1][1][n]), (n_iter, n)
