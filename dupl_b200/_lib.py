@@ -140,6 +140,7 @@ _PROTOTYPES = {
     "dupl_ptc_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "dupl_ptc_loss_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p] * 3),
     "dupl_gemm_plan": (C.c_int, [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 3),
+    "dupl_set_gemm_sm_limit": (C.c_int, [C.c_int32]),
     "dupl_ptc_prepare": (C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 6),
     "dupl_ptc_mask_reduce": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dupl_ptc_dg": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 3),

@@ -104,8 +104,15 @@ int sm_count() {
   return n;
 }
 
+static std::atomic<int> g_gemm_sm_limit{0};
+int gemm_sms() {
+  const int lim = g_gemm_sm_limit.load(std::memory_order_relaxed), n = sm_count();
+  return (lim >= 2 && lim < n) ? (lim & ~1) : n;
+}
+
 }  // namespace dupl
 
+extern "C" int dupl_set_gemm_sm_limit(int32_t sms) { return dupl::g_gemm_sm_limit.exchange(sms < 0 ? 0 : sms); }
 extern "C" int dupl_version(void) { return DUPL_ABI_VERSION; }
 extern "C" const char* dupl_last_error(void) { return dupl::g_err; }
 extern "C" int64_t dupl_launch_count(void) { return dupl::g_launches.load(); }

@@ -52,6 +52,7 @@ int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1
                      uint32_t b2);
 
 int sm_count();
+int gemm_sms();  // SMs the persistent GEMM grid may occupy (dupl_set_gemm_sm_limit)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

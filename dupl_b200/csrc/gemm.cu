@@ -360,7 +360,7 @@ static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
   }
   const int m_pairs = cdiv(cdiv(P.M, GEMM_BM), 2), n_tiles = cdiv(P.N, BN);
   const int total = m_pairs * n_tiles * P.groups * P.ksplit;  // work items, one per cluster of 2 CTAs
-  const int clusters = total < sm_count() / 2 ? total : sm_count() / 2;
+  const int clusters = total < gemm_sms() / 2 ? total : gemm_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -384,7 +384,7 @@ static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
 // make 74 = 2 x 37 slots, so the M=3140 training shapes (39 / 117 / 156 tiles of 256) fit badly without this.
 static void choose_tiling(int M, int N, int k_blocks, int groups, int max_split, bool allow_192, int& bn_out, int& ks_out,
                           int& kper_out) {
-  const int slots = sm_count() / 2;
+  const int slots = gemm_sms() / 2;
   const int m_pairs = cdiv(cdiv(M, GEMM_BM), 2);
   double best = 1e30;
   bn_out = 256; ks_out = 1; kper_out = k_blocks;

@@ -76,9 +76,10 @@ def dgrad(dy_planes, wt_planes, M, n_out, k_contr):
     return out
 
 
-def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr):
-    """dW[n_rows, n_cols] = dY^T @ X, operands as transposed planes [n_rows, k_contr], [n_cols, k_contr]."""
-    out = torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt_planes[0].device)
+def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr, out=None):
+    """dW[n_rows, n_cols] = dY^T @ X, operands as transposed planes [n_rows, k_contr], [n_cols, k_contr].
+    out: fp32 buffer of n_rows*n_cols elements to write into (a gradient-arena view), else a fresh tensor."""
+    out = torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt_planes[0].device) if out is None else out.view(n_rows, n_cols)
     ops.gemm_bf16x3([dict(a=dyt_planes, w=xt_planes, out_f32=out)], n_rows, n_cols, k_contr, L.EPI_F32, ksplit=L.MAX_KSPLIT)
     return out
 
@@ -186,6 +187,57 @@ def _forward_heads(net, S, tok, pl, dp):
     return (cls_x4, seg, x4, cls_aux), S
 
 
+# ------------------------------------------------------------------ where the parameter gradients go
+class _DictSink(dict):
+    """Default: gradients are fresh tensors handed back to autograd (AccumulateGrad / DistributedDataParallel hooks)."""
+
+    def out(self, name):
+        return None
+
+    def put(self, name, g):
+        if g is not None:
+            self[name] = g
+
+
+class _ArenaSink:
+    """Gradients land in the student's flat arena (grad_arena.GradArena): big wgrad GEMMs write their view in place, the rest
+    is copied; autograd sees no parameter gradients.  `put` order == backward_order(net)."""
+
+    def __init__(self, arena):
+        self.arena = arena
+
+    def out(self, name):
+        return self.arena.out(name)
+
+    def put(self, name, g):
+        self.arena.put(name, g)
+
+
+def backward_order(net):
+    """Names of the trainable parameters of one student in the order `_backward` finishes their gradients."""
+    aux_idx = net.encoder.aux_block_index()
+    aux_final = aux_idx == E.DEPTH - 1
+    order = ["classifier.weight"]
+    if aux_final:
+        order.append("aux_classifier.weight")
+    order += ["decoder.conv8.weight", "decoder.conv7.weight", "decoder.conv6.weight", "encoder.norm.weight", "encoder.norm.bias"]
+    for i in reversed(range(E.DEPTH)):
+        bp = f"encoder.blocks.{i}."
+        if not aux_final and i == aux_idx:
+            order.append("aux_classifier.weight")
+        order += [bp + "mlp.fc2.bias", bp + "mlp.fc2.weight", bp + "mlp.fc1.bias", bp + "mlp.fc1.weight", bp + "norm2.weight",
+                  bp + "norm2.bias", bp + "attn.proj.bias", bp + "attn.proj.weight", bp + "attn.qkv.bias", bp + "attn.qkv.weight",
+                  bp + "norm1.weight", bp + "norm1.bias"]
+    order += ["encoder.patch_embed.proj.bias", "encoder.patch_embed.proj.weight", "encoder.cls_token"]
+    return order
+
+
+def make_grad_arena(net, chunk_elems=6 << 20, group=None):
+    from .grad_arena import GradArena
+    net._grad_arena = GradArena(trainable_parameters(net), backward_order(net), chunk_elems=chunk_elems, group=group)
+    return net._grad_arena
+
+
 # ------------------------------------------------------------------ backward
 def _gmp_bwd(x_rows, w, dlogits, argmax, dx, S):
     B, K = dlogits.shape
@@ -211,23 +263,23 @@ def _conv_bwd(d_out, act_planes, col_planes, wmat_t, S, cin, d_in, in_tokens, in
     return wgrad(dt, col_t, 512, 9 * cin, _pad64(Mp))
 
 
-def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
+def _backward(net, S, g_cls, g_seg, g_x4, g_aux, sink=None):
+    """-> sink (a dict name -> gradient by default).  Every trainable parameter is `put` exactly once, in backward_order()."""
     pl = net.planes()
     dp = _decoder_planes(net)
     dev = S.xn.device
     f32 = dict(dtype=torch.float32, device=dev)
     M, Mp, N, B, np_ = S.M, S.Mp, S.N, S.B, S.np
     Mpad = _pad64(M)
-    grads = {}
+    grads = sink if sink is not None else _DictSink()
     K = net.num_classes - 1
 
     d_xn = torch.zeros(M, D, **f32)          # grad wrt the final-normed tokens
     if g_x4 is not None:
         L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_x4)), L.ptr(d_xn), B, np_, D, D, N, 1, _st(dev)), "dupl_nchw_to_rows_add")
-    if g_cls is not None:
-        grads["classifier.weight"] = _gmp_bwd(S.xn, S.wc, g_cls, S.arg_c, d_xn, S).reshape(K, D, 1, 1)
-    if g_aux is not None and S.aux_is_final:
-        grads["aux_classifier.weight"] = _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_xn, S).reshape(K, D, 1, 1)
+    grads.put("classifier.weight", None if g_cls is None else _gmp_bwd(S.xn, S.wc, g_cls, S.arg_c, d_xn, S).reshape(K, D, 1, 1))
+    if S.aux_is_final:
+        grads.put("aux_classifier.weight", None if g_aux is None else _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_xn, S).reshape(K, D, 1, 1))
     if g_seg is not None:
         # conv8 (1x1): seg_rows = h7 @ W8^T
         Cn = net.num_classes
@@ -240,55 +292,66 @@ def _backward(net, S, g_cls, g_seg, g_x4, g_aux):
         d_h7 = dgrad(dsp, w8t, Mp, 512, Cp)
         h7t = transpose_planes(S.h7, Mp, 512)
         dw8 = wgrad(dst, h7t, Cp, 512, _pad64(Mp))
-        grads["decoder.conv8.weight"] = dw8[:Cn].reshape(Cn, 512, 1, 1).contiguous()
+        grads.put("decoder.conv8.weight", dw8[:Cn].reshape(Cn, 512, 1, 1))
         # conv7 + relu, conv6 + relu
         d_h6 = torch.empty(Mp, 512, **f32)
         dw7 = _conv_bwd(d_h7, S.h7, S.col7, dp.get_t("conv7"), S, 512, d_h6, 0, 0, False)
-        grads["decoder.conv7.weight"] = dw7.reshape(512, 3, 3, 512).permute(0, 3, 1, 2).contiguous()
+        grads.put("decoder.conv7.weight", dw7.reshape(512, 3, 3, 512).permute(0, 3, 1, 2))
         dw6 = _conv_bwd(d_h6, S.h6, S.col6, dp.get_t("conv6"), S, D, d_xn, N, 1, True)
-        grads["decoder.conv6.weight"] = dw6.reshape(512, 3, 3, D).permute(0, 3, 1, 2).contiguous()
+        grads.put("decoder.conv6.weight", dw6.reshape(512, 3, 3, D).permute(0, 3, 1, 2))
+    else:
+        for n in ("decoder.conv8.weight", "decoder.conv7.weight", "decoder.conv6.weight"):
+            grads.put(n, None)
 
     # final LayerNorm
     d_tok = torch.zeros(M, D, **f32)
     dg, db = layernorm_bwd(d_xn, S.tok_final, pl.vec("norm.weight"), d_tok)
-    grads["encoder.norm.weight"], grads["encoder.norm.bias"] = dg, db
+    grads.put("encoder.norm.weight", dg)
+    grads.put("encoder.norm.bias", db)
 
     scale = (D // E.HEADS) ** -0.5
     for i in reversed(range(E.DEPTH)):
         bp = f"blocks.{i}."
+        ep = "encoder." + bp
         b = S.blocks[i]
-        if g_aux is not None and not S.aux_is_final and i == S.aux_idx:
+        if not S.aux_is_final and i == S.aux_idx:
             # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
-            grads["aux_classifier.weight"] = _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_tok, S).reshape(K, D, 1, 1)
+            grads.put("aux_classifier.weight", None if g_aux is None else _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_tok, S).reshape(K, D, 1, 1))
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
-        dpl, dt, grads["encoder." + bp + "mlp.fc2.bias"] = split_transpose(d_tok, M, D, want_colsum=True)
-        grads["encoder." + bp + "mlp.fc2.weight"] = wgrad(dt, transpose_planes(b.hid, M, 4 * D), D, 4 * D, Mpad)
+        dpl, dt, cs = split_transpose(d_tok, M, D, want_colsum=True)
+        grads.put(ep + "mlp.fc2.bias", cs)
+        grads.put(ep + "mlp.fc2.weight", wgrad(dt, transpose_planes(b.hid, M, 4 * D), D, 4 * D, Mpad, out=grads.out(ep + "mlp.fc2.weight")))
         d_hid = dgrad(dpl, pl.plane_t(bp + "mlp.fc2.weight"), M, 4 * D, D)
         L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid), L.ptr(b.h_pre), d_hid.numel(), _st(dev)), "dupl_gelu_bwd")
-        dpl, dt, grads["encoder." + bp + "mlp.fc1.bias"] = split_transpose(d_hid, M, 4 * D, want_colsum=True)
-        grads["encoder." + bp + "mlp.fc1.weight"] = wgrad(dt, transpose_planes(b.xn2, M, D), 4 * D, D, Mpad)
+        dpl, dt, cs = split_transpose(d_hid, M, 4 * D, want_colsum=True)
+        grads.put(ep + "mlp.fc1.bias", cs)
+        grads.put(ep + "mlp.fc1.weight", wgrad(dt, transpose_planes(b.xn2, M, D), 4 * D, D, Mpad, out=grads.out(ep + "mlp.fc1.weight")))
         d_xn2 = dgrad(dpl, pl.plane_t(bp + "mlp.fc1.weight"), M, D, 4 * D)
         dg, db = layernorm_bwd(d_xn2, b.x_mid, pl.vec(bp + "norm2.weight"), d_tok)
-        grads["encoder." + bp + "norm2.weight"], grads["encoder." + bp + "norm2.bias"] = dg, db
+        grads.put(ep + "norm2.weight", dg)
+        grads.put(ep + "norm2.bias", db)
         # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-        dpl, dt, grads["encoder." + bp + "attn.proj.bias"] = split_transpose(d_tok, M, D, want_colsum=True)
-        grads["encoder." + bp + "attn.proj.weight"] = wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad)
+        dpl, dt, cs = split_transpose(d_tok, M, D, want_colsum=True)
+        grads.put(ep + "attn.proj.bias", cs)
+        grads.put(ep + "attn.proj.weight", wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad, out=grads.out(ep + "attn.proj.weight")))
         bfk = dict(dtype=torch.bfloat16, device=dev)
         d_att = (torch.empty(M, D, **bfk), torch.empty(M, D, **bfk))     # dO as split planes: operand of the attention backward
         ops.gemm_bf16x3([dict(a=dpl, w=pl.plane_t(bp + "attn.proj.weight"), out=d_att)], M, D, D, L.EPI_SPLIT)
         d_qkv = ops.attention_bwd(b.qkv, b.att, d_att, b.lse, B, N, E.HEADS, scale)
-        dpl, dt, grads["encoder." + bp + "attn.qkv.bias"] = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
-        grads["encoder." + bp + "attn.qkv.weight"] = wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad)
+        dpl, dt, cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
+        grads.put(ep + "attn.qkv.bias", cs)
+        grads.put(ep + "attn.qkv.weight", wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad, out=grads.out(ep + "attn.qkv.weight")))
         d_xn1 = dgrad(dpl, pl.plane_t(bp + "attn.qkv.weight"), M, D, 3 * D)
         dg, db = layernorm_bwd(d_xn1, b.x_in, pl.vec(bp + "norm1.weight"), d_tok)
-        grads["encoder." + bp + "norm1.weight"], grads["encoder." + bp + "norm1.bias"] = dg, db
+        grads.put(ep + "norm1.weight", dg)
+        grads.put(ep + "norm1.bias", db)
 
     # ---- patch embedding (pos_embed is frozen, vit.py:243)
-    _, dt, grads["encoder.patch_embed.proj.bias"] = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1,
-                                                                      want_colsum=True)
-    dwpe = wgrad(dt, transpose_planes(S.patch, Mp, D), D, D, _pad64(Mp))
-    grads["encoder.patch_embed.proj.weight"] = dwpe.reshape(D, 3, 16, 16)
-    grads["encoder.cls_token"] = colsum(d_tok, B, D, tokens=N, np_=1, first=0).reshape(1, 1, D)
+    _, dt, cs = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1, want_colsum=True)
+    grads.put("encoder.patch_embed.proj.bias", cs)
+    dwpe = wgrad(dt, transpose_planes(S.patch, Mp, D), D, D, _pad64(Mp), out=grads.out("encoder.patch_embed.proj.weight"))
+    grads.put("encoder.patch_embed.proj.weight", dwpe.reshape(D, 3, 16, 16))
+    grads.put("encoder.cls_token", colsum(d_tok, B, D, tokens=N, np_=1, first=0).reshape(1, 1, D))
     return grads
 
 
@@ -316,13 +379,21 @@ class StudentFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_cls, g_seg, g_x4, g_aux):
+        arena = getattr(ctx.net, "_grad_arena", None) if getattr(ctx.net, "_use_arena", False) else None
         with torch.no_grad():
+            if arena is not None:
+                # gradients go straight into the student's flat arena (and from there, chunk by chunk, into the
+                # overlapped all-reduce); the parameters' .grad are views of it, autograd gets nothing to accumulate
+                _backward(ctx.net, ctx.S, g_cls, g_seg, g_x4, g_aux, sink=_ArenaSink(arena))
+                arena.end_call()
+                ctx.S = None
+                return (None, None, None, *([None] * len(ctx.names)))
             grads = _backward(ctx.net, ctx.S, g_cls, g_seg, g_x4, g_aux)
         ctx.S = None
         out = []
         for n, shape in ctx.names:
             g = grads.get(n)
-            out.append(None if g is None else g.reshape(shape))
+            out.append(None if g is None else g.reshape(shape).contiguous())
         return (None, None, None, *out)
 
 

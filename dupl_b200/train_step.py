@@ -192,6 +192,29 @@ class TrainStep:
         if capture:                 # one graph for everything: the CAM half is captured inline, not replayed as a sub-graph
             for st in (self.pseudo, self._cam_only, self._cam_aux):
                 st.graph = False
+        # capture=True: the students' gradients live in flat arenas (grad_arena.GradArena) and, with several ranks, are averaged
+        # chunk by chunk WHILE the backward pass runs (what DistributedDataParallel's reducer does for the reference,
+        # train_final_voc.py:155,470-471) by a process group of its own whose NCCL kernels are kept to a few CTAs
+        self._arenas = None
+        self._comm_sms = 0
+        if capture:
+            import os
+            from . import train
+            net = model.module if hasattr(model, "module") else model
+            group = None
+            if self._world() > 1:
+                import torch.distributed as dist
+                ctas = int(os.environ.get("DUPL_NCCL_MAX_CTAS", "4"))
+                if ctas > 0 and dist.get_backend() == "nccl":
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = ctas
+                    opts.config.min_ctas = min(ctas, 4)
+                    group = dist.new_group(backend="nccl", pg_options=opts)
+                    # SMs the persistent GEMM grid leaves alone while gradient chunks are in flight (2 per NCCL CTA: a CTA
+                    # pair of the GEMM needs both SMs of its slot)
+                    self._comm_sms = int(os.environ.get("DUPL_COMM_SMS", str(2 * ctas)))
+            chunk = int(os.environ.get("DUPL_GRAD_CHUNK_ELEMS", str(6 << 20)))
+            self._arenas = [train.make_grad_arena(n, chunk_elems=chunk, group=group) for n in (net.branch1, net.branch2)]
         K = args.num_classes - 1
         self.thres_start = torch.ones(K, device=dev) * args.high_thre
         self.thres_target = torch.tensor(args.high_thres_target, dtype=torch.float32, device=dev)
@@ -202,6 +225,10 @@ class TrainStep:
         net = model.module if hasattr(model, "module") else model
         for n in (net.branch1, net.branch2):
             n._use_kept = self.reuse_forward
+            n._use_arena = self._arenas is not None
+        if self._arenas is not None:
+            for a in self._arenas:
+                a.begin_step(1 if inputs_aug is None else 2)   # phase C: the plain and the augmented view both reach every parameter
         if inputs_aug is None:
             res = model(inputs)
         else:
@@ -313,16 +340,23 @@ class TrainStep:
         import torch.distributed as dist
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
-    def _all_reduce_grads(self):
-        """train_final_voc.py:155,470: DistributedDataParallel averages the gradients over the ranks.  Same result here with ONE
-        NCCL all-reduce of the flattened gradients (732.7 MB fp32), issued on the current stream so that it can be captured
-        into the iteration's CUDA graph.  Every rank starts from the same parameters (same seed, as in the script)."""
-        import torch.distributed as dist
-        grads = [p.grad for g in self.optim.param_groups for p in g["params"] if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
+    def _backward(self, loss):
+        """loss.backward() with the gradients landing in the students' arenas; finished chunks are averaged over the ranks
+        while the rest of the backward pass runs (grad_arena.GradArena), the persistent GEMM grid leaving `_comm_sms` SMs to
+        the NCCL kernels meanwhile.  On return every .grad is final on the current stream."""
+        from . import _lib as L
+        limit = self._comm_sms if self._world() > 1 else 0
+        prev = 0
+        if limit > 0:
+            prev = L.lib().dupl_set_gemm_sm_limit(torch.cuda.get_device_properties(loss.device).multi_processor_count - limit)
+        try:
+            loss.backward()
+        finally:
+            if limit > 0:
+                L.lib().dupl_set_gemm_sm_limit(prev)
+        for a in self._arenas:
+            a.finish()
+            a.bind_grads()
 
     # ------------------------------------------------------------------ whole-iteration CUDA graph
     def _phase_key(self, n_iter, inputs, cls_label, inputs_aug):
@@ -380,10 +414,7 @@ class TrainStep:
                 with torch.cuda.stream(side):
                     for _ in range(2):
                         loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
-                        self.optim.zero_grad(set_to_none=True)
-                        loss.backward()
-                        if self._world() > 1:
-                            self._all_reduce_grads()
+                        self._backward(loss)
                         self.optim.step_captured()
                     with torch.no_grad():
                         for p, q in zip(params, saved_p):
@@ -398,14 +429,11 @@ class TrainStep:
                 torch.cuda.current_stream(dev).wait_stream(side)
                 self.optim.global_step = saved_step
                 del saved_p, saved_s
-                self.optim.zero_grad(set_to_none=True)
                 graph = torch.cuda.CUDAGraph()
                 multi = self._world() > 1
                 with torch.cuda.graph(graph, **(dict(capture_error_mode="thread_local") if multi else {})):
                     loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
-                    loss.backward()
-                    if multi:
-                        self._all_reduce_grads()
+                    self._backward(loss)
                     self.optim.step_captured()
                 st["graph"], st["loss"], st["parts"] = graph, loss.detach(), {k: v.detach() for k, v in parts.items()}
             self.optim.advance_schedule()

@@ -112,6 +112,12 @@ int dupl_gemm_bf16x3(const dupl_gemm_args* args, void* stream);
  * this shape on the current device (148 SMs assumed without a device).  No launch. */
 int dupl_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t groups, int32_t max_ksplit, int32_t* tile_n, int32_t* ksplit,
                    int32_t* work_items);
+/* Host-only: the persistent GEMM grid uses at most `sms` SMs from now on (0 = all).  The data-parallel training step
+ * (train_final_voc.py:155,470: DistributedDataParallel overlaps the gradient all-reduce with the backward pass) leaves a few
+ * SMs to the NCCL kernels that average finished gradient chunks while the remaining wgrad GEMMs run: a persistent grid
+ * that owns every SM would make the collective wait for a kernel boundary and then delay the next GEMM's statically
+ * assigned tiles.  Returns the previous limit. */
+int dupl_set_gemm_sm_limit(int32_t sms);
 
 /* LayerNorm over the last dim (biased variance, eps inside the sqrt; vit.py:146,152,256 with
  * eps=1e-6 from deit.py:100) of x[rows, cols] -> split bf16 planes and/or fp32 (either output may be

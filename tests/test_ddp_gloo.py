@@ -60,41 +60,62 @@ def test_student_function_under_ddp_world_size_2():
         assert out[0][1:] == out[1][1:]  # identical averaged gradients on both ranks
 
 
-def _worker_allreduce(rank, world, port, out):
+def _worker_arena(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from dupl_b200.train_step import TrainStep
-    ps = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
-    ps[0].grad = torch.full((3, 5), float(rank + 1))
-    ps[1].grad = torch.arange(7.0) * (rank + 1)
-    # ps[2] never received a gradient (like encoder.head.*): it must be skipped, not break the flattening
+    from dupl_b200.grad_arena import GradArena
+    names = ["head", "w2", "b2", "w1", "b1", "unused"]
+    shapes = [(3, 5), (40, 8), (40,), (64, 4), (64,), (2, 2)]
+    params = [(n, torch.nn.Parameter(torch.zeros(s))) for n, s in zip(names, shapes)]
+    arena = GradArena(params, names, chunk_elems=300, device=torch.device("cpu"))
+    assert len(arena.chunks) >= 2 and arena.flat.numel() % GradArena.ALIGN == 0
+    log = []
+    orig = arena._reduce
 
-    class _Opt:
-        param_groups = [{"params": ps[:2]}, {"params": ps[2:]}]
-
-    step = TrainStep.__new__(TrainStep)
-    step.optim = _Opt()
-    orig = dist.all_reduce
-
-    def avg_all_reduce(t, op=None):           # gloo has no AVG: emulate it (NCCL provides it natively)
-        orig(t, op=dist.ReduceOp.SUM)
-        t.div_(world)
-    dist.all_reduce = avg_all_reduce
-    step._all_reduce_grads()
-    out[rank] = (ps[0].grad.tolist(), ps[1].grad.tolist(), ps[2].grad is None)
+    def spy(lo, hi):
+        log.append((lo, hi))
+        orig(lo, hi)
+    arena._reduce = spy
+    for step_no in range(2):
+        # phase-C shape of a step: two backward calls reach the arena; the first writes, the second accumulates and releases
+        # finished chunks to the (asynchronous) all-reduce as it goes; "unused" never receives a gradient
+        arena.begin_step(2)
+        for call in range(2):
+            for n, s in zip(names[:-1], shapes[:-1]):
+                g = torch.full(s, float((rank + 1) * (call + 1) * (step_no + 1)))
+                if call == 0 and n == "w1":
+                    arena.out(n).copy_(g)            # in-place write into the view, like a wgrad GEMM epilogue
+                    g = arena.out(n)
+                elif call == 1 and n == "b2":
+                    g = None                         # this call contributes nothing to b2
+                arena.put(n, g)
+            arena.put("unused", None)
+            issued_mid = len(log)
+            arena.end_call()
+        assert issued_mid >= 1                       # chunks were released DURING the last call, before finish()
+        arena.finish()
+        arena.bind_grads()
+    p = dict(params)
+    out[rank] = (p["w2"].grad.flatten()[0].item(), p["b2"].grad.flatten()[0].item(), p["w1"].grad.flatten()[0].item(),
+                 p["unused"].grad is None, p["w1"].grad.data_ptr() == arena.views["w1"].data_ptr(), log)
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_in_graph_gradient_all_reduce_averages_over_ranks():
-    """TrainStep._all_reduce_grads (what the captured multi-rank step does instead of DDP's reducer): mean over ranks,
-    parameters without a gradient are skipped."""
+def test_gradient_arena_chunked_all_reduce_averages_over_ranks():
+    """grad_arena.GradArena (what the captured multi-rank step does instead of DDP's reducer): gradients written / accumulated
+    in place, finished chunks all-reduced in arena order while the backward pass is still running, mean over ranks,
+    parameters without a gradient keep .grad = None, .grad are views of the arena."""
     port = 29900 + os.getpid() % 90
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker_allreduce, args=(2, port, out), nprocs=2, join=True)
-        assert out[0] == out[1]
-        g0, g1, none2 = out[0]
-        assert none2 and all(abs(v - 1.5) < 1e-6 for row in g0 for v in row)
-        assert all(abs(v - 1.5 * i) < 1e-6 for i, v in enumerate(g1))
+        mp.spawn(_worker_arena, args=(2, port, out), nprocs=2, join=True)
+        assert out[0][:5] == out[1][:5]
+        w2, b2, w1, unused_none, is_view, log = out[0]
+        # second step: rank r contributes (r+1)*2*(1 + 2) to w2 / w1 and (r+1)*2*1 to b2; mean over ranks 1 and 2 = 1.5 x
+        assert abs(w2 - 1.5 * 6) < 1e-6 and abs(w1 - 1.5 * 6) < 1e-6 and abs(b2 - 1.5 * 2) < 1e-6
+        assert unused_none and is_view
+        assert out[0][5] == out[1][5]                     # every rank enqueued the same sequence of collectives
+        half = len(log) // 2
+        assert log[:half] == log[half:] and [lo for lo, _ in log[:half]] == sorted(lo for lo, _ in log[:half])
