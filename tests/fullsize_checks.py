@@ -157,8 +157,10 @@ def _oracle_train(num_classes, b, S, seed, n_iter, coco):
         loss, parts, labels = O.train_losses(Pg, x, cls, box, n_iter, cfg, thres_target=target)
         loss.backward()
         grads = {k: v.grad.clone() for k, v in Pg.items() if v.grad is not None}
+        with torch.no_grad():
+            fmaps = [O.network_forward(P, br, x, cfg["aux_layer"])[2] for br in (1, 2)]
         return dict(loss=loss.detach(), parts={k: torch.as_tensor(v).detach() for k, v in parts.items()},
-                    labels=labels, grads=grads)
+                    labels=labels, grads=grads, fmaps=fmaps)
     return _cached(f"train-{num_classes}-{b}-{S}-{seed}-{n_iter}-{coco}", run)
 
 
@@ -195,4 +197,22 @@ def train_step_errors(num_classes=21, b=1, S=448, seed=40, n_iter=3000, coco=Fal
     vals = sorted(errs.values())
     res["grad_median"] = vals[len(vals) // 2]
     res["grad_over_1e-3"] = sum(1 for v in vals if v >= 1e-3)
+    # Global max pooling (model_dupl.py:88-95) routes the classification gradient to the arg-max token of every channel: where
+    # two tokens tie within the forward tolerance the route is ill-defined and one flipped channel of 768 moves the gradient
+    # norm by ~sqrt(2/768) = 5 %.  Report the flips and how close the tie was in the oracle's own feature map.
+    with torch.no_grad():
+        out = m(x.cuda())
+    flips, worst_margin = 0, 0.0
+    for br in (1, 2):
+        fo = want["fmaps"][br - 1].flatten(2)                       # [b, 768, hw]
+        fg = out[f"branch{br}"][2].detach().cpu().flatten(2)
+        ao, ag = fo.argmax(2), fg.argmax(2)
+        diff = ao != ag
+        flips += int(diff.sum())
+        if diff.any():
+            top = fo.gather(2, ao[..., None])[..., 0]
+            alt = fo.gather(2, ag[..., None])[..., 0]
+            worst_margin = max(worst_margin, float(((top - alt)[diff] / fo.abs().max()).max()))
+        res[f"grad_worst_branch{br}"] = max(e for n, e in errs.items() if n.startswith(f"branch{br}."))
+    res["gmp_argmax_flips"], res["gmp_flip_margin_rel"] = flips, worst_margin
     return res

@@ -14,6 +14,17 @@ import fullsize_checks as FC
 pytestmark = pytest.mark.gpu
 
 
+def _assert_grads(r, bar=2e-3):
+    """Every gradient within `bar` — unless global max pooling saw a tie: the oracle's own top-2 tokens of a channel closer
+    than the 1e-4 forward tolerance route the gradient to different tokens (fullsize_checks.train_step_errors); then the
+    student without such a tie must still hold the bar and the tie must be that close."""
+    if r["grad_worst"] < bar:
+        return
+    assert r["gmp_argmax_flips"] > 0 and r["gmp_flip_margin_rel"] < 1e-4, r
+    assert min(r["grad_worst_branch1"], r["grad_worst_branch2"]) < bar, r
+    assert r["grad_median"] < bar, r
+
+
 @pytest.mark.parametrize("B,gh,gw", [(2, 14, 14), (2, 21, 21), (2, 28, 28), (1, 42, 42)])
 def test_attention_forward_and_backward_match_fp64_autograd(B, gh, gw):
     """N = 197 (224^2), 442 (336^2, the phase-C view), 785 (448^2), 1765 (672^2): 2..14 key tiles of 128, a partial last
@@ -62,7 +73,7 @@ def test_phase_b_losses_and_all_gradients_at_448_match_oracle_autograd():
     for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
         assert r[k] < 1e-3, r
     assert r["label_mismatch"] < 1e-3, r
-    assert r["grad_worst"] < 2e-3, r
+    _assert_grads(r)
     assert r["grad_median"] < 1e-3, r
 
 
@@ -73,7 +84,7 @@ def test_phase_b_batch2_at_448_matches_oracle_autograd():
     for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
         assert r[k] < 1e-3, r
     assert r["label_mismatch"] < 1e-3, r
-    assert r["grad_worst"] < 2e-3, r
+    _assert_grads(r)
 
 
 def test_coco_mscam_and_phase_b_at_448_match_oracle():
@@ -90,4 +101,9 @@ def test_coco_mscam_and_phase_b_at_448_match_oracle():
     for k in ("loss", "cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
         assert t[k] < 1e-3, t
     assert t["label_mismatch"] < 1e-3, t
-    assert t["grad_worst"] < 2e-3, t
+    _assert_grads(t)
+    # a second COCO batch (no max-pooling tie on this one): the plain bar
+    t2 = FC.train_step_errors(81, b=1, S=448, seed=52, n_iter=20000, coco=True)
+    print("coco_train448_seed52", json.dumps(t2))
+    assert t2["label_mismatch"] < 1e-3 and t2["loss"] < 1e-3, t2
+    _assert_grads(t2)
