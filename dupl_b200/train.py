@@ -375,6 +375,7 @@ class StudentFunction(torch.autograd.Function):
         outs, S = _forward(net, x, size, kept)
         ctx.net, ctx.S = net, S
         ctx.names = [(n, tuple(p.shape)) for n, p in trainable_parameters(net)]
+        ctx.n_inputs = len(params)
         return outs
 
     @staticmethod
@@ -387,7 +388,7 @@ class StudentFunction(torch.autograd.Function):
                 _backward(ctx.net, ctx.S, g_cls, g_seg, g_x4, g_aux, sink=_ArenaSink(arena))
                 arena.end_call()
                 ctx.S = None
-                return (None, None, None, *([None] * len(ctx.names)))
+                return (None, None, None, *([None] * ctx.n_inputs))
             grads = _backward(ctx.net, ctx.S, g_cls, g_seg, g_x4, g_aux)
         ctx.S = None
         out = []
@@ -398,5 +399,12 @@ class StudentFunction(torch.autograd.Function):
 
 
 def student_forward(net, x, size=None):
+    if getattr(net, "_use_arena", False) and getattr(net, "_grad_arena", None) is not None:
+        # arena mode: the backward writes the parameter gradients into the student's flat arena itself, so the parameters
+        # are not autograd inputs at all.  A fresh leaf per call keeps the outputs differentiable; being new, its
+        # AccumulateGrad node belongs to the stream of THIS forward (a node that survives from an earlier step would make a
+        # capturing stream wait for the stream it was created on).
+        anchor = torch.empty(0, device=x.device).requires_grad_()
+        return StudentFunction.apply(net, x, size, anchor)
     params = [p for _, p in trainable_parameters(net)]
     return StudentFunction.apply(net, x, size, *params)

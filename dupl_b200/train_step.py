@@ -429,9 +429,14 @@ class TrainStep:
                 torch.cuda.current_stream(dev).wait_stream(side)
                 self.optim.global_step = saved_step
                 del saved_p, saved_s
+                # the warm-up's autograd graph must be gone before capture: its AccumulateGrad nodes (kept alive through
+                # `loss`) belong to the warm-up, and autograd would make the capturing stream wait for their stream at the end
+                # of the captured backward ("dependency created on uncaptured work"); capturing on the warm-up's stream makes
+                # the two coincide in any case
+                del loss, parts
                 graph = torch.cuda.CUDAGraph()
                 multi = self._world() > 1
-                with torch.cuda.graph(graph, **(dict(capture_error_mode="thread_local") if multi else {})):
+                with torch.cuda.graph(graph, stream=side, **(dict(capture_error_mode="thread_local") if multi else {})):
                     loss, parts, _ = self.losses(st["x"], st["cls"], st["box"], n_iter, st["aug"])
                     self._backward(loss)
                     self.optim.step_captured()

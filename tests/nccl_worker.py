@@ -71,6 +71,7 @@ def main():
         elif p.grad is not None:
             missing.append("unexpected:" + n)
     chunks = [len(a.chunks) for a in step._arenas]
+    del loss
     # ---- 2. k captured steps, then every parameter bit-identical across ranks
     init = {n: p.detach().clone() for n, p in m2.named_parameters()}
     losses = []
