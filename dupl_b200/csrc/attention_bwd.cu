@@ -20,7 +20,7 @@ namespace dupl {
 constexpr int AB_THREADS = 128;
 constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
 constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
-constexpr int AB_SMEM = 4 * AB_T128 + 8 * AB_T64 + 1024 + 2048;  // 128 KB + alignment slack + barriers / per-tile statistics
+constexpr int AB_SMEM = 4 * AB_T128 + 3 * 4 * AB_T64 + 1024 + 2048;  // 64 KB resident tiles + 3 stages x 32 KB + alignment slack + barriers / per-tile statistics
 
 struct AttnBwdTcParams {
   CUtensorMap tm_qkv128_hi, tm_qkv128_lo, tm_qkv64_hi, tm_qkv64_lo;  // [M, 3*heads*64] planes, boxes of 128 / 64 rows
@@ -78,6 +78,13 @@ __device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
   }
 }
 
+// Both kernels are software-pipelined over the tile loop: the S / dP MMAs of tile j+1 are issued BEFORE the threads turn
+// tile j into dS (their accumulators are double-buffered in tensor memory, the K/V resp. Q/dO tiles triple-buffered in shared
+// memory), so the tensor pipe always has the next tile's products queued while the exp / split arithmetic of the current tile
+// runs; the only waits left on the critical path are for data that was issued a whole iteration earlier.  (The round-1
+// kernels ran MMA -> wait -> arithmetic -> wait -> MMA strictly in sequence: 26-29 % tensor-pipe activity.)
+constexpr int AB_STAGES = 3;
+
 // ------------------------------------------------------------------------------------------------ dQ
 // grid (q tiles of 128, heads, images)
 __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdTcParams p) {
@@ -85,14 +92,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                     // hi | lo, 128 rows
   uint8_t* sdO = sQ + 2 * AB_T128;        // hi | lo, 128 rows
-  uint8_t* sK = sdO + 2 * AB_T128;        // [2 stages][hi | lo], 64 rows
-  uint8_t* sV = sK + 4 * AB_T64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 4 * AB_T64);
+  uint8_t* sK = sdO + 2 * AB_T128;        // [AB_STAGES][hi | lo], 64 rows
+  uint8_t* sV = sK + AB_STAGES * 2 * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AB_STAGES * 2 * AB_T64);
   uint64_t* bar_q = bars;          // Q, dO landed
-  uint64_t* bar_kv = bars + 1;     // [2]
-  uint64_t* bar_s = bars + 3;      // S, dP complete
-  uint64_t* bar_d = bars + 4;      // dQ MMAs of this tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_kv = bars + 1;     // [AB_STAGES]
+  uint64_t* bar_s = bars + 4;      // [2] S, dP of tile j complete (buffer j & 1)
+  uint64_t* bar_d = bars + 6;      // [2] dQ MMAs of tile j complete (dS buffer j & 1, K/V stage j % 3 free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -101,12 +108,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   const int n_kv = (p.tokens + 63) / 64;
 
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -114,10 +121,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  constexpr int TM_S = 0, TM_DP = 64, TM_DQ = 128, TM_DS = 192;
+  constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DS = 320;  // S, dP, dS: two 64-column buffers each
 
   auto load_kv = [&](int j) {
-    const int st = j & 1;
+    const int st = j % AB_STAGES;
     mbar_arrive_expect_tx(&bar_kv[st], 4 * AB_T64);
     tma_load_2d(sK + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], hd + head * 64, row0 + j * 64);
     tma_load_2d(sK + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], hd + head * 64, row0 + j * 64);
@@ -130,8 +137,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
     tma_load_2d(sQ + AB_T128, &p.tm_qkv128_lo, bar_q, head * 64, row0 + qt * 128);
     tma_load_2d(sdO, &p.tm_do128_hi, bar_q, head * 64, row0 + qt * 128);
     tma_load_2d(sdO + AB_T128, &p.tm_do128_lo, bar_q, head * 64, row0 + qt * 128);
-    load_kv(0);
-    if (n_kv > 1) load_kv(1);
+    for (int j = 0; j < AB_STAGES && j < n_kv; ++j) load_kv(j);
   }
 
   const int qrow = qt * 128 + tid;
@@ -146,43 +152,57 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   const uint64_t dQh = umma_desc_sw128(smem_u32(sQ)), dQl = umma_desc_sw128(smem_u32(sQ + AB_T128));
   const uint64_t dOh = umma_desc_sw128(smem_u32(sdO)), dOl = umma_desc_sw128(smem_u32(sdO + AB_T128));
 
+  // warp 0 (all lanes, the issuing lane is elected inside the MMA wrappers): S = Q K^T and dP = dO V^T of tile j
+  auto issue_s_dp = [&](int j) {
+    const int st = j % AB_STAGES, b = j & 1;
+    mbar_wait(&bar_kv[st], static_cast<uint32_t>((j / AB_STAGES) & 1));
+    tc_fence_after();
+    const uint32_t k0 = smem_u32(sK + st * 2 * AB_T64), v0 = smem_u32(sV + st * 2 * AB_T64);
+    mma_ss_split(tm + TM_S + b * 64, dQh, dQl, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_kk, 32, false);
+    mma_ss_split(tm + TM_DP + b * 64, dOh, dOl, umma_desc_sw128(v0), umma_desc_sw128(v0 + AB_T64), idesc_kk, 32, false);
+    tc_commit(&bar_s[b]);
+  };
+  if (warp == 0) {
+    mbar_wait(bar_q, 0);
+    issue_s_dp(0);
+  }
+
   for (int j = 0; j < n_kv; ++j) {
-    const int st = j & 1;
-    const uint32_t ph = static_cast<uint32_t>(j & 1), kv_ph = static_cast<uint32_t>((j >> 1) & 1);
-    const uint64_t dKh = umma_desc_sw128(smem_u32(sK + st * 2 * AB_T64)), dKl = umma_desc_sw128(smem_u32(sK + st * 2 * AB_T64 + AB_T64));
-    const uint64_t dVh = umma_desc_sw128(smem_u32(sV + st * 2 * AB_T64)), dVl = umma_desc_sw128(smem_u32(sV + st * 2 * AB_T64 + AB_T64));
-    if (warp == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[st], kv_ph);
-      tc_fence_after();
-      mma_ss_split(tm + TM_S, dQh, dQl, dKh, dKl, idesc_kk, 32, false);   // S  = Q K^T
-      mma_ss_split(tm + TM_DP, dOh, dOl, dVh, dVl, idesc_kk, 32, false);  // dP = dO V^T
-      tc_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
+    const int b = j & 1;
+    if (warp == 0 && j + 1 < n_kv) issue_s_dp(j + 1);  // queued behind dQ(j-1): runs while the threads work on tile j
+    mbar_wait(&bar_s[b], static_cast<uint32_t>((j >> 1) & 1));
     tc_fence_after();
     float s[64], dp[64];
-    load_row64(tm + TM_S + lane_base, s);
-    load_row64(tm + TM_DP + lane_base, dp);
+    load_row64(tm + TM_S + b * 64 + lane_base, s);
+    load_row64(tm + TM_DP + b * 64 + lane_base, dp);
     const int kv_valid = p.tokens - j * 64;
 #pragma unroll
     for (int c = 0; c < 64; ++c) {
       const float pv = (q_ok && c < kv_valid) ? fast_exp2(fmaf(s[c], c2, -lse2)) : 0.0f;
       s[c] = p.scale * pv * (dp[c] - Di);  // dS
     }
-    store_split_row(tm + TM_DS + lane_base, s);
+    if (j >= 2) {  // dQ(j-2) read this dS buffer
+      mbar_wait(&bar_d[b], static_cast<uint32_t>(((j - 2) >> 1) & 1));
+      tc_fence_after();
+    }
+    store_split_row(tm + TM_DS + b * 64 + lane_base, s);
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      mma_ts_split(tm + TM_DQ, tm + TM_DS, dKh, dKl, idesc_mn, 2048, j > 0);  // dQ += dS K
-      tc_commit(bar_d);
+      const uint32_t k0 = smem_u32(sK + (j % AB_STAGES) * 2 * AB_T64);
+      mma_ts_split(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, 2048, j > 0);  // dQ += dS K
+      tc_commit(&bar_d[b]);
     }
-    mbar_wait(bar_d, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 2 < n_kv) load_kv(j + 2);
+    // tile j+2 goes into the stage of tile j-1, free once dQ(j-1) (issued a whole iteration ago) has completed
+    if (tid == 0 && j >= 1 && j + 2 < n_kv) {
+      mbar_wait(&bar_d[b ^ 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
+      load_kv(j + 2);
+    }
   }
+  mbar_wait(&bar_d[(n_kv - 1) & 1], static_cast<uint32_t>(((n_kv - 1) >> 1) & 1));
+  tc_fence_after();
 
   float dq[64];
   load_row64(tm + TM_DQ + lane_base, dq);
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tm, 256);
+    tmem_dealloc(tm, 512);
   }
 }
 
@@ -206,16 +226,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                   // hi | lo, 128 rows
   uint8_t* sV = sK + 2 * AB_T128;
-  uint8_t* sQ = sV + 2 * AB_T128;       // [2 stages][hi | lo], 64 rows
-  uint8_t* sdO = sQ + 4 * AB_T64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + 4 * AB_T64);
+  uint8_t* sQ = sV + 2 * AB_T128;       // [AB_STAGES][hi | lo], 64 rows
+  uint8_t* sdO = sQ + AB_STAGES * 2 * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + AB_STAGES * 2 * AB_T64);
   uint64_t* bar_kv = bars;
-  uint64_t* bar_q = bars + 1;  // [2]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_d = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  // per 64-query tile: lse * log2(e) (+inf on padding rows) | D, double-buffered; [stage][0:64 lse2, 64:128 D]
-  float* s_stat = reinterpret_cast<float*>(bars + 8);
+  uint64_t* bar_q = bars + 1;  // [AB_STAGES]
+  uint64_t* bar_s = bars + 4;  // [2] S^T, dP^T of tile i complete (buffer i & 1)
+  uint64_t* bar_d = bars + 6;  // dV / dK MMAs of a tile complete (P^T / dS^T buffer and Q/dO stage free): one phase per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // per 64-query tile: lse * log2(e) (+inf on padding rows) | D, double-buffered; [tile & 1][0:64 lse2, 64:128 D]
+  float* s_stat = reinterpret_cast<float*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int kt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   const int n_q = (p.tokens + 63) / 64;
 
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -237,10 +257,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  constexpr int TM_ST = 0, TM_DPT = 64, TM_DV = 128, TM_DK = 192, TM_PT = 256, TM_DST = 320;
+  // S^T, dP^T: two 64-column buffers each; P^T, dS^T (split: hi | lo) single-buffered — all 512 columns in use
+  constexpr int TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_PT = 384, TM_DST = 448;
 
   auto load_q = [&](int i) {
-    const int st = i & 1;
+    const int st = i % AB_STAGES;
     mbar_arrive_expect_tx(&bar_q[st], 4 * AB_T64);
     tma_load_2d(sQ + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_q[st], head * 64, row0 + i * 64);
     tma_load_2d(sQ + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_q[st], head * 64, row0 + i * 64);
@@ -253,8 +274,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     tma_load_2d(sK + AB_T128, &p.tm_qkv128_lo, bar_kv, hd + head * 64, row0 + kt * 128);
     tma_load_2d(sV, &p.tm_qkv128_hi, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
     tma_load_2d(sV + AB_T128, &p.tm_qkv128_lo, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
-    load_q(0);
-    if (n_q > 1) load_q(1);
+    for (int i = 0; i < AB_STAGES && i < n_q; ++i) load_q(i);
   }
 
   const int key = kt * 128 + tid;
@@ -276,26 +296,31 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   s_stat[tid] = fetch_stat(0);
   __syncthreads();
 
+  // warp 0: S^T = K Q^T and dP^T = V dO^T of query tile i
+  auto issue_s_dp = [&](int i) {
+    const int st = i % AB_STAGES, b = i & 1;
+    mbar_wait(&bar_q[st], static_cast<uint32_t>((i / AB_STAGES) & 1));
+    tc_fence_after();
+    const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
+    mma_ss_split(tm + TM_ST + b * 64, dKh, dKl, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_kk, 32, false);
+    mma_ss_split(tm + TM_DPT + b * 64, dVh, dVl, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_kk, 32, false);
+    tc_commit(&bar_s[b]);
+  };
+  if (warp == 0) {
+    mbar_wait(bar_kv, 0);
+    issue_s_dp(0);
+  }
+
   for (int i = 0; i < n_q; ++i) {
-    const int st = i & 1;
+    const int b = i & 1;
+    if (warp == 0 && i + 1 < n_q) issue_s_dp(i + 1);  // queued behind dV / dK of tile i-1
     const float stat_next = (i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
-    const uint32_t ph = static_cast<uint32_t>(i & 1), q_ph = static_cast<uint32_t>((i >> 1) & 1);
-    const uint64_t dQh = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64)), dQl = umma_desc_sw128(smem_u32(sQ + st * 2 * AB_T64 + AB_T64));
-    const uint64_t dOh = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64)), dOl = umma_desc_sw128(smem_u32(sdO + st * 2 * AB_T64 + AB_T64));
-    if (warp == 0) {
-      if (i == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(&bar_q[st], q_ph);
-      tc_fence_after();
-      mma_ss_split(tm + TM_ST, dKh, dKl, dQh, dQl, idesc_kk, 32, false);   // S^T  = K Q^T
-      mma_ss_split(tm + TM_DPT, dVh, dVl, dOh, dOl, idesc_kk, 32, false);  // dP^T = V dO^T
-      tc_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
+    mbar_wait(&bar_s[b], static_cast<uint32_t>((i >> 1) & 1));
     tc_fence_after();
     float s[64], dp[64];
-    load_row64(tm + TM_ST + lane_base, s);
-    load_row64(tm + TM_DPT + lane_base, dp);
-    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + st * 128);
+    load_row64(tm + TM_ST + b * 64 + lane_base, s);
+    load_row64(tm + TM_DPT + b * 64 + lane_base, dp);
+    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + b * 128);
     const float kscale = k_ok ? p.scale : 0.0f;
 #pragma unroll
     for (int c4 = 0; c4 < 16; ++c4) {
@@ -309,22 +334,28 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         dp[c] = kscale * pv * (dp[c] - d[e]);
       }
     }
+    if (i >= 1) {  // dV / dK of tile i-1 read the P^T / dS^T buffers and the Q / dO stage of tile i-1
+      mbar_wait(bar_d, static_cast<uint32_t>((i - 1) & 1));
+      tc_fence_after();
+      if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // into the stage tile i-1 has just released
+    }
     store_split_row(tm + TM_PT + lane_base, s);
     store_split_row(tm + TM_DST + lane_base, dp);
-    s_stat[(st ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier below, last turn)
+    s_stat[(b ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier of the last turn)
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      mma_ts_split(tm + TM_DV, tm + TM_PT, dOh, dOl, idesc_mn, 2048, i > 0);   // dV += P^T dO
-      mma_ts_split(tm + TM_DK, tm + TM_DST, dQh, dQl, idesc_mn, 2048, i > 0);  // dK += dS^T Q
+      const int st = i % AB_STAGES;
+      const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
+      mma_ts_split(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, 2048, i > 0);   // dV += P^T dO
+      mma_ts_split(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, 2048, i > 0);  // dK += dS^T Q
       tc_commit(bar_d);
     }
-    mbar_wait(bar_d, ph);
-    tc_fence_after();
-    if (tid == 0 && i + 2 < n_q) load_q(i + 2);
   }
+  mbar_wait(bar_d, static_cast<uint32_t>((n_q - 1) & 1));
+  tc_fence_after();
 
   float dv[64];
   load_row64(tm + TM_DV + lane_base, dv);
