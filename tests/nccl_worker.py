@@ -26,7 +26,14 @@ def batch(seed, b, S):
     return synth_images(b, S, S, seed=seed).cuda(), synth_cls_labels(b, 20, seed=seed).cuda(), synth_boxes(b, S, S, seed=seed)
 
 
+def mark(msg):
+    if os.environ.get("DUPL_TEST_TRACE"):
+        print(f"[rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("DUPL_TEST_WATCHDOG", "240")), exit=True)   # a hang names its line
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -51,15 +58,20 @@ def main():
         g = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
         expect = g if expect is None else {n: expect[n] + g[n] for n in g}
     expect = {n: v / world for n, v in expect.items()}
+    mark("expected gradients done")
     # ---- arena path on this rank's own batch (chunk size small enough for several chunks even at test size)
     os.environ.setdefault("DUPL_GRAD_CHUNK_ELEMS", str(4 << 20))
     m2 = model()
     opt = make_optimizer(m2, capturable=True)
     step = TrainStep(m2, opt, capture=True)
     x, cls, box = batch(100 + rank, b, S)
+    mark("arena step constructed")
     loss, _, _ = step.losses(x, cls, box, n_iter)
+    mark("arena losses done")
     step._backward(loss)
+    mark("arena backward issued")
     torch.cuda.synchronize()
+    mark("arena backward complete")
     worst, missing = 0.0, []
     for n, p in m2.named_parameters():
         if n in expect:
@@ -78,6 +90,7 @@ def main():
     for i in range(3):
         l, _ = step(x, cls, box, n_iter + i)
         losses.append(float(l))
+        mark(f"captured step {i} done")
     torch.cuda.synchronize()
     chk = torch.stack([p.detach().contiguous().view(torch.int32).to(torch.int64).sum() for p in m2.parameters()])
     lo, hi = chk.clone(), chk.clone()

@@ -18,7 +18,7 @@ def test_arena_all_reduce_matches_mean_of_rank_gradients_and_replicas_stay_in_sy
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29655", os.path.join(ROOT, "tests", "nccl_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DUPL_TEST_SIZE=str(size)))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=400, env=dict(os.environ, DUPL_TEST_SIZE=str(size)))
     assert out.returncode == 0, out.stderr[-3000:]
     r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     print(json.dumps(r))
