@@ -17,7 +17,12 @@
 
 namespace dupl {
 
-constexpr int AB_THREADS = 128;
+// 16 warps: warp w owns TMEM lane quadrant w % 4 (rows 32 (w % 4) .. +31 of the tile) and column group w / 4 (16 of the 64
+// columns).  With 4 warps (one per scheduler, a whole 64-column row per thread) the exp / split arithmetic issued one
+// instruction every 5 cycles (ncu: 1.0 active warp per scheduler, 0.2 eligible; 25 % tensor-pipe activity): the kernels were
+// bound by the latency of a single warp's dependent instruction stream, not by the MMAs.
+constexpr int AB_GROUPS = 4, AB_COLS = 64 / AB_GROUPS;
+constexpr int AB_THREADS = 128 * AB_GROUPS;
 constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
 constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
 constexpr int AB_SMEM = 4 * AB_T128 + 3 * 4 * AB_T64 + 1024 + 2048;  // 64 KB resident tiles + 3 stages x 32 KB + alignment slack + barriers / per-tile statistics
@@ -64,6 +69,22 @@ __device__ __forceinline__ void store_split_row(uint32_t taddr, const float (&v)
   for (int c = 0; c < 64; c += 2) split2_bf16(v[c], v[c + 1], hi[c >> 1], lo[c >> 1]);
   tmem_st_32x32(taddr, hi);
   tmem_st_32x32(taddr + 32, lo);
+}
+// 16 fp32 columns of a row -> 8 packed bf16x2 words in the hi plane (columns [0,32) of the operand) and 8 in the lo plane
+// (+32); `taddr` already points at this thread's word offset (8 * column group) of the hi plane.
+__device__ __forceinline__ void store_split_cols16(uint32_t taddr, const float (&v)[AB_COLS]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) split2_bf16(v[c], v[c + 1], hi[c >> 1], lo[c >> 1]);
+  tmem_st_32x8(taddr, hi);
+  tmem_st_32x8(taddr + 32, lo);
+}
+__device__ __forceinline__ void load_cols16(uint32_t taddr, float (&v)[AB_COLS]) {
+  uint32_t a[16];
+  tmem_ld_32x16(taddr, a);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(a[c]);
 }
 
 __device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
@@ -120,7 +141,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int grp = warp >> 2;                                                // column group of this thread
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
   constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DS = 320;  // S, dP, dS: two 64-column buffers each
 
   auto load_kv = [&](int j) {
@@ -140,7 +162,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
     for (int j = 0; j < AB_STAGES && j < n_kv; ++j) load_kv(j);
   }
 
-  const int qrow = qt * 128 + tid;
+  const int qrow = qt * 128 + (tid & 127);
   const bool q_ok = qrow < p.tokens;
   const long grow = static_cast<long>(row0) + qrow;
   const float lse2 = q_ok ? p.lse[grow * p.heads + head] * 1.44269504088896340736f : 0.0f;
@@ -172,12 +194,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
     if (warp == 0 && j + 1 < n_kv) issue_s_dp(j + 1);  // queued behind dQ(j-1): runs while the threads work on tile j
     mbar_wait(&bar_s[b], static_cast<uint32_t>((j >> 1) & 1));
     tc_fence_after();
-    float s[64], dp[64];
-    load_row64(tm + TM_S + b * 64 + lane_base, s);
-    load_row64(tm + TM_DP + b * 64 + lane_base, dp);
-    const int kv_valid = p.tokens - j * 64;
+    float s[AB_COLS], dp[AB_COLS];
+    load_cols16(tm + TM_S + b * 64 + grp * AB_COLS + lane_base, s);
+    load_cols16(tm + TM_DP + b * 64 + grp * AB_COLS + lane_base, dp);
+    const int kv_valid = p.tokens - j * 64 - grp * AB_COLS;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
+    for (int c = 0; c < AB_COLS; ++c) {
       const float pv = (q_ok && c < kv_valid) ? fast_exp2(fmaf(s[c], c2, -lse2)) : 0.0f;
       s[c] = p.scale * pv * (dp[c] - Di);  // dS
     }
@@ -185,7 +207,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
       mbar_wait(&bar_d[b], static_cast<uint32_t>(((j - 2) >> 1) & 1));
       tc_fence_after();
     }
-    store_split_row(tm + TM_DS + b * 64 + lane_base, s);
+    store_split_cols16(tm + TM_DS + b * 64 + grp * (AB_COLS / 2) + lane_base, s);
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
@@ -204,12 +226,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   mbar_wait(&bar_d[(n_kv - 1) & 1], static_cast<uint32_t>(((n_kv - 1) >> 1) & 1));
   tc_fence_after();
 
-  float dq[64];
-  load_row64(tm + TM_DQ + lane_base, dq);
+  float dq[AB_COLS];
+  load_cols16(tm + TM_DQ + grp * AB_COLS + lane_base, dq);
   if (q_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + grow * 3 * hd + head * 64);
+    float4* o = reinterpret_cast<float4*>(p.dqkv + grow * 3 * hd + head * 64 + grp * AB_COLS);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
+    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
   }
   tc_fence_before();
   __syncthreads();
@@ -256,7 +278,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int grp = warp >> 2;                                                // column (= query) group of this thread
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
   // S^T, dP^T: two 64-column buffers each; P^T, dS^T (split: hi | lo) single-buffered — all 512 columns in use
   constexpr int TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_PT = 384, TM_DST = 448;
 
@@ -277,7 +300,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     for (int i = 0; i < AB_STAGES && i < n_q; ++i) load_q(i);
   }
 
-  const int key = kt * 128 + tid;
+  const int key = kt * 128 + (tid & 127);
   const bool k_ok = key < p.tokens;
   const float c2 = p.scale * 1.44269504088896340736f;
   constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);
@@ -293,7 +316,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     const long r = (static_cast<long>(row0) + q) * p.heads + head;
     return tid < 64 ? p.lse[r] * 1.44269504088896340736f : p.Dvec[r];
   };
-  s_stat[tid] = fetch_stat(0);
+  if (tid < 128) s_stat[tid] = fetch_stat(0);
   __syncthreads();
 
   // warp 0: S^T = K Q^T and dP^T = V dO^T of query tile i
@@ -314,16 +337,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   for (int i = 0; i < n_q; ++i) {
     const int b = i & 1;
     if (warp == 0 && i + 1 < n_q) issue_s_dp(i + 1);  // queued behind dV / dK of tile i-1
-    const float stat_next = (i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
+    const float stat_next = (tid < 128 && i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
     mbar_wait(&bar_s[b], static_cast<uint32_t>((i >> 1) & 1));
     tc_fence_after();
-    float s[64], dp[64];
-    load_row64(tm + TM_ST + b * 64 + lane_base, s);
-    load_row64(tm + TM_DPT + b * 64 + lane_base, dp);
-    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + b * 128);
+    float s[AB_COLS], dp[AB_COLS];
+    load_cols16(tm + TM_ST + b * 64 + grp * AB_COLS + lane_base, s);
+    load_cols16(tm + TM_DPT + b * 64 + grp * AB_COLS + lane_base, dp);
+    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + b * 128 + grp * AB_COLS);
     const float kscale = k_ok ? p.scale : 0.0f;
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
+    for (int c4 = 0; c4 < AB_COLS / 4; ++c4) {
       const float4 l4 = stat4[c4], d4 = stat4[16 + c4];
       const float l[4] = {l4.x, l4.y, l4.z, l4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -339,9 +362,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       tc_fence_after();
       if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // into the stage tile i-1 has just released
     }
-    store_split_row(tm + TM_PT + lane_base, s);
-    store_split_row(tm + TM_DST + lane_base, dp);
-    s_stat[(b ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier of the last turn)
+    store_split_cols16(tm + TM_PT + grp * (AB_COLS / 2) + lane_base, s);
+    store_split_cols16(tm + TM_DST + grp * (AB_COLS / 2) + lane_base, dp);
+    if (tid < 128) s_stat[(b ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier of the last turn)
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
@@ -357,18 +380,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   mbar_wait(bar_d, static_cast<uint32_t>((n_q - 1) & 1));
   tc_fence_after();
 
-  float dv[64];
-  load_row64(tm + TM_DV + lane_base, dv);
+  float dv[AB_COLS];
+  load_cols16(tm + TM_DV + grp * AB_COLS + lane_base, dv);
   if (k_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + 2 * hd + head * 64);
+    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + 2 * hd + head * 64 + grp * AB_COLS);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
   }
-  load_row64(tm + TM_DK + lane_base, dv);
+  load_cols16(tm + TM_DK + grp * AB_COLS + lane_base, dv);
   if (k_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + hd + head * 64);
+    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + hd + head * 64 + grp * AB_COLS);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
   }
   tc_fence_before();
   __syncthreads();
