@@ -21,8 +21,12 @@ namespace dupl {
 // columns).  With 4 warps (one per scheduler, a whole 64-column row per thread) the exp / split arithmetic issued one
 // instruction every 5 cycles (ncu: 1.0 active warp per scheduler, 0.2 eligible; 25 % tensor-pipe activity): the kernels were
 // bound by the latency of a single warp's dependent instruction stream, not by the MMAs.
+// A 17th warp issues every TMA load and every MMA and does no arithmetic: when warp 0 did both, its own instruction stream
+// (~650 instructions per tile at one-warp issue rate) was the critical path and the other warps spent half their cycles at the
+// CTA barrier waiting for it.  The arithmetic warps never synchronise with each other in the dQ kernel (mbarriers only).
 constexpr int AB_GROUPS = 4, AB_COLS = 64 / AB_GROUPS;
-constexpr int AB_THREADS = 128 * AB_GROUPS;
+constexpr int AB_MATH_THREADS = 128 * AB_GROUPS, AB_MATH_WARPS = AB_MATH_THREADS / 32;
+constexpr int AB_THREADS = AB_MATH_THREADS + 32;
 constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
 constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
 constexpr int AB_SMEM = 4 * AB_T128 + 3 * 4 * AB_T64 + 1024 + 2048;  // 64 KB resident tiles + 3 stages x 32 KB + alignment slack + barriers / per-tile statistics
@@ -79,6 +83,14 @@ __device__ __forceinline__ void store_split_cols16(uint32_t taddr, const float (
   tmem_st_32x8(taddr, hi);
   tmem_st_32x8(taddr + 32, lo);
 }
+// arrive of one warp on an mbarrier that counts warps: all lanes' preceding tcgen05 stores are complete and fenced
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  tc_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void math_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AB_MATH_THREADS) : "memory"); }
 __device__ __forceinline__ void load_cols16(uint32_t taddr, float (&v)[AB_COLS]) {
   uint32_t a[16];
   tmem_ld_32x16(taddr, a);
@@ -122,14 +134,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   uint64_t* bar_d = bars + 6;      // [2] dQ MMAs of tile j complete (dS buffer j & 1, K/V stage j % 3 free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int hd = p.heads * 64;
   const int row0 = p.row_offset + img * p.tokens;
   const int n_kv = (p.tokens + 63) / 64;
+  uint64_t* bar_ds = bars + 8;     // [2] dS of tile j stored by all arithmetic warps (count = AB_MATH_WARPS)
 
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_ds[0], AB_MATH_WARPS);
+    mbar_init(&bar_ds[1], AB_MATH_WARPS);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -141,97 +156,99 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const int grp = warp >> 2;                                                // column group of this thread
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
   constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DS = 320;  // S, dP, dS: two 64-column buffers each
 
-  auto load_kv = [&](int j) {
-    const int st = j % AB_STAGES;
-    mbar_arrive_expect_tx(&bar_kv[st], 4 * AB_T64);
-    tma_load_2d(sK + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], hd + head * 64, row0 + j * 64);
-    tma_load_2d(sK + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], hd + head * 64, row0 + j * 64);
-    tma_load_2d(sV + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
-    tma_load_2d(sV + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 4 * AB_T128);
-    tma_load_2d(sQ, &p.tm_qkv128_hi, bar_q, head * 64, row0 + qt * 128);
-    tma_load_2d(sQ + AB_T128, &p.tm_qkv128_lo, bar_q, head * 64, row0 + qt * 128);
-    tma_load_2d(sdO, &p.tm_do128_hi, bar_q, head * 64, row0 + qt * 128);
-    tma_load_2d(sdO + AB_T128, &p.tm_do128_lo, bar_q, head * 64, row0 + qt * 128);
-    for (int j = 0; j < AB_STAGES && j < n_kv; ++j) load_kv(j);
-  }
-
-  const int qrow = qt * 128 + (tid & 127);
-  const bool q_ok = qrow < p.tokens;
-  const long grow = static_cast<long>(row0) + qrow;
-  const float lse2 = q_ok ? p.lse[grow * p.heads + head] * 1.44269504088896340736f : 0.0f;
-  const float Di = q_ok ? p.Dvec[grow * p.heads + head] : 0.0f;
-  const float c2 = p.scale * 1.44269504088896340736f;
-
-  constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);  // B K-major
-  constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);  // B MN-major
-  const uint64_t dQh = umma_desc_sw128(smem_u32(sQ)), dQl = umma_desc_sw128(smem_u32(sQ + AB_T128));
-  const uint64_t dOh = umma_desc_sw128(smem_u32(sdO)), dOl = umma_desc_sw128(smem_u32(sdO + AB_T128));
-
-  // warp 0 (all lanes, the issuing lane is elected inside the MMA wrappers): S = Q K^T and dP = dO V^T of tile j
-  auto issue_s_dp = [&](int j) {
-    const int st = j % AB_STAGES, b = j & 1;
-    mbar_wait(&bar_kv[st], static_cast<uint32_t>((j / AB_STAGES) & 1));
-    tc_fence_after();
-    const uint32_t k0 = smem_u32(sK + st * 2 * AB_T64), v0 = smem_u32(sV + st * 2 * AB_T64);
-    mma_ss_split(tm + TM_S + b * 64, dQh, dQl, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_kk, 32, false);
-    mma_ss_split(tm + TM_DP + b * 64, dOh, dOl, umma_desc_sw128(v0), umma_desc_sw128(v0 + AB_T64), idesc_kk, 32, false);
-    tc_commit(&bar_s[b]);
-  };
-  if (warp == 0) {
+  if (warp == AB_MATH_WARPS) {
+    // ------------------------------------------------------------------ TMA + MMA warp
+    auto load_kv = [&](int j) {
+      const int st = j % AB_STAGES;
+      mbar_arrive_expect_tx(&bar_kv[st], 4 * AB_T64);
+      tma_load_2d(sK + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], hd + head * 64, row0 + j * 64);
+      tma_load_2d(sK + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], hd + head * 64, row0 + j * 64);
+      tma_load_2d(sV + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
+      tma_load_2d(sV + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_kv[st], 2 * hd + head * 64, row0 + j * 64);
+    };
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, 4 * AB_T128);
+      tma_load_2d(sQ, &p.tm_qkv128_hi, bar_q, head * 64, row0 + qt * 128);
+      tma_load_2d(sQ + AB_T128, &p.tm_qkv128_lo, bar_q, head * 64, row0 + qt * 128);
+      tma_load_2d(sdO, &p.tm_do128_hi, bar_q, head * 64, row0 + qt * 128);
+      tma_load_2d(sdO + AB_T128, &p.tm_do128_lo, bar_q, head * 64, row0 + qt * 128);
+      for (int j = 0; j < AB_STAGES && j < n_kv; ++j) load_kv(j);
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);  // B K-major
+    constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);  // B MN-major
+    const uint64_t dQh = umma_desc_sw128(smem_u32(sQ)), dQl = umma_desc_sw128(smem_u32(sQ + AB_T128));
+    const uint64_t dOh = umma_desc_sw128(smem_u32(sdO)), dOl = umma_desc_sw128(smem_u32(sdO + AB_T128));
+    // all lanes; the issuing lane is elected inside the MMA wrappers: S = Q K^T and dP = dO V^T of tile j
+    auto issue_s_dp = [&](int j) {
+      const int st = j % AB_STAGES, b = j & 1;
+      mbar_wait(&bar_kv[st], static_cast<uint32_t>((j / AB_STAGES) & 1));
+      tc_fence_after();
+      const uint32_t k0 = smem_u32(sK + st * 2 * AB_T64), v0 = smem_u32(sV + st * 2 * AB_T64);
+      mma_ss_split(tm + TM_S + b * 64, dQh, dQl, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_kk, 32, false);
+      mma_ss_split(tm + TM_DP + b * 64, dOh, dOl, umma_desc_sw128(v0), umma_desc_sw128(v0 + AB_T64), idesc_kk, 32, false);
+      tc_commit(&bar_s[b]);
+    };
     mbar_wait(bar_q, 0);
     issue_s_dp(0);
-  }
-
-  for (int j = 0; j < n_kv; ++j) {
-    const int b = j & 1;
-    if (warp == 0 && j + 1 < n_kv) issue_s_dp(j + 1);  // queued behind dQ(j-1): runs while the threads work on tile j
-    mbar_wait(&bar_s[b], static_cast<uint32_t>((j >> 1) & 1));
-    tc_fence_after();
-    float s[AB_COLS], dp[AB_COLS];
-    load_cols16(tm + TM_S + b * 64 + grp * AB_COLS + lane_base, s);
-    load_cols16(tm + TM_DP + b * 64 + grp * AB_COLS + lane_base, dp);
-    const int kv_valid = p.tokens - j * 64 - grp * AB_COLS;
-#pragma unroll
-    for (int c = 0; c < AB_COLS; ++c) {
-      const float pv = (q_ok && c < kv_valid) ? fast_exp2(fmaf(s[c], c2, -lse2)) : 0.0f;
-      s[c] = p.scale * pv * (dp[c] - Di);  // dS
-    }
-    if (j >= 2) {  // dQ(j-2) read this dS buffer
-      mbar_wait(&bar_d[b], static_cast<uint32_t>(((j - 2) >> 1) & 1));
-      tc_fence_after();
-    }
-    store_split_cols16(tm + TM_DS + b * 64 + grp * (AB_COLS / 2) + lane_base, s);
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1;
+      // S / dP of tile j+1 overwrite the buffers of tile j-1: the arithmetic warps are done with those (their bar_ds arrival
+      // for tile j-1 was waited for below, one turn ago)
+      if (j + 1 < n_kv) issue_s_dp(j + 1);
+      mbar_wait(&bar_ds[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
       const uint32_t k0 = smem_u32(sK + (j % AB_STAGES) * 2 * AB_T64);
       mma_ts_split(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, 2048, j > 0);  // dQ += dS K
       tc_commit(&bar_d[b]);
+      // tile j+2 goes into the stage of tile j-1, free once dQ(j-1) (issued a whole turn ago) has completed
+      if (j >= 1 && j + 2 < n_kv) {
+        mbar_wait(&bar_d[b ^ 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
+        if (lane == 0) load_kv(j + 2);
+        __syncwarp();
+      }
     }
-    // tile j+2 goes into the stage of tile j-1, free once dQ(j-1) (issued a whole iteration ago) has completed
-    if (tid == 0 && j >= 1 && j + 2 < n_kv) {
-      mbar_wait(&bar_d[b ^ 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
-      load_kv(j + 2);
-    }
-  }
-  mbar_wait(&bar_d[(n_kv - 1) & 1], static_cast<uint32_t>(((n_kv - 1) >> 1) & 1));
-  tc_fence_after();
-
-  float dq[AB_COLS];
-  load_cols16(tm + TM_DQ + grp * AB_COLS + lane_base, dq);
-  if (q_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + grow * 3 * hd + head * 64 + grp * AB_COLS);
+  } else {
+    // ------------------------------------------------------------------ arithmetic warps: thread = (row, 16-column group)
+    const int grp = warp >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int qrow = qt * 128 + (tid & 127);
+    const bool q_ok = qrow < p.tokens;
+    const long grow = static_cast<long>(row0) + qrow;
+    const float lse2 = q_ok ? p.lse[grow * p.heads + head] * 1.44269504088896340736f : 0.0f;
+    const float Di = q_ok ? p.Dvec[grow * p.heads + head] : 0.0f;
+    const float c2 = p.scale * 1.44269504088896340736f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1;
+      mbar_wait(&bar_s[b], static_cast<uint32_t>((j >> 1) & 1));
+      tc_fence_after();
+      float s[AB_COLS], dp[AB_COLS];
+      load_cols16(tm + TM_S + b * 64 + grp * AB_COLS + lane_base, s);
+      load_cols16(tm + TM_DP + b * 64 + grp * AB_COLS + lane_base, dp);
+      const int kv_valid = p.tokens - j * 64 - grp * AB_COLS;
 #pragma unroll
-    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
+      for (int c = 0; c < AB_COLS; ++c) {
+        const float pv = (q_ok && c < kv_valid) ? fast_exp2(fmaf(s[c], c2, -lse2)) : 0.0f;
+        s[c] = p.scale * pv * (dp[c] - Di);  // dS
+      }
+      if (j >= 2) {  // dQ(j-2) read this dS buffer
+        mbar_wait(&bar_d[b], static_cast<uint32_t>(((j - 2) >> 1) & 1));
+        tc_fence_after();
+      }
+      store_split_cols16(tm + TM_DS + b * 64 + grp * (AB_COLS / 2) + lane_base, s);
+      warp_arrive(&bar_ds[b], lane);
+    }
+    mbar_wait(&bar_d[(n_kv - 1) & 1], static_cast<uint32_t>(((n_kv - 1) >> 1) & 1));
+    tc_fence_after();
+    float dq[AB_COLS];
+    load_cols16(tm + TM_DQ + grp * AB_COLS + lane_base, dq);
+    if (q_ok) {
+      float4* o = reinterpret_cast<float4*>(p.dqkv + grow * 3 * hd + head * 64 + grp * AB_COLS);
+#pragma unroll
+      for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -259,14 +276,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   // per 64-query tile: lse * log2(e) (+inf on padding rows) | D, double-buffered; [tile & 1][0:64 lse2, 64:128 D]
   float* s_stat = reinterpret_cast<float*>(bars + 12);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int hd = p.heads * 64;
   const int row0 = p.row_offset + img * p.tokens;
   const int n_q = (p.tokens + 63) / 64;
+  uint64_t* bar_ds = bars + 7;  // P^T / dS^T of a tile stored by all arithmetic warps (count = AB_MATH_WARPS): one phase per tile
 
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_ds, AB_MATH_WARPS);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -278,120 +297,128 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const int grp = warp >> 2;                                                // column (= query) group of this thread
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
   // S^T, dP^T: two 64-column buffers each; P^T, dS^T (split: hi | lo) single-buffered — all 512 columns in use
   constexpr int TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_PT = 384, TM_DST = 448;
 
-  auto load_q = [&](int i) {
-    const int st = i % AB_STAGES;
-    mbar_arrive_expect_tx(&bar_q[st], 4 * AB_T64);
-    tma_load_2d(sQ + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_q[st], head * 64, row0 + i * 64);
-    tma_load_2d(sQ + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_q[st], head * 64, row0 + i * 64);
-    tma_load_2d(sdO + st * 2 * AB_T64, &p.tm_do64_hi, &bar_q[st], head * 64, row0 + i * 64);
-    tma_load_2d(sdO + st * 2 * AB_T64 + AB_T64, &p.tm_do64_lo, &bar_q[st], head * 64, row0 + i * 64);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 4 * AB_T128);
-    tma_load_2d(sK, &p.tm_qkv128_hi, bar_kv, hd + head * 64, row0 + kt * 128);
-    tma_load_2d(sK + AB_T128, &p.tm_qkv128_lo, bar_kv, hd + head * 64, row0 + kt * 128);
-    tma_load_2d(sV, &p.tm_qkv128_hi, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
-    tma_load_2d(sV + AB_T128, &p.tm_qkv128_lo, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
-    for (int i = 0; i < AB_STAGES && i < n_q; ++i) load_q(i);
-  }
-
-  const int key = kt * 128 + (tid & 127);
-  const bool k_ok = key < p.tokens;
-  const float c2 = p.scale * 1.44269504088896340736f;
-  constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);
-  constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);
-  const uint64_t dKh = umma_desc_sw128(smem_u32(sK)), dKl = umma_desc_sw128(smem_u32(sK + AB_T128));
-  const uint64_t dVh = umma_desc_sw128(smem_u32(sV)), dVl = umma_desc_sw128(smem_u32(sV + AB_T128));
-
-  // thread t < 64 fetches lse of query t of a tile, thread 64 + t its D (one coalesced-ish load per thread and tile,
-  // issued one tile ahead; the tile loop then reads them as shared-memory broadcasts)
-  auto fetch_stat = [&](int i) -> float {
-    const int q = i * 64 + (tid & 63);
-    if (q >= p.tokens) return tid < 64 ? __int_as_float(0x7f800000) : 0.0f;
-    const long r = (static_cast<long>(row0) + q) * p.heads + head;
-    return tid < 64 ? p.lse[r] * 1.44269504088896340736f : p.Dvec[r];
-  };
-  if (tid < 128) s_stat[tid] = fetch_stat(0);
-  __syncthreads();
-
-  // warp 0: S^T = K Q^T and dP^T = V dO^T of query tile i
-  auto issue_s_dp = [&](int i) {
-    const int st = i % AB_STAGES, b = i & 1;
-    mbar_wait(&bar_q[st], static_cast<uint32_t>((i / AB_STAGES) & 1));
-    tc_fence_after();
-    const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
-    mma_ss_split(tm + TM_ST + b * 64, dKh, dKl, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_kk, 32, false);
-    mma_ss_split(tm + TM_DPT + b * 64, dVh, dVl, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_kk, 32, false);
-    tc_commit(&bar_s[b]);
-  };
-  if (warp == 0) {
+  if (warp == AB_MATH_WARPS) {
+    // ------------------------------------------------------------------ TMA + MMA warp
+    auto load_q = [&](int i) {
+      const int st = i % AB_STAGES;
+      mbar_arrive_expect_tx(&bar_q[st], 4 * AB_T64);
+      tma_load_2d(sQ + st * 2 * AB_T64, &p.tm_qkv64_hi, &bar_q[st], head * 64, row0 + i * 64);
+      tma_load_2d(sQ + st * 2 * AB_T64 + AB_T64, &p.tm_qkv64_lo, &bar_q[st], head * 64, row0 + i * 64);
+      tma_load_2d(sdO + st * 2 * AB_T64, &p.tm_do64_hi, &bar_q[st], head * 64, row0 + i * 64);
+      tma_load_2d(sdO + st * 2 * AB_T64 + AB_T64, &p.tm_do64_lo, &bar_q[st], head * 64, row0 + i * 64);
+    };
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_kv, 4 * AB_T128);
+      tma_load_2d(sK, &p.tm_qkv128_hi, bar_kv, hd + head * 64, row0 + kt * 128);
+      tma_load_2d(sK + AB_T128, &p.tm_qkv128_lo, bar_kv, hd + head * 64, row0 + kt * 128);
+      tma_load_2d(sV, &p.tm_qkv128_hi, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
+      tma_load_2d(sV + AB_T128, &p.tm_qkv128_lo, bar_kv, 2 * hd + head * 64, row0 + kt * 128);
+      for (int i = 0; i < AB_STAGES && i < n_q; ++i) load_q(i);
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_kk = umma_idesc_bf16(64, 0, 0);
+    constexpr uint32_t idesc_mn = umma_idesc_bf16(64, 0, 1);
+    const uint64_t dKh = umma_desc_sw128(smem_u32(sK)), dKl = umma_desc_sw128(smem_u32(sK + AB_T128));
+    const uint64_t dVh = umma_desc_sw128(smem_u32(sV)), dVl = umma_desc_sw128(smem_u32(sV + AB_T128));
+    // S^T = K Q^T and dP^T = V dO^T of query tile i
+    auto issue_s_dp = [&](int i) {
+      const int st = i % AB_STAGES, b = i & 1;
+      mbar_wait(&bar_q[st], static_cast<uint32_t>((i / AB_STAGES) & 1));
+      tc_fence_after();
+      const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
+      mma_ss_split(tm + TM_ST + b * 64, dKh, dKl, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_kk, 32, false);
+      mma_ss_split(tm + TM_DPT + b * 64, dVh, dVl, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_kk, 32, false);
+      tc_commit(&bar_s[b]);
+    };
     mbar_wait(bar_kv, 0);
     issue_s_dp(0);
-  }
-
-  for (int i = 0; i < n_q; ++i) {
-    const int b = i & 1;
-    if (warp == 0 && i + 1 < n_q) issue_s_dp(i + 1);  // queued behind dV / dK of tile i-1
-    const float stat_next = (tid < 128 && i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
-    mbar_wait(&bar_s[b], static_cast<uint32_t>((i >> 1) & 1));
-    tc_fence_after();
-    float s[AB_COLS], dp[AB_COLS];
-    load_cols16(tm + TM_ST + b * 64 + grp * AB_COLS + lane_base, s);
-    load_cols16(tm + TM_DPT + b * 64 + grp * AB_COLS + lane_base, dp);
-    const float4* stat4 = reinterpret_cast<const float4*>(s_stat + b * 128 + grp * AB_COLS);
-    const float kscale = k_ok ? p.scale : 0.0f;
-#pragma unroll
-    for (int c4 = 0; c4 < AB_COLS / 4; ++c4) {
-      const float4 l4 = stat4[c4], d4 = stat4[16 + c4];
-      const float l[4] = {l4.x, l4.y, l4.z, l4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = c4 * 4 + e;
-        const float pv = k_ok ? fast_exp2(fmaf(s[c], c2, -l[e])) : 0.0f;  // padding queries: lse2 = +inf -> 0
-        s[c] = pv;
-        dp[c] = kscale * pv * (dp[c] - d[e]);
+    for (int i = 0; i < n_q; ++i) {
+      if (i + 1 < n_q) issue_s_dp(i + 1);  // queued behind dV / dK of tile i-1
+      mbar_wait(bar_ds, static_cast<uint32_t>(i & 1));
+      tc_fence_after();
+      // tile i+2 goes into the stage of tile i-1, free once dV / dK of tile i-1 have completed — which they have: the
+      // arithmetic warps waited for exactly that before they stored tile i.  (The wait sits BEFORE this tile's commit: with
+      // one barrier for all tiles, a wait issued after it could find the phase flipped twice.)
+      if (i >= 1 && i + 2 < n_q) {
+        mbar_wait(bar_d, static_cast<uint32_t>((i - 1) & 1));
+        if (lane == 0) load_q(i + 2);
+        __syncwarp();
       }
-    }
-    if (i >= 1) {  // dV / dK of tile i-1 read the P^T / dS^T buffers and the Q / dO stage of tile i-1
-      mbar_wait(bar_d, static_cast<uint32_t>((i - 1) & 1));
-      tc_fence_after();
-      if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // into the stage tile i-1 has just released
-    }
-    store_split_cols16(tm + TM_PT + grp * (AB_COLS / 2) + lane_base, s);
-    store_split_cols16(tm + TM_DST + grp * (AB_COLS / 2) + lane_base, dp);
-    if (tid < 128) s_stat[(b ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1: every thread is past its reads (barrier of the last turn)
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      tc_fence_after();
       const int st = i % AB_STAGES;
       const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
       mma_ts_split(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, 2048, i > 0);   // dV += P^T dO
       mma_ts_split(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, 2048, i > 0);  // dK += dS^T Q
       tc_commit(bar_d);
     }
-  }
-  mbar_wait(bar_d, static_cast<uint32_t>((n_q - 1) & 1));
-  tc_fence_after();
-
-  float dv[AB_COLS];
-  load_cols16(tm + TM_DV + grp * AB_COLS + lane_base, dv);
-  if (k_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + 2 * hd + head * 64 + grp * AB_COLS);
+  } else {
+    // ------------------------------------------------------------------ arithmetic warps: thread = (key row, 16-query group)
+    const int grp = warp >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int key = kt * 128 + (tid & 127);
+    const bool k_ok = key < p.tokens;
+    const float c2 = p.scale * 1.44269504088896340736f;
+    // thread t < 64 fetches lse of query t of a tile, thread 64 + t its D (one coalesced-ish load per thread and tile,
+    // issued one tile ahead; the tile loop then reads them as shared-memory broadcasts)
+    auto fetch_stat = [&](int i) -> float {
+      const int q = i * 64 + (tid & 63);
+      if (q >= p.tokens) return tid < 64 ? __int_as_float(0x7f800000) : 0.0f;
+      const long r = (static_cast<long>(row0) + q) * p.heads + head;
+      return tid < 64 ? p.lse[r] * 1.44269504088896340736f : p.Dvec[r];
+    };
+    if (tid < 128) s_stat[tid] = fetch_stat(0);
+    math_warps_sync();
+    for (int i = 0; i < n_q; ++i) {
+      const int b = i & 1;
+      const float stat_next = (tid < 128 && i + 1 < n_q) ? fetch_stat(i + 1) : 0.0f;
+      mbar_wait(&bar_s[b], static_cast<uint32_t>((i >> 1) & 1));
+      tc_fence_after();
+      float s[AB_COLS], dp[AB_COLS];
+      load_cols16(tm + TM_ST + b * 64 + grp * AB_COLS + lane_base, s);
+      load_cols16(tm + TM_DPT + b * 64 + grp * AB_COLS + lane_base, dp);
+      const float4* stat4 = reinterpret_cast<const float4*>(s_stat + b * 128 + grp * AB_COLS);
+      const float kscale = k_ok ? p.scale : 0.0f;
 #pragma unroll
-    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
-  }
-  load_cols16(tm + TM_DK + grp * AB_COLS + lane_base, dv);
-  if (k_ok) {
-    float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + hd + head * 64 + grp * AB_COLS);
+      for (int c4 = 0; c4 < AB_COLS / 4; ++c4) {
+        const float4 l4 = stat4[c4], d4 = stat4[16 + c4];
+        const float l[4] = {l4.x, l4.y, l4.z, l4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-    for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 * 4 + e;
+          const float pv = k_ok ? fast_exp2(fmaf(s[c], c2, -l[e])) : 0.0f;  // padding queries: lse2 = +inf -> 0
+          s[c] = pv;
+          dp[c] = kscale * pv * (dp[c] - d[e]);
+        }
+      }
+      if (i >= 1) {  // dV / dK of tile i-1 read the P^T / dS^T buffers
+        mbar_wait(bar_d, static_cast<uint32_t>((i - 1) & 1));
+        tc_fence_after();
+      }
+      store_split_cols16(tm + TM_PT + grp * (AB_COLS / 2) + lane_base, s);
+      store_split_cols16(tm + TM_DST + grp * (AB_COLS / 2) + lane_base, dp);
+      if (tid < 128) s_stat[(b ^ 1) * 128 + tid] = stat_next;  // buffer of tile i-1
+      warp_arrive(bar_ds, lane);
+      // the statistics of tile i+1 must be visible to every arithmetic warp, and nobody may still read buffer b^1 (tile i-1)
+      // when it is overwritten two lines above: one barrier among the arithmetic warps per tile covers both
+      math_warps_sync();
+    }
+    mbar_wait(bar_d, static_cast<uint32_t>((n_q - 1) & 1));
+    tc_fence_after();
+    float dv[AB_COLS];
+    load_cols16(tm + TM_DV + grp * AB_COLS + lane_base, dv);
+    if (k_ok) {
+      float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + 2 * hd + head * 64 + grp * AB_COLS);
+#pragma unroll
+      for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+    }
+    load_cols16(tm + TM_DK + grp * AB_COLS + lane_base, dv);
+    if (k_ok) {
+      float4* o = reinterpret_cast<float4*>(p.dqkv + (static_cast<long>(row0) + key) * 3 * hd + hd + head * 64 + grp * AB_COLS);
+#pragma unroll
+      for (int c = 0; c < AB_COLS / 4; ++c) o[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -5,6 +5,8 @@ No-grad calls run the inference kernels below; with gradients enabled the call i
 dupl_b200.train (one autograd.Function per student with CUDA forward and backward).  There is no
 PyTorch fallback on either path.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -142,6 +144,8 @@ def pair_forward(net1, net2, x, val=False, cam_with_grad=False):
         raise NotImplementedError("cam_with_grad is never used by the reference scripts (model_dupl.py:100-104)")
     if _wants_grad([net1, net2]):
         from . import train
+        if train._arena_mode(net1) and train._arena_mode(net2) and os.environ.get("DUPL_PAIR_BACKWARD", "1") != "0":
+            return train.pair_student_forward(net1, net2, x)      # one autograd node: grouped dgrad / wgrad launches
         return train.student_forward(net1, x), train.student_forward(net2, x)
     r1, r2 = _heads([net1, net2], x)
     return r1, r2

@@ -84,6 +84,25 @@ def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr, out=None):
     return out
 
 
+def dgrad_multi(pairs, M, n_out, k_contr):
+    """dgrad for several students in ONE grouped launch: pairs = [(dy_planes, wt_planes)] -> [dX]."""
+    outs = [torch.empty(M, n_out, dtype=torch.float32, device=dy[0].device) for dy, _ in pairs]
+    ops.gemm_bf16x3([dict(a=dy, w=wt, out_f32=o) for (dy, wt), o in zip(pairs, outs)], M, n_out, k_contr, L.EPI_F32)
+    return outs
+
+
+def wgrad_multi(pairs, n_rows, n_cols, k_contr, outs=None):
+    """wgrad for several students in ONE grouped launch: pairs = [(dyt_planes, xt_planes)], outs = per-student arena views or
+    None -> [dW [n_rows, n_cols]]."""
+    outs = list(outs) if outs is not None else [None] * len(pairs)
+    for i, (dyt, _) in enumerate(pairs):
+        outs[i] = (torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt[0].device) if outs[i] is None
+                   else outs[i].view(n_rows, n_cols))
+    ops.gemm_bf16x3([dict(a=dyt, w=xt, out_f32=o) for (dyt, xt), o in zip(pairs, outs)], n_rows, n_cols, k_contr, L.EPI_F32,
+                    ksplit=L.MAX_KSPLIT)
+    return outs
+
+
 class _Saved:
     pass
 
@@ -249,109 +268,169 @@ def _gmp_bwd(x_rows, w, dlogits, argmax, dx, S):
     return dw
 
 
-def _conv_bwd(d_out, act_planes, col_planes, wmat_t, S, cin, d_in, in_tokens, in_first, accumulate):
-    """Backward of relu(conv3x3_d5(in)): d_out fp32 [Mp, 512] (grad wrt the relu output) ->
-    d_in (+)=, returns dWmat [512, 9*cin]."""
-    dev = d_out.device
+def _conv_bwd_multi(d_outs, acts, cols, wmat_ts, S, cin, d_ins, in_tokens, in_first, accumulate):
+    """Backward of relu(conv3x3_d5(in)) for several students: d_outs fp32 [Mp, 512] each (grad wrt the relu output) ->
+    d_ins (+)=, returns [dWmat [512, 9*cin]]; the dgrad and wgrad GEMMs are one grouped launch each."""
+    dev = d_outs[0].device
     Mp = S.Mp
-    L.check(L.lib().dupl_relu_bwd(L.ptr(d_out), L.ptr(act_planes[0]), L.ptr(act_planes[1]), d_out.numel(), _st(dev)), "dupl_relu_bwd")
-    dpl, dt = split_transpose(d_out, Mp, 512)
-    dcol = dgrad(dpl, wmat_t, Mp, 9 * cin, 512)
-    L.check(L.lib().dupl_col2im3x3(L.ptr(dcol), L.ptr(d_in), S.B, S.gh, S.gw, cin, DECODER_DIL, d_in.shape[1], in_tokens, in_first,
-                                   1 if accumulate else 0, _st(dev)), "dupl_col2im3x3")
-    col_t = transpose_planes(col_planes, Mp, 9 * cin)
-    return wgrad(dt, col_t, 512, 9 * cin, _pad64(Mp))
+    dpls, dts = [], []
+    for d_out, act in zip(d_outs, acts):
+        L.check(L.lib().dupl_relu_bwd(L.ptr(d_out), L.ptr(act[0]), L.ptr(act[1]), d_out.numel(), _st(dev)), "dupl_relu_bwd")
+        dpl, dt = split_transpose(d_out, Mp, 512)
+        dpls.append(dpl)
+        dts.append(dt)
+    dcols = dgrad_multi(list(zip(dpls, wmat_ts)), Mp, 9 * cin, 512)
+    for dcol, d_in in zip(dcols, d_ins):
+        L.check(L.lib().dupl_col2im3x3(L.ptr(dcol), L.ptr(d_in), S.B, S.gh, S.gw, cin, DECODER_DIL, d_in.shape[1], in_tokens, in_first,
+                                       1 if accumulate else 0, _st(dev)), "dupl_col2im3x3")
+    col_ts = [transpose_planes(c, Mp, 9 * cin) for c in cols]
+    return wgrad_multi(list(zip(dts, col_ts)), 512, 9 * cin, _pad64(Mp))
 
 
 def _backward(net, S, g_cls, g_seg, g_x4, g_aux, sink=None):
-    """-> sink (a dict name -> gradient by default).  Every trainable parameter is `put` exactly once, in backward_order()."""
-    pl = net.planes()
-    dp = _decoder_planes(net)
-    dev = S.xn.device
-    f32 = dict(dtype=torch.float32, device=dev)
-    M, Mp, N, B, np_ = S.M, S.Mp, S.N, S.B, S.np
-    Mpad = _pad64(M)
-    grads = sink if sink is not None else _DictSink()
-    K = net.num_classes - 1
+    """One student.  -> sink (a dict name -> gradient by default)."""
+    return _backward_multi([net], [S], [g_cls], [g_seg], [g_x4], [g_aux], [sink])[0]
 
-    d_xn = torch.zeros(M, D, **f32)          # grad wrt the final-normed tokens
-    if g_x4 is not None:
-        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_x4)), L.ptr(d_xn), B, np_, D, D, N, 1, _st(dev)), "dupl_nchw_to_rows_add")
-    grads.put("classifier.weight", None if g_cls is None else _gmp_bwd(S.xn, S.wc, g_cls, S.arg_c, d_xn, S).reshape(K, D, 1, 1))
-    if S.aux_is_final:
-        grads.put("aux_classifier.weight", None if g_aux is None else _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_xn, S).reshape(K, D, 1, 1))
-    if g_seg is not None:
+
+def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
+    """Backward of `_forward` for one or both students in lock step: every dgrad / wgrad GEMM is ONE grouped launch over the
+    students (twice the tiles per launch fill the 74 CTA pairs better: 495 vs 631 us per encoder block, tools/gemm_shapes.py
+    train), everything else runs per student.  All arguments are lists over the students; every trainable parameter of every
+    student is `put` exactly once, in backward_order().  -> list of sinks."""
+    G = len(nets)
+    R = range(G)
+    pls = [n.planes() for n in nets]
+    dps = [_decoder_planes(n) for n in nets]
+    S0 = Ss[0]
+    dev = S0.xn.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    M, Mp, N, B, np_ = S0.M, S0.Mp, S0.N, S0.B, S0.np
+    if any((S.M, S.Mp, S.N, S.B, S.aux_idx) != (M, Mp, N, B, S0.aux_idx) for S in Ss):
+        raise RuntimeError("grouped backward needs students with identical shapes")
+    Mpad = _pad64(M)
+    grads = [s if s is not None else _DictSink() for s in sinks]
+    K = nets[0].num_classes - 1
+
+    d_xn = [torch.zeros(M, D, **f32) for _ in R]          # grad wrt the final-normed tokens
+    for g in R:
+        S = Ss[g]
+        if g_x4[g] is not None:
+            L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_x4[g])), L.ptr(d_xn[g]), B, np_, D, D, N, 1, _st(dev)), "dupl_nchw_to_rows_add")
+        grads[g].put("classifier.weight", None if g_cls[g] is None else _gmp_bwd(S.xn, S.wc, g_cls[g], S.arg_c, d_xn[g], S).reshape(K, D, 1, 1))
+        if S.aux_is_final:
+            grads[g].put("aux_classifier.weight",
+                         None if g_aux[g] is None else _gmp_bwd(S.aux_src, S.wa, g_aux[g], S.arg_a, d_xn[g], S).reshape(K, D, 1, 1))
+    with_seg = [g for g in R if g_seg[g] is not None]
+    if with_seg:
         # conv8 (1x1): seg_rows = h7 @ W8^T
-        Cn = net.num_classes
+        Cn = nets[0].num_classes
         Cp = _pad64(Cn)                             # contraction dim of the dgrad padded to a multiple of 64 (21 -> 64, 81 -> 128)
-        d_seg_rows = torch.zeros(Mp, Cp, **f32)
-        L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_seg)), L.ptr(d_seg_rows), B, np_, Cn, Cp, 0, 0, _st(dev)), "dupl_nchw_to_rows_add")
-        dsp, dst = split_transpose(d_seg_rows, Mp, Cp)
-        w8 = dp.get("conv8")
-        w8t = transpose_planes(w8, S.n8, 512)                       # [512, pad64(n8)]
-        d_h7 = dgrad(dsp, w8t, Mp, 512, Cp)
-        h7t = transpose_planes(S.h7, Mp, 512)
-        dw8 = wgrad(dst, h7t, Cp, 512, _pad64(Mp))
-        grads.put("decoder.conv8.weight", dw8[:Cn].reshape(Cn, 512, 1, 1))
+        dsps, dsts, w8ts, h7ts = [], [], [], []
+        for g in with_seg:
+            S = Ss[g]
+            d_seg_rows = torch.zeros(Mp, Cp, **f32)
+            L.check(L.lib().dupl_nchw_to_rows_add(L.ptr(L.f32c(g_seg[g])), L.ptr(d_seg_rows), B, np_, Cn, Cp, 0, 0, _st(dev)), "dupl_nchw_to_rows_add")
+            dsp, dst = split_transpose(d_seg_rows, Mp, Cp)
+            dsps.append(dsp)
+            dsts.append(dst)
+            w8ts.append(transpose_planes(dps[g].get("conv8"), S.n8, 512))                      # [512, pad64(n8)]
+            h7ts.append(transpose_planes(S.h7, Mp, 512))
+        d_h7 = dgrad_multi(list(zip(dsps, w8ts)), Mp, 512, Cp)
+        dw8 = wgrad_multi(list(zip(dsts, h7ts)), Cp, 512, _pad64(Mp))
+        for i, g in enumerate(with_seg):
+            grads[g].put("decoder.conv8.weight", dw8[i][:Cn].reshape(Cn, 512, 1, 1))
         # conv7 + relu, conv6 + relu
-        d_h6 = torch.empty(Mp, 512, **f32)
-        dw7 = _conv_bwd(d_h7, S.h7, S.col7, dp.get_t("conv7"), S, 512, d_h6, 0, 0, False)
-        grads.put("decoder.conv7.weight", dw7.reshape(512, 3, 3, 512).permute(0, 3, 1, 2))
-        dw6 = _conv_bwd(d_h6, S.h6, S.col6, dp.get_t("conv6"), S, D, d_xn, N, 1, True)
-        grads.put("decoder.conv6.weight", dw6.reshape(512, 3, 3, D).permute(0, 3, 1, 2))
-    else:
-        for n in ("decoder.conv8.weight", "decoder.conv7.weight", "decoder.conv6.weight"):
-            grads.put(n, None)
+        d_h6 = [torch.empty(Mp, 512, **f32) for _ in with_seg]
+        dw7 = _conv_bwd_multi(d_h7, [Ss[g].h7 for g in with_seg], [Ss[g].col7 for g in with_seg], [dps[g].get_t("conv7") for g in with_seg],
+                              S0, 512, d_h6, 0, 0, False)
+        for i, g in enumerate(with_seg):
+            grads[g].put("decoder.conv7.weight", dw7[i].reshape(512, 3, 3, 512).permute(0, 3, 1, 2))
+        dw6 = _conv_bwd_multi(d_h6, [Ss[g].h6 for g in with_seg], [Ss[g].col6 for g in with_seg], [dps[g].get_t("conv6") for g in with_seg],
+                              S0, D, [d_xn[g] for g in with_seg], N, 1, True)
+        for i, g in enumerate(with_seg):
+            grads[g].put("decoder.conv6.weight", dw6[i].reshape(512, 3, 3, D).permute(0, 3, 1, 2))
+    for g in R:
+        if g_seg[g] is None:
+            for n in ("decoder.conv8.weight", "decoder.conv7.weight", "decoder.conv6.weight"):
+                grads[g].put(n, None)
 
     # final LayerNorm
-    d_tok = torch.zeros(M, D, **f32)
-    dg, db = layernorm_bwd(d_xn, S.tok_final, pl.vec("norm.weight"), d_tok)
-    grads.put("encoder.norm.weight", dg)
-    grads.put("encoder.norm.bias", db)
+    d_tok = [torch.zeros(M, D, **f32) for _ in R]
+    for g in R:
+        dg, db = layernorm_bwd(d_xn[g], Ss[g].tok_final, pls[g].vec("norm.weight"), d_tok[g])
+        grads[g].put("encoder.norm.weight", dg)
+        grads[g].put("encoder.norm.bias", db)
 
     scale = (D // E.HEADS) ** -0.5
+    bfk = dict(dtype=torch.bfloat16, device=dev)
     for i in reversed(range(E.DEPTH)):
         bp = f"blocks.{i}."
         ep = "encoder." + bp
-        b = S.blocks[i]
-        if not S.aux_is_final and i == S.aux_idx:
-            # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
-            grads.put("aux_classifier.weight", None if g_aux is None else _gmp_bwd(S.aux_src, S.wa, g_aux, S.arg_a, d_tok, S).reshape(K, D, 1, 1))
+        bl = [S.blocks[i] for S in Ss]
+        for g in R:
+            S = Ss[g]
+            if not S.aux_is_final and i == S.aux_idx:
+                # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
+                grads[g].put("aux_classifier.weight",
+                             None if g_aux[g] is None else _gmp_bwd(S.aux_src, S.wa, g_aux[g], S.arg_a, d_tok[g], S).reshape(K, D, 1, 1))
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
-        dpl, dt, cs = split_transpose(d_tok, M, D, want_colsum=True)
-        grads.put(ep + "mlp.fc2.bias", cs)
-        grads.put(ep + "mlp.fc2.weight", wgrad(dt, transpose_planes(b.hid, M, 4 * D), D, 4 * D, Mpad, out=grads.out(ep + "mlp.fc2.weight")))
-        d_hid = dgrad(dpl, pl.plane_t(bp + "mlp.fc2.weight"), M, 4 * D, D)
-        L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid), L.ptr(b.h_pre), d_hid.numel(), _st(dev)), "dupl_gelu_bwd")
-        dpl, dt, cs = split_transpose(d_hid, M, 4 * D, want_colsum=True)
-        grads.put(ep + "mlp.fc1.bias", cs)
-        grads.put(ep + "mlp.fc1.weight", wgrad(dt, transpose_planes(b.xn2, M, D), 4 * D, D, Mpad, out=grads.out(ep + "mlp.fc1.weight")))
-        d_xn2 = dgrad(dpl, pl.plane_t(bp + "mlp.fc1.weight"), M, D, 4 * D)
-        dg, db = layernorm_bwd(d_xn2, b.x_mid, pl.vec(bp + "norm2.weight"), d_tok)
-        grads.put(ep + "norm2.weight", dg)
-        grads.put(ep + "norm2.bias", db)
+        dpl, dt = [None] * G, [None] * G
+        for g in R:
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True)
+            grads[g].put(ep + "mlp.fc2.bias", cs)
+        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].hid, M, 4 * D)) for g in R], D, 4 * D, Mpad,
+                         outs=[grads[g].out(ep + "mlp.fc2.weight") for g in R])
+        for g in R:
+            grads[g].put(ep + "mlp.fc2.weight", dw[g])
+        d_hid = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "mlp.fc2.weight")) for g in R], M, 4 * D, D)
+        for g in R:
+            L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid[g]), L.ptr(bl[g].h_pre), d_hid[g].numel(), _st(dev)), "dupl_gelu_bwd")
+            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True)
+            grads[g].put(ep + "mlp.fc1.bias", cs)
+        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].xn2, M, D)) for g in R], 4 * D, D, Mpad,
+                         outs=[grads[g].out(ep + "mlp.fc1.weight") for g in R])
+        for g in R:
+            grads[g].put(ep + "mlp.fc1.weight", dw[g])
+        d_xn2 = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "mlp.fc1.weight")) for g in R], M, D, 4 * D)
+        for g in R:
+            dg, db = layernorm_bwd(d_xn2[g], bl[g].x_mid, pls[g].vec(bp + "norm2.weight"), d_tok[g])
+            grads[g].put(ep + "norm2.weight", dg)
+            grads[g].put(ep + "norm2.bias", db)
         # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-        dpl, dt, cs = split_transpose(d_tok, M, D, want_colsum=True)
-        grads.put(ep + "attn.proj.bias", cs)
-        grads.put(ep + "attn.proj.weight", wgrad(dt, transpose_planes(b.att, M, D), D, D, Mpad, out=grads.out(ep + "attn.proj.weight")))
-        bfk = dict(dtype=torch.bfloat16, device=dev)
-        d_att = (torch.empty(M, D, **bfk), torch.empty(M, D, **bfk))     # dO as split planes: operand of the attention backward
-        ops.gemm_bf16x3([dict(a=dpl, w=pl.plane_t(bp + "attn.proj.weight"), out=d_att)], M, D, D, L.EPI_SPLIT)
-        d_qkv = ops.attention_bwd(b.qkv, b.att, d_att, b.lse, B, N, E.HEADS, scale)
-        dpl, dt, cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
-        grads.put(ep + "attn.qkv.bias", cs)
-        grads.put(ep + "attn.qkv.weight", wgrad(dt, transpose_planes(b.xn1, M, D), 3 * D, D, Mpad, out=grads.out(ep + "attn.qkv.weight")))
-        d_xn1 = dgrad(dpl, pl.plane_t(bp + "attn.qkv.weight"), M, D, 3 * D)
-        dg, db = layernorm_bwd(d_xn1, b.x_in, pl.vec(bp + "norm1.weight"), d_tok)
-        grads.put(ep + "norm1.weight", dg)
-        grads.put(ep + "norm1.bias", db)
+        for g in R:
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True)
+            grads[g].put(ep + "attn.proj.bias", cs)
+        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].att, M, D)) for g in R], D, D, Mpad,
+                         outs=[grads[g].out(ep + "attn.proj.weight") for g in R])
+        for g in R:
+            grads[g].put(ep + "attn.proj.weight", dw[g])
+        d_att = [(torch.empty(M, D, **bfk), torch.empty(M, D, **bfk)) for _ in R]   # dO as split planes: operand of the attention backward
+        ops.gemm_bf16x3([dict(a=dpl[g], w=pls[g].plane_t(bp + "attn.proj.weight"), out=d_att[g]) for g in R], M, D, D, L.EPI_SPLIT)
+        for g in R:
+            d_qkv = ops.attention_bwd(bl[g].qkv, bl[g].att, d_att[g], bl[g].lse, B, N, E.HEADS, scale)
+            dpl[g], dt[g], cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
+            grads[g].put(ep + "attn.qkv.bias", cs)
+        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].xn1, M, D)) for g in R], 3 * D, D, Mpad,
+                         outs=[grads[g].out(ep + "attn.qkv.weight") for g in R])
+        for g in R:
+            grads[g].put(ep + "attn.qkv.weight", dw[g])
+        d_xn1 = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "attn.qkv.weight")) for g in R], M, D, 3 * D)
+        for g in R:
+            dg, db = layernorm_bwd(d_xn1[g], bl[g].x_in, pls[g].vec(bp + "norm1.weight"), d_tok[g])
+            grads[g].put(ep + "norm1.weight", dg)
+            grads[g].put(ep + "norm1.bias", db)
 
     # ---- patch embedding (pos_embed is frozen, vit.py:243)
-    _, dt, cs = split_transpose(d_tok, Mp, D, want_planes=False, tokens=N, np_=np_, first=1, want_colsum=True)
-    grads.put("encoder.patch_embed.proj.bias", cs)
-    dwpe = wgrad(dt, transpose_planes(S.patch, Mp, D), D, D, _pad64(Mp), out=grads.out("encoder.patch_embed.proj.weight"))
-    grads.put("encoder.patch_embed.proj.weight", dwpe.reshape(D, 3, 16, 16))
-    grads.put("encoder.cls_token", colsum(d_tok, B, D, tokens=N, np_=1, first=0).reshape(1, 1, D))
+    dts = []
+    for g in R:
+        _, dt_g, cs = split_transpose(d_tok[g], Mp, D, want_planes=False, tokens=N, np_=np_, first=1, want_colsum=True)
+        grads[g].put("encoder.patch_embed.proj.bias", cs)
+        dts.append(dt_g)
+    dwpe = wgrad_multi([(dts[g], transpose_planes(Ss[g].patch, Mp, D)) for g in R], D, D, _pad64(Mp),
+                       outs=[grads[g].out("encoder.patch_embed.proj.weight") for g in R])
+    for g in R:
+        grads[g].put("encoder.patch_embed.proj.weight", dwpe[g].reshape(D, 3, 16, 16))
+        grads[g].put("encoder.cls_token", colsum(d_tok[g], B, D, tokens=N, np_=1, first=0).reshape(1, 1, D))
     return grads
 
 
@@ -398,8 +477,50 @@ class StudentFunction(torch.autograd.Function):
         return (None, None, None, *out)
 
 
+class PairFunction(torch.autograd.Function):
+    """Both students of `siamese_network.forward(x)` (model_dupl.py:207-209) as ONE autograd node — arena mode only.  Its
+    backward runs the two students in lock step (_backward_multi), so every dgrad / wgrad GEMM of a layer is one grouped launch
+    over both students instead of two launches that each leave part of the 74 CTA pairs idle."""
+
+    @staticmethod
+    def forward(ctx, net1, net2, x, anchor):
+        ctx.set_materialize_grads(False)
+        outs, Ss = [], []
+        for net in (net1, net2):
+            kept = None
+            if getattr(net, "_use_kept", False) and net._kept is not None:
+                kept, net._use_kept = net._kept, False
+            o, S = _forward(net, x, None, kept)
+            outs.append(o)
+            Ss.append(S)
+        ctx.nets, ctx.Ss = (net1, net2), Ss
+        return (*outs[0], *outs[1])
+
+    @staticmethod
+    def backward(ctx, *g):
+        arenas = [n._grad_arena for n in ctx.nets]
+        with torch.no_grad():
+            _backward_multi(list(ctx.nets), ctx.Ss, [g[0], g[4]], [g[1], g[5]], [g[2], g[6]], [g[3], g[7]],
+                            [_ArenaSink(a) for a in arenas])
+            for a in arenas:
+                a.end_call()
+        ctx.Ss = None
+        return (None, None, None, None)
+
+
+def pair_student_forward(net1, net2, x):
+    """-> ((cls_x4, seg, _x4, cls_aux) of student 1, same of student 2); both nets must be in arena mode."""
+    anchor = torch.empty(0, device=x.device).requires_grad_()
+    o = PairFunction.apply(net1, net2, x, anchor)
+    return tuple(o[:4]), tuple(o[4:])
+
+
+def _arena_mode(net):
+    return getattr(net, "_use_arena", False) and getattr(net, "_grad_arena", None) is not None
+
+
 def student_forward(net, x, size=None):
-    if getattr(net, "_use_arena", False) and getattr(net, "_grad_arena", None) is not None:
+    if _arena_mode(net):
         # arena mode: the backward writes the parameter gradients into the student's flat arena itself, so the parameters
         # are not autograd inputs at all.  A fresh leaf per call keeps the outputs differentiable; being new, its
         # AccumulateGrad node belongs to the stream of THIS forward (a node that survives from an earlier step would make a
