@@ -41,30 +41,53 @@ struct AttnBwdTcParams {
   float scale;
 };
 
-// D[tmem] (+)= A[smem] B[smem]^T, 3-pass split, 64-deep contraction; b_kstep = 32 (K-major B) or 2048 (MN-major B)
+// The 12 MMAs of one 3-pass split product (64-deep contraction = 4 k-steps per pass) as ONE asm block: one elect.sync for the
+// batch and the descriptor increments as immediates.  Issued one C++ call per MMA (elect + setp + two 64-bit adds each, every
+// MMA's predicate depending on its own elect), a single warp got out one 128x64x16 MMA per ~45 cycles — more than the 32-48
+// cycles the tensor pipe needs for it, so the ISSUING warp bounded both backward kernels (ncu: 34-40 % tensor-pipe activity,
+// arithmetic warps waiting on the S / dP barrier).
+#define DUPL_MMA_SS(A, B, KA, KB, ACC)                                                                     \
+  "add.u64 ta, " A ", " #KA ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                            \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, " ACC ";\n\t"
+#define DUPL_MMA_SS_PASS(A, B, S1, S2, S3, ACC0)                                                           \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " ACC0 ";\n\t"                               \
+  DUPL_MMA_SS(A, B, 2, S1, "one") DUPL_MMA_SS(A, B, 4, S2, "one") DUPL_MMA_SS(A, B, 6, S3, "one")
+// D[tmem] (+)= A[smem] B[smem]^T, 3-pass split; BSTEP = descriptor step of B per k-step in 16-byte units: 2 (K-major B,
+// 32 B) or 128 (MN-major B, 2048 B = 16 rows)
+template <int BSTEP>
 __device__ __forceinline__ void mma_ss_split(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                             uint32_t idesc, uint32_t b_kstep, bool accumulate) {
-#pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint64_t a = (pass == 2) ? a_lo : a_hi;
-    const uint64_t b = (pass == 1) ? b_lo : b_hi;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      tc_mma_f16(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * b_kstep), idesc,
-                 (accumulate || (pass | k) != 0) ? 1u : 0u);
-  }
+                                             uint32_t idesc, bool accumulate) {
+  static_assert(BSTEP == 2, "only the K-major B form is instantiated");
+  asm volatile(
+      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 ta, tb;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 one, 0, 0;\n\t"
+      DUPL_MMA_SS_PASS("%1", "%3", "2", "4", "6", "p")     // hi * hi
+      DUPL_MMA_SS_PASS("%1", "%4", "2", "4", "6", "one")   // hi * lo
+      DUPL_MMA_SS_PASS("%2", "%3", "2", "4", "6", "one")   // lo * hi
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
 }
-// same with A in tensor memory (hi at a_tmem, lo 32 columns further)
+#define DUPL_MMA_TS(AOFF, B, KB, ACC)                                                                      \
+  "add.u32 sa, %1, " #AOFF ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [sa], tb, %4, " ACC ";\n\t"
+// same with A in tensor memory (hi plane at a_tmem, lo plane 32 columns further; 8 columns per k-step) and an MN-major B
+// (2048 B = 128 descriptor units per k-step)
 __device__ __forceinline__ void mma_ts_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
-                                             uint32_t b_kstep, bool accumulate) {
-#pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a = a_tmem + ((pass == 2) ? 32 : 0);
-    const uint64_t b = (pass == 1) ? b_lo : b_hi;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      tc_mma_f16_ts(d_tmem, a + k * 8, umma_desc_advance(b, k * b_kstep), idesc, (accumulate || (pass | k) != 0) ? 1u : 0u);
-  }
+                                             bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 tb;\n\t.reg .b32 sa;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 one, 0, 0;\n\t"
+      DUPL_MMA_TS(0, "%2", "0", "p") DUPL_MMA_TS(8, "%2", "128", "one") DUPL_MMA_TS(16, "%2", "256", "one") DUPL_MMA_TS(24, "%2", "384", "one")      // hi * hi
+      DUPL_MMA_TS(0, "%3", "0", "one") DUPL_MMA_TS(8, "%3", "128", "one") DUPL_MMA_TS(16, "%3", "256", "one") DUPL_MMA_TS(24, "%3", "384", "one")  // hi * lo
+      DUPL_MMA_TS(32, "%2", "0", "one") DUPL_MMA_TS(40, "%2", "128", "one") DUPL_MMA_TS(48, "%2", "256", "one") DUPL_MMA_TS(56, "%2", "384", "one")  // lo * hi
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
 }
 
 __device__ __forceinline__ void store_split_row(uint32_t taddr, const float (&v)[64]) {
@@ -187,8 +210,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
       mbar_wait(&bar_kv[st], static_cast<uint32_t>((j / AB_STAGES) & 1));
       tc_fence_after();
       const uint32_t k0 = smem_u32(sK + st * 2 * AB_T64), v0 = smem_u32(sV + st * 2 * AB_T64);
-      mma_ss_split(tm + TM_S + b * 64, dQh, dQl, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_kk, 32, false);
-      mma_ss_split(tm + TM_DP + b * 64, dOh, dOl, umma_desc_sw128(v0), umma_desc_sw128(v0 + AB_T64), idesc_kk, 32, false);
+      mma_ss_split<2>(tm + TM_S + b * 64, dQh, dQl, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_kk, false);
+      mma_ss_split<2>(tm + TM_DP + b * 64, dOh, dOl, umma_desc_sw128(v0), umma_desc_sw128(v0 + AB_T64), idesc_kk, false);
       tc_commit(&bar_s[b]);
     };
     mbar_wait(bar_q, 0);
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
       mbar_wait(&bar_ds[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
       const uint32_t k0 = smem_u32(sK + (j % AB_STAGES) * 2 * AB_T64);
-      mma_ts_split(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, 2048, j > 0);  // dQ += dS K
+      mma_ts_split(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, j > 0);  // dQ += dS K
       tc_commit(&bar_d[b]);
       // tile j+2 goes into the stage of tile j-1, free once dQ(j-1) (issued a whole turn ago) has completed
       if (j >= 1 && j + 2 < n_kv) {
@@ -329,8 +352,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       mbar_wait(&bar_q[st], static_cast<uint32_t>((i / AB_STAGES) & 1));
       tc_fence_after();
       const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
-      mma_ss_split(tm + TM_ST + b * 64, dKh, dKl, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_kk, 32, false);
-      mma_ss_split(tm + TM_DPT + b * 64, dVh, dVl, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_kk, 32, false);
+      mma_ss_split<2>(tm + TM_ST + b * 64, dKh, dKl, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_kk, false);
+      mma_ss_split<2>(tm + TM_DPT + b * 64, dVh, dVl, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_kk, false);
       tc_commit(&bar_s[b]);
     };
     mbar_wait(bar_kv, 0);
@@ -349,8 +372,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       }
       const int st = i % AB_STAGES;
       const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
-      mma_ts_split(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, 2048, i > 0);   // dV += P^T dO
-      mma_ts_split(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, 2048, i > 0);  // dK += dS^T Q
+      mma_ts_split(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, i > 0);   // dV += P^T dO
+      mma_ts_split(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, i > 0);  // dK += dS^T Q
       tc_commit(bar_d);
     }
   } else {

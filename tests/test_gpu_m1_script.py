@@ -34,7 +34,7 @@ def _run(tmp, tag, dropin, nproc, port):
             "--samples_per_gpu", "2", "--num_workers", "2", "--max_iters", str(ITERS), "--cam_iters", str(CAM_ITERS),
             "--log_iters", "2", "--eval_iters", "100000"]
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
     rows = [json.loads(line) for line in open(trace)]
     assert len(rows) == ITERS
