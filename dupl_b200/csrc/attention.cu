@@ -66,20 +66,6 @@ enum {  // mbarrier slots
   BAR_COUNT = BAR_O_FULL + 2
 };
 
-// 3-pass split product over a 64-deep contraction, A operand in tensor memory (hi at a_tmem, lo 32 columns
-// further), B operand in shared memory; warp-collective (leader elected inside tc_mma_f16_ts).
-__device__ __forceinline__ void issue_split_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo,
-                                                   uint32_t idesc, uint32_t b_kstep) {
-#pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a = a_tmem + ((pass == 2) ? 32 : 0);
-    const uint64_t b = (pass == 1) ? b_lo : b_hi;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16): 8 TMEM columns of A per step
-      tc_mma_f16_ts(d_tmem, a + k * 8, umma_desc_advance(b, k * b_kstep), idesc, (pass | k) != 0 ? 1u : 0u);
-  }
-}
-
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __grid_constant__ AttnParamsDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -158,11 +144,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
           dV[st][pl] = umma_desc_sw128(sV + (2 * st + pl) * ATT_KV_BYTES);
         }
       auto qk = [&](int t, int st) {  // S_t = Q_t K^T
-        issue_split_mma_ts(tm + TM_S + t * 64, tm + TM_Q + t * 64, dK[st][0], dK[st][1], idesc_qk, 32);
+        mma_ts_split<2>(tm + TM_S + t * 64, tm + TM_Q + t * 64, dK[st][0], dK[st][1], idesc_qk, false);
         tc_commit(&bars[BAR_S_FULL + t]);
       };
       auto pv = [&](int t, int st) {  // O_t = P_t V
-        issue_split_mma_ts(tm + TM_O + t * 64, tm + TM_P + t * 64, dV[st][0], dV[st][1], idesc_pv, 2048);
+        mma_ts_split<128>(tm + TM_O + t * 64, tm + TM_P + t * 64, dV[st][0], dV[st][1], idesc_pv, false);
         tc_commit(&bars[BAR_O_FULL + t]);
       };
       mbar_wait(&bars[BAR_Q], 0);

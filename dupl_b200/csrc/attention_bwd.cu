@@ -29,7 +29,7 @@ constexpr int AB_MATH_THREADS = 128 * AB_GROUPS, AB_MATH_WARPS = AB_MATH_THREADS
 constexpr int AB_THREADS = AB_MATH_THREADS + 32;
 constexpr int AB_T64 = 64 * 64 * 2;    // one plane of a 64-row tile (8 KB)
 constexpr int AB_T128 = 128 * 64 * 2;  // one plane of a 128-row tile (16 KB)
-constexpr int AB_SMEM = 4 * AB_T128 + 3 * 4 * AB_T64 + 1024 + 2048;  // 64 KB resident tiles + 3 stages x 32 KB + alignment slack + barriers / per-tile statistics
+constexpr int AB_SMEM = 4 * AB_T128 + 4 * 4 * AB_T64 + 1024 + 2048;  // 64 KB resident tiles + 4 stages x 32 KB + alignment slack + barriers / per-tile statistics
 
 struct AttnBwdTcParams {
   CUtensorMap tm_qkv128_hi, tm_qkv128_lo, tm_qkv64_hi, tm_qkv64_lo;  // [M, 3*heads*64] planes, boxes of 128 / 64 rows
@@ -40,55 +40,6 @@ struct AttnBwdTcParams {
   int tokens, row_offset, heads;
   float scale;
 };
-
-// The 12 MMAs of one 3-pass split product (64-deep contraction = 4 k-steps per pass) as ONE asm block: one elect.sync for the
-// batch and the descriptor increments as immediates.  Issued one C++ call per MMA (elect + setp + two 64-bit adds each, every
-// MMA's predicate depending on its own elect), a single warp got out one 128x64x16 MMA per ~45 cycles — more than the 32-48
-// cycles the tensor pipe needs for it, so the ISSUING warp bounded both backward kernels (ncu: 34-40 % tensor-pipe activity,
-// arithmetic warps waiting on the S / dP barrier).
-#define DUPL_MMA_SS(A, B, KA, KB, ACC)                                                                     \
-  "add.u64 ta, " A ", " #KA ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                            \
-  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, " ACC ";\n\t"
-#define DUPL_MMA_SS_PASS(A, B, S1, S2, S3, ACC0)                                                           \
-  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " ACC0 ";\n\t"                               \
-  DUPL_MMA_SS(A, B, 2, S1, "one") DUPL_MMA_SS(A, B, 4, S2, "one") DUPL_MMA_SS(A, B, 6, S3, "one")
-// D[tmem] (+)= A[smem] B[smem]^T, 3-pass split; BSTEP = descriptor step of B per k-step in 16-byte units: 2 (K-major B,
-// 32 B) or 128 (MN-major B, 2048 B = 16 rows)
-template <int BSTEP>
-__device__ __forceinline__ void mma_ss_split(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                             uint32_t idesc, bool accumulate) {
-  static_assert(BSTEP == 2, "only the K-major B form is instantiated");
-  asm volatile(
-      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 ta, tb;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "setp.eq.b32 one, 0, 0;\n\t"
-      DUPL_MMA_SS_PASS("%1", "%3", "2", "4", "6", "p")     // hi * hi
-      DUPL_MMA_SS_PASS("%1", "%4", "2", "4", "6", "one")   // hi * lo
-      DUPL_MMA_SS_PASS("%2", "%3", "2", "4", "6", "one")   // lo * hi
-      "}"
-      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
-      : "memory");
-}
-#define DUPL_MMA_TS(AOFF, B, KB, ACC)                                                                      \
-  "add.u32 sa, %1, " #AOFF ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                             \
-  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [sa], tb, %4, " ACC ";\n\t"
-// same with A in tensor memory (hi plane at a_tmem, lo plane 32 columns further; 8 columns per k-step) and an MN-major B
-// (2048 B = 128 descriptor units per k-step)
-__device__ __forceinline__ void mma_ts_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
-                                             bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 tb;\n\t.reg .b32 sa;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "setp.eq.b32 one, 0, 0;\n\t"
-      DUPL_MMA_TS(0, "%2", "0", "p") DUPL_MMA_TS(8, "%2", "128", "one") DUPL_MMA_TS(16, "%2", "256", "one") DUPL_MMA_TS(24, "%2", "384", "one")      // hi * hi
-      DUPL_MMA_TS(0, "%3", "0", "one") DUPL_MMA_TS(8, "%3", "128", "one") DUPL_MMA_TS(16, "%3", "256", "one") DUPL_MMA_TS(24, "%3", "384", "one")  // hi * lo
-      DUPL_MMA_TS(32, "%2", "0", "one") DUPL_MMA_TS(40, "%2", "128", "one") DUPL_MMA_TS(48, "%2", "256", "one") DUPL_MMA_TS(56, "%2", "384", "one")  // lo * hi
-      "}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
-      : "memory");
-}
 
 __device__ __forceinline__ void store_split_row(uint32_t taddr, const float (&v)[64]) {
   uint32_t hi[32], lo[32];
@@ -139,7 +90,7 @@ __device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
 // memory), so the tensor pipe always has the next tile's products queued while the exp / split arithmetic of the current tile
 // runs; the only waits left on the critical path are for data that was issued a whole iteration earlier.  (The round-1
 // kernels ran MMA -> wait -> arithmetic -> wait -> MMA strictly in sequence: 26-29 % tensor-pipe activity.)
-constexpr int AB_STAGES = 3;
+constexpr int AB_STAGES = 4;
 
 // ------------------------------------------------------------------------------------------------ dQ
 // grid (q tiles of 128, heads, images)
@@ -153,19 +104,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AB_STAGES * 2 * AB_T64);
   uint64_t* bar_q = bars;          // Q, dO landed
   uint64_t* bar_kv = bars + 1;     // [AB_STAGES]
-  uint64_t* bar_s = bars + 4;      // [2] S, dP of tile j complete (buffer j & 1)
-  uint64_t* bar_d = bars + 6;      // [2] dQ MMAs of tile j complete (dS buffer j & 1, K/V stage j % 3 free)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_s = bars + 5;      // [2] S, dP of tile j complete (buffer j & 1)
+  uint64_t* bar_d = bars + 7;      // [2] dQ MMAs of tile j complete (dS buffer j & 1, K/V stage of tile j free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int hd = p.heads * 64;
   const int row0 = p.row_offset + img * p.tokens;
   const int n_kv = (p.tokens + 63) / 64;
-  uint64_t* bar_ds = bars + 8;     // [2] dS of tile j stored by all arithmetic warps (count = AB_MATH_WARPS)
+  uint64_t* bar_ds = bars + 9;     // [2] dS of tile j stored by all arithmetic warps (count = AB_MATH_WARPS)
 
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     mbar_init(&bar_ds[0], AB_MATH_WARPS);
     mbar_init(&bar_ds[1], AB_MATH_WARPS);
     fence_mbar_init();
@@ -221,17 +172,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
       // S / dP of tile j+1 overwrite the buffers of tile j-1: the arithmetic warps are done with those (their bar_ds arrival
       // for tile j-1 was waited for below, one turn ago)
       if (j + 1 < n_kv) issue_s_dp(j + 1);
+      // tile j+3 goes into the stage of tile j-1, free once dQ(j-1) has completed.  The load is issued HERE, two turns before
+      // its S / dP products are: with the refill at the end of the turn and one stage less, every tile paid the full TMA
+      // latency on this warp's critical path (the arithmetic warps then spent half their time waiting for S / dP).
+      if (j >= 1 && j + 3 < n_kv) {
+        mbar_wait(&bar_d[b ^ 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
+        if (lane == 0) load_kv(j + 3);
+        __syncwarp();
+      }
       mbar_wait(&bar_ds[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
       const uint32_t k0 = smem_u32(sK + (j % AB_STAGES) * 2 * AB_T64);
-      mma_ts_split(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, j > 0);  // dQ += dS K
+      mma_ts_split<128>(tm + TM_DQ, tm + TM_DS + b * 64, umma_desc_sw128(k0), umma_desc_sw128(k0 + AB_T64), idesc_mn, j > 0);  // dQ += dS K
       tc_commit(&bar_d[b]);
-      // tile j+2 goes into the stage of tile j-1, free once dQ(j-1) (issued a whole turn ago) has completed
-      if (j >= 1 && j + 2 < n_kv) {
-        mbar_wait(&bar_d[b ^ 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
-        if (lane == 0) load_kv(j + 2);
-        __syncwarp();
-      }
     }
   } else {
     // ------------------------------------------------------------------ arithmetic warps: thread = (row, 16-column group)
@@ -293,21 +246,21 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + AB_STAGES * 2 * AB_T64);
   uint64_t* bar_kv = bars;
   uint64_t* bar_q = bars + 1;  // [AB_STAGES]
-  uint64_t* bar_s = bars + 4;  // [2] S^T, dP^T of tile i complete (buffer i & 1)
-  uint64_t* bar_d = bars + 6;  // dV / dK MMAs of a tile complete (P^T / dS^T buffer and Q/dO stage free): one phase per tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_s = bars + 5;  // [2] S^T, dP^T of tile i complete (buffer i & 1)
+  uint64_t* bar_d = bars + 7;  // dV / dK MMAs of a tile complete (P^T / dS^T buffer and Q/dO stage free): one phase per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   // per 64-query tile: lse * log2(e) (+inf on padding rows) | D, double-buffered; [tile & 1][0:64 lse2, 64:128 D]
-  float* s_stat = reinterpret_cast<float*>(bars + 12);
+  float* s_stat = reinterpret_cast<float*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
   const int hd = p.heads * 64;
   const int row0 = p.row_offset + img * p.tokens;
   const int n_q = (p.tokens + 63) / 64;
-  uint64_t* bar_ds = bars + 7;  // P^T / dS^T of a tile stored by all arithmetic warps (count = AB_MATH_WARPS): one phase per tile
+  uint64_t* bar_ds = bars + 8;  // P^T / dS^T of a tile stored by all arithmetic warps (count = AB_MATH_WARPS): one phase per tile
 
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_ds, AB_MATH_WARPS);
     fence_mbar_init();
   }
@@ -360,20 +313,20 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     issue_s_dp(0);
     for (int i = 0; i < n_q; ++i) {
       if (i + 1 < n_q) issue_s_dp(i + 1);  // queued behind dV / dK of tile i-1
-      mbar_wait(bar_ds, static_cast<uint32_t>(i & 1));
-      tc_fence_after();
-      // tile i+2 goes into the stage of tile i-1, free once dV / dK of tile i-1 have completed — which they have: the
-      // arithmetic warps waited for exactly that before they stored tile i.  (The wait sits BEFORE this tile's commit: with
-      // one barrier for all tiles, a wait issued after it could find the phase flipped twice.)
-      if (i >= 1 && i + 2 < n_q) {
+      // tile i+3 goes into the stage of tile i-1, free once dV / dK of tile i-1 have completed; issued two turns before its
+      // S^T / dP^T products are.  (The wait sits BEFORE this tile's commit: with one barrier for all tiles, a wait issued after
+      // it could find the phase flipped twice.)
+      if (i >= 1 && i + 3 < n_q) {
         mbar_wait(bar_d, static_cast<uint32_t>((i - 1) & 1));
-        if (lane == 0) load_q(i + 2);
+        if (lane == 0) load_q(i + 3);
         __syncwarp();
       }
+      mbar_wait(bar_ds, static_cast<uint32_t>(i & 1));
+      tc_fence_after();
       const int st = i % AB_STAGES;
       const uint32_t q0 = smem_u32(sQ + st * 2 * AB_T64), o0 = smem_u32(sdO + st * 2 * AB_T64);
-      mma_ts_split(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, i > 0);   // dV += P^T dO
-      mma_ts_split(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, i > 0);  // dK += dS^T Q
+      mma_ts_split<128>(tm + TM_DV, tm + TM_PT, umma_desc_sw128(o0), umma_desc_sw128(o0 + AB_T64), idesc_mn, i > 0);   // dV += P^T dO
+      mma_ts_split<128>(tm + TM_DK, tm + TM_DST, umma_desc_sw128(q0), umma_desc_sw128(q0 + AB_T64), idesc_mn, i > 0);  // dK += dS^T Q
       tc_commit(bar_d);
     }
   } else {

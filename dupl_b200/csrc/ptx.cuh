@@ -255,6 +255,72 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, in
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- batched issue of a 3-pass split product
+// The 12 MMAs of one 3-pass split product (64-deep contraction = 4 k-steps per pass) as ONE asm block: one elect.sync for the
+// batch and the descriptor increments as immediates.  Issued one C++ call per MMA (elect + setp + two 64-bit adds each, every
+// MMA's predicate depending on its own elect), a single warp got out one 128x64x16 MMA per ~45 cycles — more than the 32-48
+// cycles the tensor pipe needs for it, so the ISSUING warp bounded both backward kernels (ncu: 34-40 % tensor-pipe activity,
+// arithmetic warps waiting on the S / dP barrier).
+#define DUPL_MMA_SS(A, B, KA, KB, ACC)                                                                     \
+  "add.u64 ta, " A ", " #KA ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                            \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, " ACC ";\n\t"
+#define DUPL_MMA_SS_PASS(A, B, S1, S2, S3, ACC0)                                                           \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " ACC0 ";\n\t"                               \
+  DUPL_MMA_SS(A, B, 2, S1, "one") DUPL_MMA_SS(A, B, 4, S2, "one") DUPL_MMA_SS(A, B, 6, S3, "one")
+// D[tmem] (+)= A[smem] B[smem]^T, 3-pass split; BSTEP = descriptor step of B per k-step in 16-byte units: 2 (K-major B,
+// 32 B) or 128 (MN-major B, 2048 B = 16 rows)
+template <int BSTEP>
+__device__ __forceinline__ void mma_ss_split(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, bool accumulate) {
+  static_assert(BSTEP == 2, "only the K-major B form is instantiated");
+  asm volatile(
+      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 ta, tb;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 one, 0, 0;\n\t"
+      DUPL_MMA_SS_PASS("%1", "%3", "2", "4", "6", "p")     // hi * hi
+      DUPL_MMA_SS_PASS("%1", "%4", "2", "4", "6", "one")   // hi * lo
+      DUPL_MMA_SS_PASS("%2", "%3", "2", "4", "6", "one")   // lo * hi
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
+}
+#define DUPL_MMA_TS(AOFF, B, KB, ACC)                                                                      \
+  "add.u32 sa, %1, " #AOFF ";\n\tadd.u64 tb, " B ", " KB ";\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [sa], tb, %4, " ACC ";\n\t"
+// same with A in tensor memory (hi plane at a_tmem, lo plane 32 columns further; 8 columns per k-step); BSTEP = 2 (K-major B)
+// or 128 (MN-major B: 2048 B = 16 rows per k-step)
+template <int BSTEP>
+__device__ __forceinline__ void mma_ts_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                             bool accumulate) {
+  static_assert(BSTEP == 2 || BSTEP == 128, "B descriptor step: 2 (K-major) or 128 (MN-major)");
+  if (BSTEP == 2) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, one;\n\t.reg .b64 tb;\n\t.reg .b32 sa;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 one, 0, 0;\n\t"
+        DUPL_MMA_TS(0, "%2", "0", "p") DUPL_MMA_TS(8, "%2", "2", "one") DUPL_MMA_TS(16, "%2", "4", "one") DUPL_MMA_TS(24, "%2", "6", "one")      // hi * hi
+        DUPL_MMA_TS(0, "%3", "0", "one") DUPL_MMA_TS(8, "%3", "2", "one") DUPL_MMA_TS(16, "%3", "4", "one") DUPL_MMA_TS(24, "%3", "6", "one")  // hi * lo
+        DUPL_MMA_TS(32, "%2", "0", "one") DUPL_MMA_TS(40, "%2", "2", "one") DUPL_MMA_TS(48, "%2", "4", "one") DUPL_MMA_TS(56, "%2", "6", "one")  // lo * hi
+        "}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
+        : "memory");
+    return;
+  }
+  asm volatile(
+      "{\n\t.reg .pred e, p, one;\n\t.reg .b64 tb;\n\t.reg .b32 sa;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 one, 0, 0;\n\t"
+      DUPL_MMA_TS(0, "%2", "0", "p") DUPL_MMA_TS(8, "%2", "128", "one") DUPL_MMA_TS(16, "%2", "256", "one") DUPL_MMA_TS(24, "%2", "384", "one")      // hi * hi
+      DUPL_MMA_TS(0, "%3", "0", "one") DUPL_MMA_TS(8, "%3", "128", "one") DUPL_MMA_TS(16, "%3", "256", "one") DUPL_MMA_TS(24, "%3", "384", "one")  // hi * lo
+      DUPL_MMA_TS(32, "%2", "0", "one") DUPL_MMA_TS(40, "%2", "128", "one") DUPL_MMA_TS(48, "%2", "256", "one") DUPL_MMA_TS(56, "%2", "384", "one")  // lo * hi
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- split-bf16 helpers
 // x = hi + lo + O(2^-17 |x|): two bf16 planes carry ~16 mantissa bits through the tensor core.
 // Experiment builds only (make emu, tools/precision_table.py): -DDUPL_EMU_TF32 rounds every value to TF32 (10 explicit
