@@ -136,3 +136,52 @@ class SegCrfSweep:
             cms["crf"].update(gt, out["crf_pred"][0])
             cms["cam"].update(gt, out["cam_label"][0], pseudo=True)
         return {k: cm.all_reduce().scores() for k, cm in cms.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Interop with the files the reference's tools write and read
+# ---------------------------------------------------------------------------------------------------------------------
+def load_checkpoint(model, path_or_state_dict, map_location="cpu"):
+    """tools/eval_seg_voc.py:172-177 / eval_seg_coco_ddp.py: the training script saves `model.state_dict()` of the
+    DistributedDataParallel wrapper (train_final_voc.py:508), so every key carries a `module.` prefix; the tools strip it and
+    load with strict=True.  Same here (into a dupl_b200 siamese_network, whose state-dict schema is the reference's)."""
+    from collections import OrderedDict
+    sd = torch.load(path_or_state_dict, map_location=map_location) if isinstance(path_or_state_dict, (str, bytes)) or hasattr(
+        path_or_state_dict, "__fspath__") else path_or_state_dict
+    new = OrderedDict((k.replace("module.", ""), v) for k, v in sd.items())
+    model.load_state_dict(state_dict=new, strict=True)
+    return model
+
+
+def save_msc_seg(path, seg):
+    """tools/eval_seg_voc.py:83-84: the multi-scale logits of one image as a pickled dict `{"msc_seg": float32[1,C,h,w]}`."""
+    import numpy as np
+    np.save(path, {"msc_seg": seg.detach().float().cpu().numpy()})
+
+
+def load_msc_seg(path, device=None):
+    """tools/eval_seg_voc.py:116-117 (`np.load(..., allow_pickle=True).item()["msc_seg"]`) -> float32 tensor [1,C,h,w]."""
+    import numpy as np
+    arr = np.load(path, allow_pickle=True).item()["msc_seg"]
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+    return t.to(device) if device is not None else t
+
+
+def crf_from_logits_file(logit_path, image_u8, crf=None, device="cuda"):
+    """crf_proc._job (tools/eval_seg_voc.py:113-137) for one image on the GPU: logits file + uint8 image [H,W,3] (numpy or
+    tensor) -> (pred uint8 [H,W] numpy, Q float32 [C,H,W] cuda)."""
+    import numpy as np
+    crf = crf or DenseCRF(iter_max=10, pos_w=1, pos_xy_std=1, bi_w=4, bi_xy_std=121, bi_rgb_std=5)
+    img = torch.as_tensor(np.ascontiguousarray(image_u8) if not torch.is_tensor(image_u8) else image_u8).to(device=device, dtype=torch.uint8)
+    H, W = img.shape[:2]
+    logit = F.interpolate(load_msc_seg(logit_path, device), size=(H, W), mode="bilinear", align_corners=False)
+    q = crf(img, F.softmax(logit, dim=1)[0])
+    return q.argmax(0).to(torch.uint8).cpu().numpy(), q
+
+
+def save_label_png(path, pred):
+    """imageio.imsave(segs_dir/name.png, pred.astype(uint8)) of the tools (tools/eval_seg_voc.py:140): 8-bit single-channel PNG."""
+    import numpy as np
+    from PIL import Image
+    arr = pred.detach().cpu().numpy() if torch.is_tensor(pred) else np.asarray(pred)
+    Image.fromarray(np.squeeze(arr).astype(np.uint8)).save(path)
