@@ -354,6 +354,9 @@ class Harness:
 
     def finish(self):
         if self.dist is not None:
+            import gc
+            gc.collect()                  # captured graphs that still reference NCCL work must be gone first
+            torch.cuda.synchronize()
             self.dist.destroy_process_group()
 
 

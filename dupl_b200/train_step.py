@@ -219,6 +219,13 @@ class TrainStep:
         self.thres_start = torch.ones(K, device=dev) * args.high_thre
         self.thres_target = torch.tensor(args.high_thres_target, dtype=torch.float32, device=dev)
 
+    def close(self):
+        """Drops the captured graphs (they hold the NCCL work of the gradient group: release them before
+        torch.distributed.destroy_process_group(), which otherwise waits forever for the communicator)."""
+        self._graphs.clear()
+        for st in (self.pseudo, self._cam_only, self._cam_aux):
+            st._g = None
+
     # ------------------------------------------------------------------ pieces
     def _forward(self, inputs, inputs_aug=None):
         model = self.model

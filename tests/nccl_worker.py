@@ -103,6 +103,12 @@ def main():
         print("RESULT " + json.dumps({"world": world, "grad_mean_worst_rel": float(w), "missing": missing[:5], "chunks": chunks,
                                       "params_checked": int(chk.numel()), "params_in_sync": bool((lo == hi).all()),
                                       "params_moved": moved, "losses": losses}))
+    # the captured graphs hold NCCL work of the gradient group: release them before the communicators go away
+    # (destroy_process_group() blocks forever on a communicator that a live CUDA graph still references)
+    import gc
+    del step, opt, m2, m, eager
+    gc.collect()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
