@@ -93,6 +93,17 @@ class CrfArgs(C.Structure):
                 ("values", C.c_void_p), ("values_bytes", C.c_size_t), ("meta", C.c_void_p)]
 
 
+class AdamwParam(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("plane_hi", C.c_void_p), ("plane_lo", C.c_void_p), ("numel", C.c_int64), ("lr", C.c_float), ("reserved", C.c_int32)]
+
+
+class AdamwArgs(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("items", C.c_void_p), ("active", C.c_void_p), ("steps", C.c_void_p), ("coef", C.c_void_p),
+                ("lr_scale", C.c_void_p), ("n_params", C.c_int32), ("n_items", C.c_int64),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/dupl.h
 _PROTOTYPES = {
     "dupl_version": (C.c_int, []),
@@ -145,6 +156,8 @@ _PROTOTYPES = {
     "dupl_ptc_mask_reduce": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dupl_ptc_dg": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 3),
     "dupl_ptc_norm_bwd_rows": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p] * 2),
+    "dupl_adamw_items": (C.c_int, [c_i64p, C.c_int32, c_i32p, C.c_int64, c_i64p]),
+    "dupl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p]),
     "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,
                                   C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "dupl_crf_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

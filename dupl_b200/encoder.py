@@ -80,6 +80,15 @@ class StudentPlanes:
             else:
                 ops.split_bf16(w, out=hit[1])
 
+    def sync_keys(self):
+        """Declares every cached plane current for the parameters as they are now (after refresh_all(), or when an optimizer
+        that writes the planes itself — optim.FusedPolyWarmupAdamW — owns them)."""
+        for name, (key, planes) in list(self._planes.items()):
+            if name.endswith("^T"):
+                continue
+            p = self._params()[name]
+            self._planes[name] = ((p.data_ptr(), p._version), planes)
+
     def plane_t(self, name):
         """Transposed planes [K, N] of a Linear weight [N, K] (B operand of the dgrad GEMM), cached like plane()."""
         p = self._params()[name]

@@ -144,9 +144,29 @@ class PolyWarmupAdamW(torch.optim.AdamW):
         super().step(closure)
 
 
-def make_optimizer(model, args=Args, capturable=False):
-    """utils/train_helper.py:21-87 (get_optimizer): 4 groups, heads and decoders at 10x learning rate."""
+def make_optimizer(model, args=Args, capturable=False, fused=None):
+    """utils/train_helper.py:21-87 (get_optimizer): 4 groups, heads and decoders at 10x learning rate.
+    fused (default: on for capturable on CUDA; DUPL_FUSED_ADAMW=0 switches it off): optim.FusedPolyWarmupAdamW, one launch
+    for all tensors of both students that also rewrites the split-bf16 planes of the GEMM weights."""
+    import os
     g = model.get_param_groups()
+    if fused is None:
+        fused = capturable and os.environ.get("DUPL_FUSED_ADAMW", "1") != "0"
+    if fused and all(p.is_cuda for grp in g for p in grp):
+        from .optim import FusedPolyWarmupAdamW
+        lookup = {}
+        for net in (model.branch1, model.branch2):
+            pl = net.planes()
+            pdict = dict(net.encoder.named_parameters())
+            for name in pl.GEMM_WEIGHTS:
+                lookup[id(pdict[name])] = pl.plane(name)
+        return FusedPolyWarmupAdamW(
+            params=[{"params": g[0], "lr": args.lr, "weight_decay": args.wt_decay},
+                    {"params": g[1], "lr": args.lr, "weight_decay": args.wt_decay},
+                    {"params": g[2], "lr": args.lr * 10, "weight_decay": args.wt_decay},
+                    {"params": g[3], "lr": args.lr * 10, "weight_decay": args.wt_decay}],
+            lr=args.lr, weight_decay=args.wt_decay, betas=args.betas, warmup_iter=args.warmup_iters, max_iter=args.max_iters,
+            warmup_ratio=args.warmup_lr, power=args.power, plane_lookup=lambda p: lookup.get(id(p)))
     on_gpu = all(p.is_cuda for grp in g for p in grp)  # torch's single-kernel-per-chunk AdamW (same update rule)
     return PolyWarmupAdamW(
         params=[{"params": g[0], "lr": args.lr, "weight_decay": args.wt_decay},
@@ -171,6 +191,7 @@ class TrainStep:
         self.args = args
         self.capture = capture
         self._graphs = {}
+        self._last_graph_key = None
         self._sched = None          # static device scalars of the threshold schedule while capturing / replaying
         dev = device or next(model.parameters()).device
         self.par = PAR(num_iter=10, dilations=[1, 2, 4, 8, 12, 24]).to(dev)
@@ -414,7 +435,9 @@ class TrainStep:
                 # state and schedule are put back afterwards, so the first captured call is ONE training step like any other
                 params = [p for g in self.optim.param_groups for p in g["params"]]
                 saved_p = [p.detach().clone() for p in params]
-                saved_s = {p: {k: v.clone() for k, v in s.items() if torch.is_tensor(v)} for p, s in self.optim.state.items()}
+                fused_opt = hasattr(self.optim, "snapshot")
+                saved_s = self.optim.snapshot() if fused_opt else \
+                    {p: {k: v.clone() for k, v in s.items() if torch.is_tensor(v)} for p, s in self.optim.state.items()}
                 saved_step = self.optim.global_step
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
@@ -426,13 +449,21 @@ class TrainStep:
                     with torch.no_grad():
                         for p, q in zip(params, saved_p):
                             p.copy_(q)
-                        for p, s in self.optim.state.items():
-                            for k, v in s.items():
-                                if torch.is_tensor(v):
-                                    if p in saved_s and k in saved_s[p]:
-                                        v.copy_(saved_s[p][k])
-                                    else:
-                                        v.zero_()
+                        if fused_opt:
+                            self.optim.restore(saved_s)
+                        else:
+                            for p, s in self.optim.state.items():
+                                for k, v in s.items():
+                                    if torch.is_tensor(v):
+                                        if p in saved_s and k in saved_s[p]:
+                                            v.copy_(saved_s[p][k])
+                                        else:
+                                            v.zero_()
+                        # the weight planes follow the restored parameters; with the fused optimizer they are never re-split
+                        # inside the graph (its update kernel rewrites them), so they must be current when capture starts
+                        for b in (self.model.branch1, self.model.branch2):
+                            b.planes().refresh_all()
+                            b.planes().sync_keys()
                 torch.cuda.current_stream(dev).wait_stream(side)
                 self.optim.global_step = saved_step
                 del saved_p, saved_s
@@ -448,12 +479,22 @@ class TrainStep:
                     self._backward(loss)
                     self.optim.step_captured()
                 st["graph"], st["loss"], st["parts"] = graph, loss.detach(), {k: v.detach() for k, v in parts.items()}
+                if fused_opt:
+                    st["opt_tables"] = self.optim.export_tables()
+            if st.get("opt_tables") is not None and self._last_graph_key not in (None, key):
+                self.optim.import_tables(st["opt_tables"])   # another phase's graph ran in between: its flags / pointers differ
+            self._last_graph_key = key
             self.optim.advance_schedule()
             st["graph"].replay()
             # the replay updated the parameters without bumping `_version`: eager users of the weight planes must re-split
             net = self.model
             for b in (net.branch1, net.branch2):
-                b.planes().invalidate()
+                if hasattr(self.optim, "snapshot"):
+                    b.planes().sync_keys()      # the fused optimizer rewrote the planes itself; transposed copies stay graph-internal
+                    for name in [n for n in b.planes()._planes if n.endswith("^T")]:
+                        del b.planes()._planes[name]
+                else:
+                    b.planes().invalidate()
                 if getattr(b, "_dec_planes", None) is not None:
                     b._dec_planes.invalidate()
         finally:

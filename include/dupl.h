@@ -387,6 +387,39 @@ int dupl_ptc_dg(const float* G, const int64_t* mask, const float* stats, const f
 int dupl_ptc_norm_bwd_rows(const float* x, const float* inv, const float* dxh_rows, int32_t b, int32_t C, int32_t n, float* dx,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer: fused multi-tensor PolyWarmupAdamW (utils/optimizer.py:38-68, utils/train_helper.py:21-52).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dupl_adamw_param {
+  void* param;        /* fp32, updated in place */
+  const void* grad;   /* fp32 (a view of the student's gradient arena) */
+  void* exp_avg;      /* fp32 */
+  void* exp_avg_sq;   /* fp32 */
+  void* plane_hi;     /* bf16 split planes of the updated parameter in the same element order, or NULL */
+  void* plane_lo;
+  int64_t numel;      /* multiple of 4; every pointer 16-byte aligned */
+  float lr;           /* initial learning rate of the parameter's group (utils/train_helper.py: lr, or 10 lr for heads/decoders) */
+  int32_t reserved;
+} dupl_adamw_param;
+
+typedef struct dupl_adamw_args {
+  const dupl_adamw_param* params; /* device table [n_params] */
+  const int32_t* items;           /* device work list [n_items][2] = (parameter index, chunk of 2048 elements): dupl_adamw_items */
+  const int32_t* active;          /* device [n_params]: 1 = this parameter has a gradient this step (torch skips p.grad is None) */
+  int32_t* steps;                 /* device [n_params]: per-parameter step count, incremented for active parameters */
+  float* coef;                    /* device scratch [n_params][2]: 1/bias_correction1, sqrt(bias_correction2) */
+  const float* lr_scale;          /* device scalar: the schedule multiplier of this step (utils/optimizer.py:52-66) */
+  int32_t n_params;
+  int64_t n_items;
+  float beta1, beta2, eps, weight_decay;
+} dupl_adamw_args;
+
+/* Host-only: fills the work list for tensors of the given sizes (items_xy may be NULL to query the count). */
+int dupl_adamw_items(const int64_t* numel, int32_t n_params, int32_t* items_xy, int64_t capacity, int64_t* n_items);
+/* One AdamW step of every active parameter (decoupled weight decay, bias correction from the per-parameter step count,
+ * torch.optim.AdamW's operation order) + refresh of the split planes.  Two launches, no host synchronisation. */
+int dupl_adamw_step(const dupl_adamw_args* args, void* stream);
+
 /* GMM noise filter of the training loop (train_final_voc.py:358-394, sklearn GaussianMixture in the
  * reference): per image, 2-component 1-D mixture on loss[label not in {0, ignore} and loss > loss_min]; when more
  * than min_count samples exist and the means differ by more than valid_gap, every pixel whose posterior under
