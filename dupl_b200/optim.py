@@ -136,6 +136,8 @@ class FusedPolyWarmupAdamW:
     def export_tables(self):
         """The device tables as they are now (pointer table, active flags): a CUDA graph captured in this phase reads them at
         replay time, so a driver that keeps graphs of several phases restores them before replaying another phase's graph."""
+        if not self._built:
+            self._build()
         return dict(table=self._table.clone(), active=self._active.clone(), key=self._grad_ptrs)
 
     def import_tables(self, t):
@@ -144,6 +146,8 @@ class FusedPolyWarmupAdamW:
         self._grad_ptrs = t["key"]
 
     def snapshot(self):
+        if not self._built:
+            self._build()
         return dict(m=self._m.clone(), v=self._v.clone(), steps=self._steps.clone(), global_step=self.global_step,
                     lrs=[g["lr"] for g in self.param_groups])
 
