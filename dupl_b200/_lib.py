@@ -156,6 +156,11 @@ _PROTOTYPES = {
     "dupl_ptc_mask_reduce": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dupl_ptc_dg": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 3),
     "dupl_ptc_norm_bwd_rows": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p] * 2),
+    "dupl_cls_loss_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dupl_cls_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dupl_sim_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dupl_sim_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "dupl_adamw_items": (C.c_int, [c_i64p, C.c_int32, c_i32p, C.c_int64, c_i64p]),
     "dupl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p]),
     "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,

@@ -459,11 +459,13 @@ class TrainStep:
                                             v.copy_(saved_s[p][k])
                                         else:
                                             v.zero_()
-                        # the weight planes follow the restored parameters; with the fused optimizer they are never re-split
-                        # inside the graph (its update kernel rewrites them), so they must be current when capture starts
-                        for b in (self.model.branch1, self.model.branch2):
-                            b.planes().refresh_all()
-                            b.planes().sync_keys()
+                        if fused_opt:
+                            # the weight planes follow the restored parameters; with the fused optimizer they are never
+                            # re-split inside the graph (its update kernel rewrites them), so they must be current when capture
+                            # starts.  (With torch's AdamW the stale keys are what makes the capture record the re-split.)
+                            for b in (self.model.branch1, self.model.branch2):
+                                b.planes().refresh_all()
+                                b.planes().sync_keys()
                 torch.cuda.current_stream(dev).wait_stream(side)
                 self.optim.global_step = saved_step
                 del saved_p, saved_s

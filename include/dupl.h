@@ -387,6 +387,19 @@ int dupl_ptc_dg(const float* G, const int64_t* mask, const float* stats, const f
 int dupl_ptc_norm_bwd_rows(const float* x, const float* inv, const float* dxh_rows, int32_t b, int32_t C, int32_t n, float* dx,
                            void* stream);
 
+/* Classification loss of the loop (train_final_voc.py:299-305): sum over the T (= 4) logit tensors [b, K] of
+ * F.multilabel_soft_margin_loss(logits_t, cls_label) = mean over b*K of -[y logsigmoid(x) + (1 - y) logsigmoid(-x)].
+ * logits_dev / grads_dev: DEVICE arrays of T device pointers; label fp32 [n = b*K]; loss / grad_out: device scalars. */
+int dupl_cls_loss_fwd(const float* const* logits_dev, int32_t T, const float* label, int32_t n, float* loss, void* stream);
+int dupl_cls_loss_bwd(const float* const* logits_dev, float* const* grads_dev, int32_t T, const float* label, int32_t n,
+                      const float* grad_out, void* stream);
+/* Discrepancy loss (train_final_voc.py:440-447): (1 + mean cos(f1.detach(), f2)) + (1 + mean cos(f2.detach(), f1)) with
+ * nn.CosineSimilarity(dim=-1, eps) over rows = b*768 vectors of n = 784 spatial positions.  bwd: d1 = d loss / d f1 (from the
+ * second term), d2 = d loss / d f2 (from the first), both scaled by *grad_out. */
+int dupl_sim_loss_fwd(const float* f1, const float* f2, int32_t rows, int32_t n, float eps, float* cos_rows, float* loss, void* stream);
+int dupl_sim_loss_bwd(const float* f1, const float* f2, int32_t rows, int32_t n, float eps, const float* grad_out, float* d1, float* d2,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer: fused multi-tensor PolyWarmupAdamW (utils/optimizer.py:38-68, utils/train_helper.py:21-52).
  * ---------------------------------------------------------------------------------------- */
