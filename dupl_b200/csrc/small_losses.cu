@@ -19,15 +19,20 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // logsigmoid(x) = min(x, 0) - log1p(exp(-|x|))  (torch's formula)
 __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.0f) - log1pf(expf(-fabsf(x))); }
 
+struct ClsPtrs {   // by value in the kernel parameters: no device-side pointer table, nothing to copy before a (captured) launch
+  const float* x[8];
+  float* g[8];
+};
+
 // loss = sum_t mean_{b,k} -[y logsig(x_t) + (1 - y) logsig(-x_t)] over the T logit tensors; one block.
-__global__ void __launch_bounds__(256) cls_loss_fwd_kernel(const float* const* __restrict__ logits, int T,
+__global__ void __launch_bounds__(256) cls_loss_fwd_kernel(const ClsPtrs ptrs, int T,
                                                            const float* __restrict__ label, int n, float* __restrict__ loss) {
   __shared__ float sh[8];
   float total = 0.0f;
   for (int t = 0; t < T; ++t) {           // one mean per tensor, then their sum: the order of the script
     float acc = 0.0f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float x = logits[t][i], y = label[i];
+      const float x = ptrs.x[t][i], y = label[i];
       acc -= y * log_sigmoid(x) + (1.0f - y) * log_sigmoid(-x);
     }
     acc = warp_sum_f(acc);
@@ -44,15 +49,14 @@ __global__ void __launch_bounds__(256) cls_loss_fwd_kernel(const float* const* _
 }
 
 // d loss / d x_t[i] = gout * (sigmoid(x) - y) / n
-__global__ void __launch_bounds__(256) cls_loss_bwd_kernel(const float* const* __restrict__ logits, float* const* __restrict__ grads,
-                                                           int T, const float* __restrict__ label, int n,
+__global__ void __launch_bounds__(256) cls_loss_bwd_kernel(const ClsPtrs ptrs, int T, const float* __restrict__ label, int n,
                                                            const float* __restrict__ gout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (i >= n || t >= T) return;
-  const float x = logits[t][i];
+  const float x = ptrs.x[t][i];
   const float s = 1.0f / (1.0f + expf(-x));
-  grads[t][i] = __ldg(gout) * (s - label[i]) / static_cast<float>(n);
+  ptrs.g[t][i] = __ldg(gout) * (s - label[i]) / static_cast<float>(n);
 }
 
 // One warp per (image, channel) row of n spatial positions: cos = (x . y) / (max(|x|, eps) max(|y|, eps))
@@ -117,17 +121,28 @@ __global__ void __launch_bounds__(256) sim_finish_kernel(const float* __restrict
 
 using namespace dupl;
 
-extern "C" int dupl_cls_loss_fwd(const float* const* logits_dev, int32_t T, const float* label, int32_t n, float* loss, void* stream) {
-  DUPL_CHECK_ARG(logits_dev && label && loss && T >= 1 && T <= 8 && n > 0, "dupl_cls_loss_fwd: bad arguments");
-  cls_loss_fwd_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, T, label, n, loss);
+extern "C" int dupl_cls_loss_fwd(const float* const* logits, int32_t T, const float* label, int32_t n, float* loss, void* stream) {
+  DUPL_CHECK_ARG(logits && label && loss && T >= 1 && T <= 8 && n > 0, "dupl_cls_loss_fwd: bad arguments");
+  ClsPtrs P = {};
+  for (int t = 0; t < T; ++t) {
+    DUPL_CHECK_ARG(logits[t] != nullptr, "dupl_cls_loss_fwd: logits[%d] is NULL", t);
+    P.x[t] = logits[t];
+  }
+  cls_loss_fwd_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, T, label, n, loss);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }
 
-extern "C" int dupl_cls_loss_bwd(const float* const* logits_dev, float* const* grads_dev, int32_t T, const float* label, int32_t n,
+extern "C" int dupl_cls_loss_bwd(const float* const* logits, float* const* grads, int32_t T, const float* label, int32_t n,
                                  const float* grad_out, void* stream) {
-  DUPL_CHECK_ARG(logits_dev && grads_dev && label && grad_out && T >= 1 && T <= 8 && n > 0, "dupl_cls_loss_bwd: bad arguments");
-  cls_loss_bwd_kernel<<<dim3(cdiv(n, 256), T), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, grads_dev, T, label, n, grad_out);
+  DUPL_CHECK_ARG(logits && grads && label && grad_out && T >= 1 && T <= 8 && n > 0, "dupl_cls_loss_bwd: bad arguments");
+  ClsPtrs P = {};
+  for (int t = 0; t < T; ++t) {
+    DUPL_CHECK_ARG(logits[t] != nullptr && grads[t] != nullptr, "dupl_cls_loss_bwd: NULL tensor %d", t);
+    P.x[t] = logits[t];
+    P.g[t] = grads[t];
+  }
+  cls_loss_bwd_kernel<<<dim3(cdiv(n, 256), T), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, T, label, n, grad_out);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

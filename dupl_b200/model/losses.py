@@ -235,3 +235,76 @@ def get_seg_loss_upsampled(pred_lowres, label, ignore_index=255):
 def get_seg_loss_conflict_v2(*args, **kwargs):
     """train_final_coco.py:21 imports this name but the reference never defines or calls it."""
     raise NotImplementedError("get_seg_loss_conflict_v2 does not exist in the reference's model/losses.py either")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two losses the scripts compute inline with torch ops (train_final_voc.py:299-305 and :440-447), fused (SURVEY A11 / A12)
+# ---------------------------------------------------------------------------------------------------------------------
+def _ptr_table(tensors):
+    """HOST array of the tensors' device pointers (passed by value into the kernel parameters: capturable)."""
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _ClsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls_label, *logits):
+        L.require_cuda(cls_label, *logits)
+        xs = [L.f32c(x.detach()) for x in logits]
+        y = L.f32c(cls_label.detach())
+        if any(x.shape != y.shape for x in xs):
+            raise ValueError("multilabel_soft_margin_sum: every logits tensor must have the shape of cls_label")
+        dev = y.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        tab = _ptr_table(xs)
+        L.check(L.lib().dupl_cls_loss_fwd(tab, len(xs), L.ptr(y), y.numel(), L.ptr(loss), L.stream_ptr(dev)), "dupl_cls_loss_fwd")
+        ctx.xs, ctx.y, ctx.tab = xs, y, tab
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xs, y = ctx.xs, ctx.y
+        grads = [torch.empty_like(x) for x in xs]
+        gtab = _ptr_table(grads)
+        g = L.f32c(grad_out).reshape(1)
+        L.check(L.lib().dupl_cls_loss_bwd(ctx.tab, gtab, len(xs), L.ptr(y), y.numel(), L.ptr(g), L.stream_ptr(y.device)),
+                "dupl_cls_loss_bwd")
+        return (None, *grads)
+
+
+def multilabel_soft_margin_sum(logits, cls_label):
+    """sum_t F.multilabel_soft_margin_loss(logits[t], cls_label) for the 4 classification heads of the two students
+    (train_final_voc.py:299-305) in one kernel (+ one for the gradients)."""
+    return _ClsLoss.apply(cls_label, *logits)
+
+
+class _SimLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, eps):
+        L.require_cuda(f1, f2)
+        a, b = L.f32c(f1.detach()), L.f32c(f2.detach())
+        if a.shape != b.shape or a.dim() != 4:
+            raise ValueError("discrepancy_loss expects two [b, C, h, w] feature maps of the same shape")
+        rows, n = a.shape[0] * a.shape[1], a.shape[2] * a.shape[3]
+        dev = a.device
+        cos_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        L.check(L.lib().dupl_sim_loss_fwd(L.ptr(a), L.ptr(b), rows, n, float(eps), L.ptr(cos_rows), L.ptr(loss), L.stream_ptr(dev)),
+                "dupl_sim_loss_fwd")
+        ctx.a, ctx.b, ctx.eps = a, b, float(eps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.a, ctx.b
+        d1, d2 = torch.empty_like(a), torch.empty_like(b)
+        g = L.f32c(grad_out).reshape(1)
+        L.check(L.lib().dupl_sim_loss_bwd(L.ptr(a), L.ptr(b), a.shape[0] * a.shape[1], a.shape[2] * a.shape[3], ctx.eps, L.ptr(g),
+                                          L.ptr(d1), L.ptr(d2), L.stream_ptr(a.device)), "dupl_sim_loss_bwd")
+        return d1, d2, None
+
+
+def discrepancy_loss(fmap_1, fmap_2, eps=1e-6):
+    """(1 + cos(fmap_1.detach(), fmap_2).mean()) + (1 + cos(fmap_2.detach(), fmap_1).mean()) with
+    nn.CosineSimilarity(dim=-1, eps) over the flattened spatial axis (train_final_voc.py:440-447), fused."""
+    return _SimLoss.apply(fmap_1, fmap_2, eps)

@@ -2,8 +2,8 @@
 loop body of train_final_voc.py:186-472 / train_final_coco.py:182-464 for all three phases (A: n_iter < cam_iters,
 CAM + cls/PTC losses; B: + PAR pseudo-labels and seg loss; C: n_iter >= gmm_iters, + the strongly augmented view, the GMM
 noise filter on the GPU and the consistency term), built from the drop-in modules of this package.  The script-side glue the reference executes with stock torch ops between the
-calls into the model / helpers (classification loss, F.interpolate of logits and CAMs, cosine
-discrepancy loss, loss weighting, AdamW) stays stock torch here as well; everything the reference
+calls into the model / helpers is fused where it costs launches (classification loss x4, cosine discrepancy loss,
+up-sampling + CE, AdamW) and stock torch for the rest (F.interpolate of the CAMs, loss weighting); everything the reference
 reaches through model(...), cam_helper, PAR and model.losses runs in libdupl.so.
 
 Differences from the script, none of which changes a number:
@@ -19,7 +19,8 @@ import torch
 import torch.nn.functional as F
 
 from .gmm import gmm_noise_filter
-from .model.losses import ce_sum_upsampled, get_masked_ptc_loss, get_seg_loss_upsampled
+from .model.losses import (ce_sum_upsampled, discrepancy_loss, get_masked_ptc_loss, get_seg_loss_upsampled,
+                           multilabel_soft_margin_sum)
 from .model.PAR import PAR
 from .pipeline import CamParStep, denormalize_img2
 from .utils import cam_helper
@@ -305,8 +306,8 @@ class TrainStep:
         cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
         cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
 
-        cls_loss = (F.multilabel_soft_margin_loss(cls_1, cls_label) + F.multilabel_soft_margin_loss(cls_aux_1, cls_label) +
-                    F.multilabel_soft_margin_loss(cls_2, cls_label) + F.multilabel_soft_margin_loss(cls_aux_2, cls_label))
+        # 4 x F.multilabel_soft_margin_loss (train_final_voc.py:299-305) in one kernel
+        cls_loss = multilabel_soft_margin_sum((cls_1, cls_aux_1, cls_2, cls_aux_2), cls_f)
 
         if n_iter < a.cam_iters and not a.ptc_in_phase_a:
             ptc_loss = one                                     # train_final_coco.py:216
@@ -344,10 +345,7 @@ class TrainStep:
                     regs.append(ce_sum_upsampled(torch.flip(aug, dims=[3]), target, a.ignore_index))
                 reg_loss = regs[0] + regs[1]
 
-        f1 = fmap_1.view(fmap_1.shape[0], fmap_1.shape[1], -1)
-        f2 = fmap_2.view(fmap_2.shape[0], fmap_2.shape[1], -1)
-        cos = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
-        sim_loss = (1 + cos(f1.detach(), f2).mean()) + (1 + cos(f2.detach(), f1).mean())
+        sim_loss = discrepancy_loss(fmap_1, fmap_2, eps=1e-6)     # train_final_voc.py:440-447, fused
 
         w = a.loss_weights(n_iter)
         loss = w["cls"] * cls_loss + w["ptc"] * ptc_loss + w["seg"] * seg_loss + w["sim"] * sim_loss + w["reg"] * reg_loss

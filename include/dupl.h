@@ -389,9 +389,9 @@ int dupl_ptc_norm_bwd_rows(const float* x, const float* inv, const float* dxh_ro
 
 /* Classification loss of the loop (train_final_voc.py:299-305): sum over the T (= 4) logit tensors [b, K] of
  * F.multilabel_soft_margin_loss(logits_t, cls_label) = mean over b*K of -[y logsigmoid(x) + (1 - y) logsigmoid(-x)].
- * logits_dev / grads_dev: DEVICE arrays of T device pointers; label fp32 [n = b*K]; loss / grad_out: device scalars. */
-int dupl_cls_loss_fwd(const float* const* logits_dev, int32_t T, const float* label, int32_t n, float* loss, void* stream);
-int dupl_cls_loss_bwd(const float* const* logits_dev, float* const* grads_dev, int32_t T, const float* label, int32_t n,
+ * logits / grads: HOST arrays of T (<= 8) device pointers; label fp32 [n = b*K]; loss / grad_out: device scalars. */
+int dupl_cls_loss_fwd(const float* const* logits, int32_t T, const float* label, int32_t n, float* loss, void* stream);
+int dupl_cls_loss_bwd(const float* const* logits, float* const* grads, int32_t T, const float* label, int32_t n,
                       const float* grad_out, void* stream);
 /* Discrepancy loss (train_final_voc.py:440-447): (1 + mean cos(f1.detach(), f2)) + (1 + mean cos(f2.detach(), f1)) with
  * nn.CosineSimilarity(dim=-1, eps) over rows = b*768 vectors of n = 784 spatial positions.  bwd: d1 = d loss / d f1 (from the

@@ -136,3 +136,35 @@ def test_consistency_ce_sum_upsampled_matches_torch(b, C, h, w, H, W, frac):
         assert rel_err(p_gpu.grad, p_ref.grad) < 1e-4
     else:
         assert torch.count_nonzero(p_gpu.grad) == 0
+
+
+def test_fused_classification_and_discrepancy_losses_match_torch():
+    """train_final_voc.py:299-305 (4 x F.multilabel_soft_margin_loss) and :440-447 (cosine discrepancy along the spatial axis):
+    value and gradients of the fused kernels against the torch expressions of the script."""
+    import torch.nn.functional as F
+    from dupl_b200.model.losses import discrepancy_loss, multilabel_soft_margin_sum
+    g = torch.Generator().manual_seed(3)
+    for K, dt in ((20, torch.float32), (80, torch.uint8)):
+        y = (torch.rand(4, K, generator=g) < 0.15).to(dt).cuda()
+        xs = [(torch.randn(4, K, generator=g) * 3).cuda().requires_grad_() for _ in range(4)]
+        ref = sum(F.multilabel_soft_margin_loss(x, y) for x in xs)
+        gr = torch.autograd.grad(ref * 1.7, xs)
+        xs2 = [x.detach().clone().requires_grad_() for x in xs]
+        got = multilabel_soft_margin_sum(xs2, y.float())
+        gg = torch.autograd.grad(got * 1.7, xs2)
+        assert abs(got.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item()))
+        for a, b_ in zip(gg, gr):
+            assert rel_err(a, b_) < 1e-5
+    f1 = torch.randn(4, 768, 28, 28, generator=g).cuda().requires_grad_()
+    f2 = (0.3 * f1.detach() + torch.randn(4, 768, 28, 28, generator=g).cuda()).requires_grad_()
+    cos = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
+    a, b_ = f1.view(4, 768, -1), f2.view(4, 768, -1)
+    ref = (1 + cos(a.detach(), b_).mean()) + (1 + cos(b_.detach(), a).mean())
+    g1, g2 = torch.autograd.grad(ref * 0.1, (f1, f2))
+    x1, x2 = f1.detach().clone().requires_grad_(), f2.detach().clone().requires_grad_()
+    got = discrepancy_loss(x1, x2)
+    h1, h2 = torch.autograd.grad(got * 0.1, (x1, x2))
+    assert abs(got.item() - ref.item()) < 1e-6
+    assert rel_err(h1, g1) < 1e-4 and rel_err(h2, g2) < 1e-4
+    z = torch.zeros(1, 2, 3, 3, device="cuda")                      # zero vectors: norms clamp at eps, loss = 2, no NaN
+    assert discrepancy_loss(z, z).item() == 2.0

@@ -209,11 +209,13 @@ def test_coco_step_matches_oracle_loop(n_iter):
     _check_step(m, P, O.COCO_CFG, CocoArgs, n_iter, 81, cls_dtype=torch.uint8, seed=60)
 
 
-def test_captured_iteration_matches_the_eager_iteration():
-    """TrainStep(capture=True): the whole iteration as one CUDA graph.  Three steps (capture + 2 replays) must leave the same
-    parameters as three eager steps: same kernels in the same order; the only arithmetic difference is torch's capturable
-    AdamW, which evaluates the bias corrections in fp32 on the device (1 - 0.999f is 4.7e-5 off 1e-3) instead of in double
-    on the host, i.e. ~2e-5 relative on the size of the first updates."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_captured_iteration_matches_the_eager_iteration(fused):
+    """TrainStep(capture=True): the whole iteration as one CUDA graph (gradients in the flat arenas, both students' backward in
+    lock step, fused multi-tensor AdamW or torch's capturable AdamW).  Three steps (capture + 2 replays) must leave the same
+    parameters as three eager steps with torch.optim.AdamW: same forward / backward kernels; the optimizers differ by fp32
+    rounding only (torch's capturable AdamW evaluates the bias corrections in fp32 on the device: 1 - 0.999f is 4.7e-5 off
+    1e-3, i.e. ~2e-5 relative on the size of the first updates)."""
     from dupl_b200.train_step import TrainStep, make_optimizer
     from helpers import synth_boxes, synth_cls_labels
     b, S = 2, 64
@@ -223,7 +225,7 @@ def test_captured_iteration_matches_the_eager_iteration():
     finals, losses = [], []
     for capture in (False, True):
         m, _ = _models()
-        optim = make_optimizer(m, capturable=capture)
+        optim = make_optimizer(m, capturable=capture, fused=fused and capture)
         step = TrainStep(m, optim, capture=capture)
         ls = []
         for i in range(3):
@@ -235,6 +237,7 @@ def test_captured_iteration_matches_the_eager_iteration():
     for a, b_ in zip(*losses):
         assert abs(a - b_) < 1e-4 * max(1.0, abs(a)), losses
     assert abs(losses[0][0] - losses[1][0]) < 1e-6 and abs(losses[0][1] - losses[1][1]) < 2e-6   # before any sizeable update: identical
+    assert losses[1][2] != losses[1][0]                      # the replays really train (the forward sees the updated weights)
     worst = max(_nrel(finals[1][n], finals[0][n]) for n in finals[0])
     assert worst < 1e-4, worst
 
