@@ -130,18 +130,30 @@ def _heads(nets, x, aux_seg_only=False):
     return out
 
 
+def _with_cam_grad(net, outs):
+    """model_dupl.py:100-104 (cam_with_grad=True; no reference script uses it): a CAM that carries gradient w.r.t. the feature
+    map, built from `_x4` exactly as the reference does — on top of the kernels' outputs, so autograd reaches the encoder
+    through the feature-map gradient of the student's backward."""
+    import torch.nn.functional as F
+    cls_x4, seg, x4, cls_aux = outs
+    cam_grad = F.conv2d(x4, net.classifier.weight.detach())
+    cam_grad = cam_grad + F.adaptive_max_pool2d(-cam_grad, (1, 1))
+    cam_grad = cam_grad / F.adaptive_max_pool2d(cam_grad, (1, 1)) + 1e-5
+    return cls_x4, seg, x4, cls_aux, cam_grad
+
+
 def network_forward(net, x, val=False, cam_with_grad=False):
-    if cam_with_grad:
-        raise NotImplementedError("cam_with_grad is never used by the reference scripts (model_dupl.py:100-104)")
     if _wants_grad([net]):
         from . import train
-        return train.student_forward(net, x)
-    return _heads([net], x)[0]
+        outs = train.student_forward(net, x)
+    else:
+        outs = _heads([net], x)[0]
+    return _with_cam_grad(net, outs) if cam_with_grad else outs
 
 
 def pair_forward(net1, net2, x, val=False, cam_with_grad=False):
     if cam_with_grad:
-        raise NotImplementedError("cam_with_grad is never used by the reference scripts (model_dupl.py:100-104)")
+        return network_forward(net1, x, cam_with_grad=True), network_forward(net2, x, cam_with_grad=True)
     if _wants_grad([net1, net2]):
         from . import train
         if train._arena_mode(net1) and train._arena_mode(net2) and os.environ.get("DUPL_PAIR_BACKWARD", "1") != "0":

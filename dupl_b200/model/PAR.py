@@ -40,8 +40,9 @@ class PAR(nn.Module):
     def forward(self, imgs, masks):
         L.require_cuda(imgs, masks)
         if masks.shape[-2:] != imgs.shape[-2:]:
-            # PAR.py:66 resizes with align_corners=True; on the hot path the sizes always match.
-            raise NotImplementedError("PAR: masks must already have the image size (identity resize on the hot path)")
+            # PAR.py:66: masks are first brought to the image size (bilinear, align_corners=True).  Every call on the hot path
+            # passes equal sizes (identity); the general case is the reference's own one-line torch resize in front of the kernels.
+            masks = torch.nn.functional.interpolate(masks, size=imgs.shape[-2:], mode="bilinear", align_corners=True)
         if masks.shape[0] != imgs.shape[0]:
             raise ValueError("PAR: imgs and masks must have the same batch size")
         aff = self.affinity(imgs)

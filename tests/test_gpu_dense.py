@@ -210,3 +210,31 @@ def test_val_forward_matches_oracle():
                 assert rel_err(g, w) < 1e-3
         one = m(x.cuda(), val=True, branch=2)
         assert torch.equal(one[1], res["branch2"][1])
+
+
+def test_cam_with_grad_and_par_mask_resize_follow_the_reference():
+    """The two interface corners no reference script exercises: siamese_network.forward(cam_with_grad=True)
+    (model_dupl.py:100-104, 176-185) returns a fifth tensor computed from `_x4` like the reference; PAR.forward resizes masks of
+    another size with align_corners=True (PAR.py:66) before propagating."""
+    import torch.nn.functional as F
+    from dupl_b200.model.PAR import PAR
+    from oracle import dupl_oracle as O
+    m, P = _load_model()
+    x = synth_images(1, 64, 64, seed=6)
+    with torch.no_grad():
+        out = m(x.cuda(), cam_with_grad=True, branch=1)
+        want = O.network_forward(P, 1, x)
+    assert len(out) == 5 and out[4].shape == (1, 20, 4, 4)
+    cg = F.conv2d(want[2], P["branch1.classifier.weight"])
+    cg = cg + F.adaptive_max_pool2d(-cg, (1, 1))
+    cg = cg / F.adaptive_max_pool2d(cg, (1, 1)) + 1e-5
+    assert rel_err(out[4], cg) < 2e-3
+    both = m(x.cuda(), cam_with_grad=True)
+    assert set(both) == {"branch1", "branch2"} and len(both["branch2"]) == 5
+    par = PAR(num_iter=3, dilations=[1, 2]).cuda()
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(1, 3, 24, 20, generator=g)
+    small = torch.rand(1, 3, 12, 10, generator=g).softmax(1)
+    got = par(img.cuda(), small.cuda())
+    ref = O.par_forward(img, F.interpolate(small, size=(24, 20), mode="bilinear", align_corners=True), dilations=(1, 2), num_iter=3)
+    assert got.shape == (1, 3, 24, 20) and (got.cpu() - ref).abs().max().item() < 1e-5
