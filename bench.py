@@ -742,7 +742,7 @@ def measure_crf(h, steps):
 
 def run_train(h, args):
     K = 80 if args.dataset == "coco" else 20
-    t = measure_train(h, args, K, args.steps, args.warmup, want_roofline=True)
+    t = measure_train(h, args, K, args.steps, args.warmup, want_roofline=not args.no_roofline)
     ms_step, e2e_ms = h.max_over_ranks(t["ms"], t["e2e_ms"])
     imgs = BATCH * h.world
     peaks, peak_kind = load_peaks()
@@ -798,9 +798,10 @@ def run_train(h, args):
                     "ms_per_step": e2e_ms},
             "gpu_launches": t.get("launches"), "clocks": t["clocks"], "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),
             "ranks_in_sync": t["ranks_in_sync"], "params_checked": t["params_checked"],
-            "roofline": gemm_roofline(t["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_TRAIN * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
-                                      "the same K steps launched eagerly (no graph, no optimizer step) right after the timed region"),
-            "hbm_kernels": t["timer"].hbm_kernels(peaks),
+            "roofline": None if t["timer"] is None else gemm_roofline(
+                t["timer"], peaks, peak_kind, GFLOP_PER_IMAGE_TRAIN * 1e9 * BATCH / (ms_step * 1e-3) / 1e12,
+                "the same K steps launched eagerly (no graph, no optimizer step) right after the timed region"),
+            "hbm_kernels": None if t["timer"] is None else t["timer"].hbm_kernels(peaks),
         }
         line.update(secondary)
         if h.world == 1 and not args.no_cpu_baseline:
@@ -906,6 +907,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="train: skip the secondary cam_par / crf / reference_gpu measurements")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the unmodified reference on the GPU")
+    ap.add_argument("--no-roofline", action="store_true", help="train: skip the eager per-kernel timing pass (quick experiments)")
     ap.add_argument("--no-fuse-students", dest="fuse_students", action="store_false",
                     help="one encoder pass per student instead of both students per grouped GEMM launch")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed step with CUDA events around every op")

@@ -169,6 +169,10 @@ def pair_forward_aug(net1, net2, x_aug, scale=0.75):
     from . import train
     H, W = x_aug.shape[-2:]
     size = (int(H * scale), int(W * scale))
+    # F.interpolate(scale_factor=s) maps coordinates with 1/s, a size-based resize with H/out: identical only when H*s is an
+    # integer; the patch grid further needs multiples of 16 (448 -> 336 for the scripts' crop size)
+    if size[0] != H * scale or size[1] != W * scale or size[0] % 16 or size[1] % 16:
+        raise ValueError(f"need_sp: {H}x{W} * {scale} must be integer multiples of 16 (got {H * scale}x{W * scale})")
     if _wants_grad([net1, net2]):
         return train.student_forward(net1, x_aug, size)[1], train.student_forward(net2, x_aug, size)[1]
     with torch.no_grad():
