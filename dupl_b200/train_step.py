@@ -224,18 +224,23 @@ class TrainStep:
             from . import train
             net = model.module if hasattr(model, "module") else model
             group = None
-            if self._world() > 1:
+            world = self._world()
+            # Measured on B200 (profiles/r02_summary.md): at 2 ranks ONE all-reduce per student after the backward is fastest
+            # (52.9 ms vs 53.2-53.8 chunked: the 733 MB take 1.8 ms over NVLink and overlapping costs more SM time than it hides);
+            # at 8 ranks chunked + overlapped wins (50.6 ms vs 51.3) when NCCL is kept to 16 CTAs and the persistent GEMM grid
+            # leaves 16 SMs alone — without that reservation the collective's CTAs delay statically assigned GEMM tiles (55.8 ms).
+            overlap = os.environ.get("DUPL_GRAD_OVERLAP", "1" if world >= 4 else "0") != "0"
+            chunk = int(os.environ.get("DUPL_GRAD_CHUNK_ELEMS", str(6 << 20 if overlap else 1 << 30)))
+            if world > 1 and overlap:
                 import torch.distributed as dist
-                ctas = int(os.environ.get("DUPL_NCCL_MAX_CTAS", "4"))
+                ctas = int(os.environ.get("DUPL_NCCL_MAX_CTAS", "16"))
                 if ctas > 0 and dist.get_backend() == "nccl":
                     opts = dist.ProcessGroupNCCL.Options()
                     opts.config.max_ctas = ctas
                     opts.config.min_ctas = min(ctas, 4)
                     group = dist.new_group(backend="nccl", pg_options=opts)
-                    # SMs the persistent GEMM grid leaves alone while gradient chunks are in flight (2 per NCCL CTA: a CTA
-                    # pair of the GEMM needs both SMs of its slot)
-                    self._comm_sms = int(os.environ.get("DUPL_COMM_SMS", str(2 * ctas)))
-            chunk = int(os.environ.get("DUPL_GRAD_CHUNK_ELEMS", str(6 << 20)))
+                    # SMs the persistent GEMM grid leaves alone while gradient chunks are in flight
+                    self._comm_sms = int(os.environ.get("DUPL_COMM_SMS", "16"))
             self._arenas = [train.make_grad_arena(n, chunk_elems=chunk, group=group) for n in (net.branch1, net.branch2)]
         K = args.num_classes - 1
         self.thres_start = torch.ones(K, device=dev) * args.high_thre

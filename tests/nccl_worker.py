@@ -61,6 +61,7 @@ def main():
     mark("expected gradients done")
     # ---- arena path on this rank's own batch (chunk size small enough for several chunks even at test size)
     os.environ.setdefault("DUPL_GRAD_CHUNK_ELEMS", str(4 << 20))
+    os.environ.setdefault("DUPL_GRAD_OVERLAP", "1")     # the chunked / overlapped path with its own NCCL group (default from 4 ranks)
     m2 = model()
     opt = make_optimizer(m2, capturable=True)
     step = TrainStep(m2, opt, capture=True)
