@@ -161,6 +161,9 @@ _PROTOTYPES = {
     "dupl_sim_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dupl_sim_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "dupl_randaug_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dupl_randaug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, c_f32p, C.c_void_p,
+                               C.c_size_t, C.c_void_p]),
     "dupl_adamw_items": (C.c_int, [c_i64p, C.c_int32, c_i32p, C.c_int64, c_i64p]),
     "dupl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p]),
     "dupl_gmm_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float,

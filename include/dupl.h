@@ -401,6 +401,18 @@ int dupl_sim_loss_bwd(const float* f1, const float* f2, int32_t rows, int32_t n,
                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Strong augmentation on the device (utils/imutils.py:305-317 augment_data_strong, utils/randomaug.py:161-262).
+ * images fp32 [B,3,H,W] in [0,1] (the denormalised batch) -> out fp32 [B,3,H,W] = normalised, horizontally flipped result of
+ * n_ops Pillow operations per image.  ops_dev: DEVICE int32 [n_ops][B], operation index per step and image in the order of
+ * augment_list() (0 AutoContrast, 1 Equalize, 2 Posterize, 3 Color, 4 Contrast, 5 Brightness, 6 Sharpness), drawn by the caller
+ * (random.choices on the host, as the reference does); magnitudes7: HOST array of the 7 operations' magnitudes
+ * (m/30 * (max - min) + min).  Bit-exact with Pillow.  The caller owns the workspace.
+ * ---------------------------------------------------------------------------------------- */
+int dupl_randaug_workspace_bytes(int32_t B, int32_t H, int32_t W, size_t* bytes);
+int dupl_randaug(const float* images, float* out, int32_t B, int32_t H, int32_t W, const int32_t* ops_dev, int32_t n_ops,
+                 const float* magnitudes7, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer: fused multi-tensor PolyWarmupAdamW (utils/optimizer.py:38-68, utils/train_helper.py:21-52).
  * ---------------------------------------------------------------------------------------- */
 typedef struct dupl_adamw_param {
