@@ -48,11 +48,11 @@ def augment_data_strong(images, n=4, m=20, ops=None, out=None):
     if torch.is_tensor(ops) and ops.is_cuda:
         ops_dev = ops.to(torch.int32).contiguous()
     else:
-        host = torch.tensor(ops if ops is not None else draw_ops(B, n), dtype=torch.int32)
-        ops_dev = host.pin_memory().to(dev, non_blocking=True) if host.numel() else host.to(dev)
-    n_ops = ops_dev.shape[0] if ops_dev.dim() == 2 else 0
-    if n_ops and ops_dev.shape[1] != B:
+        host = torch.as_tensor(ops if ops is not None else draw_ops(B, n), dtype=torch.int32).reshape(-1, B)
+        ops_dev = host.pin_memory().to(dev, non_blocking=True) if host.numel() else torch.zeros(1, B, dtype=torch.int32, device=dev)[:0]
+    if ops_dev.dim() != 2 or ops_dev.shape[1] != B:
         raise ValueError("ops must be [n][batch]")
+    n_ops = ops_dev.shape[0]
     key = (B, H, W, dev)
     ws = _WS.get(key)
     if ws is None:
@@ -61,6 +61,7 @@ def augment_data_strong(images, n=4, m=20, ops=None, out=None):
         ws = _WS[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
     out = torch.empty_like(x) if out is None else out
     mags = (C.c_float * 7)(*_magnitudes(m))
-    L.check(L.lib().dupl_randaug(L.ptr(x), L.ptr(out), B, H, W, L.ptr(ops_dev), n_ops, mags, L.ptr(ws), ws.numel(),
+    ops_ptr = L.ptr(ops_dev) if n_ops else L.ptr(ws)        # never dereferenced when n_ops == 0
+    L.check(L.lib().dupl_randaug(L.ptr(x), L.ptr(out), B, H, W, ops_ptr, n_ops, mags, L.ptr(ws), ws.numel(),
                                  L.stream_ptr(dev)), "dupl_randaug")
     return out
