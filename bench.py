@@ -501,14 +501,14 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     if K == 80:
         cls = cls.to(torch.uint8)           # COCO labels are uint8 (datasets/coco.py)
     phase_c = getattr(args, "phase", "B") == "C"
-    # phase B: cam_iters <= n_iter < gmm_iters; phase C adds the augmented view (synthetic: another seeded batch), GMM, consistency
+    # phase B: cam_iters <= n_iter < gmm_iters; phase C adds the strongly augmented view (RandAugment on the device, drawn per step
+    # like the script does), the GMM noise filter and the consistency term
     it = [train_n_iter(K, phase_c)]
     from helpers import synth_images
-    x_aug = synth_images(BATCH, SIZE, SIZE, seed=100 + h.rank) if phase_c else None
+    x_aug = None          # phase C: TrainStep augments `inputs` itself (utils.imutils.augment_data_strong on the GPU)
     x_pin, cls_pin = x.pin_memory(), cls.pin_memory()
     x_dev, cls_dev = x.to(h.dev), cls.to(h.dev)
-    aug_pin = x_aug.pin_memory() if phase_c else None
-    aug_dev = x_aug.to(h.dev) if phase_c else None
+    aug_pin = aug_dev = None
     last = {}
 
     def device_step():
@@ -518,7 +518,7 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     def e2e_step():
         xi = x_pin.to(h.dev, non_blocking=True)
         ci = cls_pin.to(h.dev, non_blocking=True)
-        ai = aug_pin.to(h.dev, non_blocking=True) if phase_c else None
+        ai = None
         loss, _ = step(xi, ci, box, it[0], ai)
         it[0] += 1
         last["loss_host"] = loss.item()   # device -> host read of the step's result
@@ -529,7 +529,7 @@ def measure_train(h, args, K, steps, warmup, want_roofline):
     if h.rank == 0:
         sampler.start()
     ms = h.time_device(device_step, steps)
-    out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 * (2 if phase_c else 1) + cls_pin.numel() * cls_pin.element_size()), d2h=4, P=P,
+    out = dict(ms=ms / steps, h2d=int(x_pin.numel() * 4 + cls_pin.numel() * cls_pin.element_size()), d2h=4, P=P,
                inputs=(x, cls, box), n_iter=it[0])
     e2e_step()
     out["e2e_ms"] = h.time_wall(e2e_step, steps) / steps

@@ -192,6 +192,7 @@ class TrainStep:
         self.args = args
         self.capture = capture
         self._graphs = {}
+        self._aug_ops = None        # captured phase C: device tensor [5][b] of RandAugment operation indices, refilled per step
         self._last_graph_key = None
         self._sched = None          # static device scalars of the threshold schedule while capturing / replaying
         dev = device or next(model.parameters()).device
@@ -306,7 +307,10 @@ class TrainStep:
             labels = (label_1, label_2)
             phase_c = n_iter >= a.gmm_iters
             if phase_c and inputs_aug is None:
-                raise ValueError("n_iter >= gmm_iters needs inputs_aug (the strongly augmented view)")
+                # train_final_voc.py:186-191: inputs_aug = augment_data_strong(denormalize_img2(inputs), n=5, m=10) — Pillow on
+                # the host in the reference, seven bit-exact kernels on the device here (utils/imutils.py of this package)
+                from .utils import imutils
+                inputs_aug = imutils.augment_data_strong(denormalize_img2(inputs.clone()), n=5, m=10, ops=self._aug_ops)
             res = self._forward(inputs, inputs_aug if phase_c else None)
         cls_1, segs_1, fmap_1, cls_aux_1 = res["branch1"]
         cls_2, segs_2, fmap_2, cls_aux_2 = res["branch2"]
@@ -422,6 +426,15 @@ class TrainStep:
                       aug=None if inputs_aug is None else torch.empty_like(inputs_aug),
                       omc=torch.zeros((), dtype=torch.float32, device=dev), done=torch.zeros((), dtype=torch.bool, device=dev))
             self._graphs[key] = st
+        phase_c_own_aug = n_iter >= self.args.gmm_iters and inputs_aug is None
+        if phase_c_own_aug:
+            from .utils import imutils
+            if st.get("aug_ops") is None:
+                st["aug_ops"] = torch.zeros(5, inputs.shape[0], dtype=torch.int32, device=dev)
+                st["aug_ops_host"] = torch.zeros(5, inputs.shape[0], dtype=torch.int32).pin_memory()
+            st["aug_ops_host"].copy_(torch.tensor(imutils.draw_ops(inputs.shape[0], 5), dtype=torch.int32))
+            st["aug_ops"].copy_(st["aug_ops_host"], non_blocking=True)
+        self._aug_ops = st.get("aug_ops") if phase_c_own_aug else None
         st["x"].copy_(inputs, non_blocking=True)
         st["cls"].copy_(cls_label, non_blocking=True)
         st["box"].copy_(torch.as_tensor(img_box).to(torch.int32), non_blocking=True)
@@ -504,6 +517,7 @@ class TrainStep:
                     b._dec_planes.invalidate()
         finally:
             self._sched = None
+            self._aug_ops = None
         return st["loss"], st["parts"]
 
 

@@ -268,3 +268,31 @@ def test_alternating_phases_with_graph_replay_use_their_own_kept_activations():
         assert torch.equal(outs[0][0], outs[1][0]), (n_iter, outs[0][0].item(), outs[1][0].item())
         for n in outs[1][1]:
             assert torch.equal(outs[0][1][n], outs[1][1][n]), (n_iter, n)
+
+
+def test_phase_c_augments_on_the_device_and_runs_captured():
+    """n_iter >= gmm_iters without an explicit augmented view: TrainStep draws the RandAugment operations like the script
+    (train_final_voc.py:190-191) and augments on the GPU; same losses as handing the same view over explicitly; the captured
+    iteration refills the operation indices per step."""
+    import random
+    from dupl_b200.pipeline import denormalize_img2
+    from dupl_b200.train_step import TrainStep, make_optimizer
+    from dupl_b200.utils import imutils
+    from helpers import synth_boxes, synth_cls_labels
+    b, S = 2, 64
+    x = synth_images(b, S, S, seed=91).cuda()
+    cls = synth_cls_labels(b, 20, seed=92).cuda()
+    box = synth_boxes(b, S, S, seed=93)
+    m, _ = _models()
+    step = TrainStep(m, None)
+    random.seed(3)
+    own, _, _ = step.losses(x, cls, box, 9000)
+    random.seed(3)
+    aug = imutils.augment_data_strong(denormalize_img2(x.clone()), n=5, m=10)
+    explicit, _, _ = step.losses(x, cls, box, 9000, inputs_aug=aug)
+    assert torch.equal(own.detach(), explicit.detach())
+    assert not torch.equal(aug, x)
+    m2, _ = _models()
+    cap = TrainStep(m2, make_optimizer(m2, capturable=True), capture=True)
+    ls = [cap(x, cls, box, 9000 + i)[0].item() for i in range(3)]
+    assert all(torch.isfinite(torch.tensor(ls))) and len(set(ls)) > 1      # different operations / updated weights per step
