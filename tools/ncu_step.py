@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""One replay of the captured training step (BASELINE metric: VOC phase B, b = 4, 448x448) inside a cudaProfilerStart/Stop
+range, for `ncu --profile-from-start off` (launch list and --set full captures: tools/gpu_r2_ncu.sh) and, with --table, a
+torch.profiler kernel table of the same replay (no ncu needed)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+from helpers import init_state_dict, synth_boxes, synth_cls_labels, synth_images  # noqa: E402
+from dupl_b200.model.model_dupl import siamese_network  # noqa: E402
+from dupl_b200.train_step import Args, TrainStep, make_optimizer  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--phase", default="B", choices=["B", "C"])
+ap.add_argument("--table", action="store_true")
+a = ap.parse_args()
+m = siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
+m.load_state_dict(init_state_dict(21), strict=True)
+m = m.cuda().train()
+step = TrainStep(m, make_optimizer(m, capturable=True), args=Args, capture=True)
+x = synth_images(4, 448, 448, seed=0).cuda()
+cls, box = synth_cls_labels(4, 20, seed=0).cuda(), synth_boxes(4, 448, 448, seed=0)
+n0 = 9000 if a.phase == "C" else 5000
+for i in range(3):
+    step(x, cls, box, n0 + i)
+torch.cuda.synchronize()
+if a.table:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step(x, cls, box, n0 + 5)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=72))
+else:
+    torch.cuda.profiler.start()
+    step(x, cls, box, n0 + 5)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
