@@ -134,6 +134,7 @@ _PROTOTYPES = {
     "dupl_refine_prologue": (C.c_int, [C.POINTER(RefinePrologueArgs), C.c_void_p]),
     "dupl_refine_epilogue": (C.c_int, [C.POINTER(RefineEpilogueArgs), C.c_void_p]),
     "dupl_split_transpose": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3),
+    "dupl_split_transpose_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3),
     "dupl_transpose_planes": (C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 6 + [C.c_void_p] * 2 + [C.c_int32, C.c_void_p]),
     "dupl_colsum": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
     "dupl_layernorm_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_void_p]),

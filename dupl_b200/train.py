@@ -28,8 +28,9 @@ def _st(dev):
     return L.stream_ptr(dev)
 
 
-def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0, want_colsum=False):
-    """fp32 rows -> (hi, lo) planes, transposed planes [Cc, pad64(R)] and (optionally, same pass) the column sums."""
+def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0, want_colsum=False, gelu_pre=None):
+    """fp32 rows -> (hi, lo) planes, transposed planes [Cc, pad64(R)] and (optionally, same pass) the column sums.
+    gelu_pre: src is the gradient w.r.t. GELU's output; it is multiplied by GELU'(gelu_pre) on the way (no separate pass)."""
     dev = src.device
     bf = dict(dtype=torch.bfloat16, device=dev)
     Rpad = _pad64(R)
@@ -41,8 +42,14 @@ def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, 
     if want_colsum:
         ws = torch.empty(((Rpad if want_t else R) + 63) // 64 * Cc, dtype=torch.float32, device=dev)
         cs = torch.empty(Cc, dtype=torch.float32, device=dev)
-    L.check(L.lib().dupl_split_transpose(L.ptr(src), R, Cc, src.shape[1], tokens, np_, first, L.ptr(hi), L.ptr(lo),
-                                         L.ptr(thi), L.ptr(tlo), Rpad, L.ptr(ws), L.ptr(cs), _st(dev)), "dupl_split_transpose")
+    if gelu_pre is not None:
+        if tokens or src.shape[1] != Cc or tuple(gelu_pre.shape) != (R, Cc):
+            raise ValueError("split_transpose(gelu_pre=...) takes dense [R, Cc] operands")
+        L.check(L.lib().dupl_split_transpose_gelu(L.ptr(src), L.ptr(gelu_pre), R, Cc, L.ptr(hi), L.ptr(lo), L.ptr(thi), L.ptr(tlo), Rpad,
+                                                  L.ptr(ws), L.ptr(cs), _st(dev)), "dupl_split_transpose_gelu")
+    else:
+        L.check(L.lib().dupl_split_transpose(L.ptr(src), R, Cc, src.shape[1], tokens, np_, first, L.ptr(hi), L.ptr(lo),
+                                             L.ptr(thi), L.ptr(tlo), Rpad, L.ptr(ws), L.ptr(cs), _st(dev)), "dupl_split_transpose")
     if want_colsum:
         return (hi, lo), (thi, tlo), cs
     return (hi, lo), (thi, tlo)
@@ -384,8 +391,8 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
             grads[g].put(ep + "mlp.fc2.weight", dw[g])
         d_hid = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "mlp.fc2.weight")) for g in R], M, 4 * D, D)
         for g in R:
-            L.check(L.lib().dupl_gelu_bwd(L.ptr(d_hid[g]), L.ptr(bl[g].h_pre), d_hid[g].numel(), _st(dev)), "dupl_gelu_bwd")
-            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True)
+            # GELU'(fc1 pre-activation) is applied inside the split / transpose pass (dupl_split_transpose_gelu)
+            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True, gelu_pre=bl[g].h_pre)
             grads[g].put(ep + "mlp.fc1.bias", cs)
         dw = wgrad_multi([(dt[g], transpose_planes(bl[g].xn2, M, D)) for g in R], 4 * D, D, Mpad,
                          outs=[grads[g].out(ep + "mlp.fc1.weight") for g in R])

@@ -295,6 +295,11 @@ int dupl_refine_epilogue(const dupl_refine_epilogue_args* args, void* stream);
 int dupl_split_transpose(const float* src, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first,
                          void* hi, void* lo, void* t_hi, void* t_lo, int32_t Rpad, float* colsum_ws, float* colsum,
                          void* stream);
+/* Same for the gradient w.r.t. GELU's output (autograd of vit.py:97-103): every element of src [R, Cc] is multiplied by
+ * GELU'(gelu_pre) (the saved fc1 pre-activation, [R, Cc] fp32) on the way — the hidden gradient never makes a separate
+ * element-wise round trip through HBM. */
+int dupl_split_transpose_gelu(const float* src, const float* gelu_pre, int32_t R, int32_t Cc, void* hi, void* lo, void* t_hi, void* t_lo,
+                              int32_t Rpad, float* colsum_ws, float* colsum, void* stream);
 /* (with colsum != NULL the same pass also produces colsum[c] = sum_r src[row(r)][c], the bias gradient of the
  * layer; colsum_ws: scratch of ceil(rows/64)*Cc floats, rows = Rpad when t_hi is given, else R.) */
 /* one or two bf16 planes [R (mapped), Cc] (row stride ld) -> their transposes [Cc, Rpad], zero padded;
