@@ -93,6 +93,14 @@ class CrfArgs(C.Structure):
                 ("values", C.c_void_p), ("values_bytes", C.c_size_t), ("meta", C.c_void_p)]
 
 
+MAX_TRANSPOSE_ITEMS = 16
+
+
+class TransposeItem(C.Structure):
+    _fields_ = [("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+                ("R", C.c_int32), ("Cc", C.c_int32), ("ld", C.c_int32), ("Rpad", C.c_int32)]
+
+
 class AdamwParam(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("plane_hi", C.c_void_p), ("plane_lo", C.c_void_p), ("numel", C.c_int64), ("lr", C.c_float), ("reserved", C.c_int32)]
@@ -136,6 +144,7 @@ _PROTOTYPES = {
     "dupl_split_transpose": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3),
     "dupl_split_transpose_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3),
     "dupl_transpose_planes": (C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 6 + [C.c_void_p] * 2 + [C.c_int32, C.c_void_p]),
+    "dupl_transpose_planes_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "dupl_colsum": (C.c_int, [C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]),
     "dupl_layernorm_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "dupl_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -123,6 +123,41 @@ __global__ void __launch_bounds__(256) transpose_u16_kernel(const unsigned short
   }
 }
 
+// Several dense plane pairs transposed by ONE launch (blockIdx.z = 2 * item + plane): the per-layer activations and weights the
+// wgrad / dgrad GEMMs of one encoder block consume.  ~200 single launches per step cost more in launch gaps inside the
+// captured graph than in copy time.
+struct TransposeItems {
+  const unsigned short* in[2 * DUPL_MAX_TRANSPOSE_ITEMS];
+  unsigned short* out[2 * DUPL_MAX_TRANSPOSE_ITEMS];
+  int R[DUPL_MAX_TRANSPOSE_ITEMS], Cc[DUPL_MAX_TRANSPOSE_ITEMS], ld[DUPL_MAX_TRANSPOSE_ITEMS], Rpad[DUPL_MAX_TRANSPOSE_ITEMS];
+};
+
+__global__ void __launch_bounds__(256) transpose_multi_kernel(const TransposeItems it) {
+  __shared__ unsigned short tile_t[64][66];  // [column][row]
+  const int item = blockIdx.z >> 1;
+  const int R = it.R[item], Cc = it.Cc[item], ld = it.ld[item], Rpad = it.Rpad[item];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  if (r0 >= Rpad || c0 >= Cc) return;
+  const unsigned short* __restrict__ in = it.in[blockIdx.z];
+  unsigned short* __restrict__ out = it.out[blockIdx.z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = warp * 8 + i, r = r0 + rr, c = c0 + 2 * lane;
+    uint32_t v = 0;
+    if (r < R && c < Cc) v = *reinterpret_cast<const uint32_t*>(in + static_cast<long>(r) * ld + c);
+    tile_t[2 * lane][rr] = static_cast<unsigned short>(v & 0xffffu);
+    tile_t[2 * lane + 1][rr] = static_cast<unsigned short>(v >> 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int cc = warp * 8 + i, c = c0 + cc, r = r0 + 2 * lane;
+    if (c < Cc && r < Rpad)
+      *reinterpret_cast<uint32_t*>(out + static_cast<long>(c) * Rpad + r) = *reinterpret_cast<const uint32_t*>(&tile_t[cc][2 * lane]);
+  }
+}
+
 // out[c] = sum_r x[map(r)][c].  Block = 32 columns x 8 row lanes; fixed summation order.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int Cc, int ld, RowMap map,
                                                      float* __restrict__ out) {
@@ -405,6 +440,30 @@ extern "C" int dupl_transpose_planes(const void* in_hi, const void* in_lo, int32
   transpose_u16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const unsigned short*>(in_hi), static_cast<const unsigned short*>(in_lo), R, Cc, ld, make_map(tokens, np, first),
       static_cast<unsigned short*>(out_hi), static_cast<unsigned short*>(out_lo), Rpad);
+  DUPL_LAUNCH_OK();
+  return DUPL_OK;
+}
+
+extern "C" int dupl_transpose_planes_multi(const dupl_transpose_item* items, int32_t n_items, void* stream) {
+  DUPL_CHECK_ARG(items != nullptr && n_items >= 1 && n_items <= DUPL_MAX_TRANSPOSE_ITEMS, "dupl_transpose_planes_multi: 1..%d items",
+                 DUPL_MAX_TRANSPOSE_ITEMS);
+  TransposeItems T;
+  int max_r = 0, max_c = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const dupl_transpose_item& e = items[i];
+    DUPL_CHECK_ARG(e.in_hi && e.in_lo && e.out_hi && e.out_lo && e.R > 0 && e.Cc > 0 && e.ld >= e.Cc && e.Rpad >= e.R,
+                   "dupl_transpose_planes_multi: bad item %d", i);
+    DUPL_CHECK_ARG(e.Cc % 2 == 0 && e.ld % 2 == 0 && e.Rpad % 2 == 0, "dupl_transpose_planes_multi: item %d: Cc, ld, Rpad must be even", i);
+    T.in[2 * i] = static_cast<const unsigned short*>(e.in_hi);
+    T.in[2 * i + 1] = static_cast<const unsigned short*>(e.in_lo);
+    T.out[2 * i] = static_cast<unsigned short*>(e.out_hi);
+    T.out[2 * i + 1] = static_cast<unsigned short*>(e.out_lo);
+    T.R[i] = e.R; T.Cc[i] = e.Cc; T.ld[i] = e.ld; T.Rpad[i] = e.Rpad;
+    max_r = e.Rpad > max_r ? e.Rpad : max_r;
+    max_c = e.Cc > max_c ? e.Cc : max_c;
+  }
+  dim3 grid(cdiv(max_r, 64), cdiv(max_c, 64), 2 * n_items);
+  transpose_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(T);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -28,7 +28,8 @@ def _st(dev):
     return L.stream_ptr(dev)
 
 
-def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0, want_colsum=False, gelu_pre=None):
+def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, first=0, want_colsum=False, gelu_pre=None,
+                    colsum_out=None):
     """fp32 rows -> (hi, lo) planes, transposed planes [Cc, pad64(R)] and (optionally, same pass) the column sums.
     gelu_pre: src is the gradient w.r.t. GELU's output; it is multiplied by GELU'(gelu_pre) on the way (no separate pass)."""
     dev = src.device
@@ -41,7 +42,7 @@ def split_transpose(src, R, Cc, want_planes=True, want_t=True, tokens=0, np_=0, 
         thi, tlo = torch.empty(Cc, Rpad, **bf), torch.empty(Cc, Rpad, **bf)
     if want_colsum:
         ws = torch.empty(((Rpad if want_t else R) + 63) // 64 * Cc, dtype=torch.float32, device=dev)
-        cs = torch.empty(Cc, dtype=torch.float32, device=dev)
+        cs = torch.empty(Cc, dtype=torch.float32, device=dev) if colsum_out is None else colsum_out.view(Cc)
     if gelu_pre is not None:
         if tokens or src.shape[1] != Cc or tuple(gelu_pre.shape) != (R, Cc):
             raise ValueError("split_transpose(gelu_pre=...) takes dense [R, Cc] operands")
@@ -60,17 +61,33 @@ def transpose_planes(planes, R, Cc, tokens=0, np_=0, first=0):
     return E.transpose_planes(planes, R, Cc, tokens, np_, first)
 
 
+def transpose_planes_multi(items):
+    """items: [(planes (hi, lo) dense [R, Cc] bf16, R, Cc)] -> [(hi^T, lo^T) [Cc, pad64(R)]], ONE launch for up to 16 pairs."""
+    outs, tab, dev = [], (L.TransposeItem * len(items))(), items[0][0][0].device
+    for i, ((hi, lo), R, Cc) in enumerate(items):
+        Rpad = _pad64(R)
+        ohi = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=dev)
+        olo = torch.empty(Cc, Rpad, dtype=torch.bfloat16, device=dev)
+        e = tab[i]
+        e.in_hi, e.in_lo, e.out_hi, e.out_lo = hi.data_ptr(), lo.data_ptr(), ohi.data_ptr(), olo.data_ptr()
+        e.R, e.Cc, e.ld, e.Rpad = R, Cc, hi.shape[1], Rpad
+        outs.append((ohi, olo))
+    L.check(L.lib().dupl_transpose_planes_multi(tab, len(items), _st(dev)), "dupl_transpose_planes_multi")
+    return outs
+
+
 def colsum(x, R, Cc, tokens=0, np_=0, first=0):
     out = torch.empty(Cc, dtype=torch.float32, device=x.device)
     L.check(L.lib().dupl_colsum(L.ptr(x), R, Cc, x.shape[1], tokens, np_, first, L.ptr(out), _st(x.device)), "dupl_colsum")
     return out
 
 
-def layernorm_bwd(dy, x, gamma, dres):
+def layernorm_bwd(dy, x, gamma, dres, dg_out=None, db_out=None):
     rows, cols = x.shape
     dev = x.device
     partial = torch.empty(2 * cols * ((rows + 15) // 16), dtype=torch.float32, device=dev)
-    dg, db = torch.empty(cols, dtype=torch.float32, device=dev), torch.empty(cols, dtype=torch.float32, device=dev)
+    dg = torch.empty(cols, dtype=torch.float32, device=dev) if dg_out is None else dg_out.view(cols)
+    db = torch.empty(cols, dtype=torch.float32, device=dev) if db_out is None else db_out.view(cols)
     L.check(L.lib().dupl_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(dres), L.ptr(partial), L.ptr(dg), L.ptr(db),
                                        rows, cols, E.LN_EPS, _st(dev)), "dupl_layernorm_bwd")
     return dg, db
@@ -364,7 +381,8 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
     # final LayerNorm
     d_tok = [torch.zeros(M, D, **f32) for _ in R]
     for g in R:
-        dg, db = layernorm_bwd(d_xn[g], Ss[g].tok_final, pls[g].vec("norm.weight"), d_tok[g])
+        dg, db = layernorm_bwd(d_xn[g], Ss[g].tok_final, pls[g].vec("norm.weight"), d_tok[g],
+                               grads[g].out("encoder.norm.weight"), grads[g].out("encoder.norm.bias"))
         grads[g].put("encoder.norm.weight", dg)
         grads[g].put("encoder.norm.bias", db)
 
@@ -380,50 +398,65 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
                 # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
                 grads[g].put("aux_classifier.weight",
                              None if g_aux[g] is None else _gmp_bwd(S.aux_src, S.wa, g_aux[g], S.arg_a, d_tok[g], S).reshape(K, D, 1, 1))
+        # every transposed operand of this block's wgrad (activations) and dgrad (weights) GEMMs, all students: ONE launch
+        w_names = ("mlp.fc2", "mlp.fc1", "attn.proj", "attn.qkv")
+        items = []
+        for g in R:
+            items += [(bl[g].hid, M, 4 * D), (bl[g].xn2, M, D), (bl[g].att, M, D), (bl[g].xn1, M, D)]
+        for g in R:
+            for wn in w_names:
+                wp = pls[g].plane(bp + wn + ".weight")
+                items.append((wp, wp[0].shape[0], wp[0].shape[1]))
+        tr = transpose_planes_multi(items)
+        act_t = [dict(zip(("hid", "xn2", "att", "xn1"), tr[4 * g:4 * g + 4])) for g in R]
+        w_t = [dict(zip(w_names, tr[4 * G + 4 * g:4 * G + 4 * g + 4])) for g in R]
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
         dpl, dt = [None] * G, [None] * G
         for g in R:
-            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True)
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True, colsum_out=grads[g].out(ep + "mlp.fc2.bias"))
             grads[g].put(ep + "mlp.fc2.bias", cs)
-        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].hid, M, 4 * D)) for g in R], D, 4 * D, Mpad,
+        dw = wgrad_multi([(dt[g], act_t[g]["hid"]) for g in R], D, 4 * D, Mpad,
                          outs=[grads[g].out(ep + "mlp.fc2.weight") for g in R])
         for g in R:
             grads[g].put(ep + "mlp.fc2.weight", dw[g])
-        d_hid = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "mlp.fc2.weight")) for g in R], M, 4 * D, D)
+        d_hid = dgrad_multi([(dpl[g], w_t[g]["mlp.fc2"]) for g in R], M, 4 * D, D)
         for g in R:
             # GELU'(fc1 pre-activation) is applied inside the split / transpose pass (dupl_split_transpose_gelu)
-            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True, gelu_pre=bl[g].h_pre)
+            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True, gelu_pre=bl[g].h_pre,
+                                                colsum_out=grads[g].out(ep + "mlp.fc1.bias"))
             grads[g].put(ep + "mlp.fc1.bias", cs)
-        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].xn2, M, D)) for g in R], 4 * D, D, Mpad,
+        dw = wgrad_multi([(dt[g], act_t[g]["xn2"]) for g in R], 4 * D, D, Mpad,
                          outs=[grads[g].out(ep + "mlp.fc1.weight") for g in R])
         for g in R:
             grads[g].put(ep + "mlp.fc1.weight", dw[g])
-        d_xn2 = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "mlp.fc1.weight")) for g in R], M, D, 4 * D)
+        d_xn2 = dgrad_multi([(dpl[g], w_t[g]["mlp.fc1"]) for g in R], M, D, 4 * D)
         for g in R:
-            dg, db = layernorm_bwd(d_xn2[g], bl[g].x_mid, pls[g].vec(bp + "norm2.weight"), d_tok[g])
+            dg, db = layernorm_bwd(d_xn2[g], bl[g].x_mid, pls[g].vec(bp + "norm2.weight"), d_tok[g],
+                                   grads[g].out(ep + "norm2.weight"), grads[g].out(ep + "norm2.bias"))
             grads[g].put(ep + "norm2.weight", dg)
             grads[g].put(ep + "norm2.bias", db)
         # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
         for g in R:
-            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True)
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True, colsum_out=grads[g].out(ep + "attn.proj.bias"))
             grads[g].put(ep + "attn.proj.bias", cs)
-        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].att, M, D)) for g in R], D, D, Mpad,
+        dw = wgrad_multi([(dt[g], act_t[g]["att"]) for g in R], D, D, Mpad,
                          outs=[grads[g].out(ep + "attn.proj.weight") for g in R])
         for g in R:
             grads[g].put(ep + "attn.proj.weight", dw[g])
         d_att = [(torch.empty(M, D, **bfk), torch.empty(M, D, **bfk)) for _ in R]   # dO as split planes: operand of the attention backward
-        ops.gemm_bf16x3([dict(a=dpl[g], w=pls[g].plane_t(bp + "attn.proj.weight"), out=d_att[g]) for g in R], M, D, D, L.EPI_SPLIT)
+        ops.gemm_bf16x3([dict(a=dpl[g], w=w_t[g]["attn.proj"], out=d_att[g]) for g in R], M, D, D, L.EPI_SPLIT)
         for g in R:
             d_qkv = ops.attention_bwd(bl[g].qkv, bl[g].att, d_att[g], bl[g].lse, B, N, E.HEADS, scale)
-            dpl[g], dt[g], cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True)
+            dpl[g], dt[g], cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True, colsum_out=grads[g].out(ep + "attn.qkv.bias"))
             grads[g].put(ep + "attn.qkv.bias", cs)
-        dw = wgrad_multi([(dt[g], transpose_planes(bl[g].xn1, M, D)) for g in R], 3 * D, D, Mpad,
+        dw = wgrad_multi([(dt[g], act_t[g]["xn1"]) for g in R], 3 * D, D, Mpad,
                          outs=[grads[g].out(ep + "attn.qkv.weight") for g in R])
         for g in R:
             grads[g].put(ep + "attn.qkv.weight", dw[g])
-        d_xn1 = dgrad_multi([(dpl[g], pls[g].plane_t(bp + "attn.qkv.weight")) for g in R], M, D, 3 * D)
+        d_xn1 = dgrad_multi([(dpl[g], w_t[g]["attn.qkv"]) for g in R], M, D, 3 * D)
         for g in R:
-            dg, db = layernorm_bwd(d_xn1[g], bl[g].x_in, pls[g].vec(bp + "norm1.weight"), d_tok[g])
+            dg, db = layernorm_bwd(d_xn1[g], bl[g].x_in, pls[g].vec(bp + "norm1.weight"), d_tok[g],
+                                   grads[g].out(ep + "norm1.weight"), grads[g].out(ep + "norm1.bias"))
             grads[g].put(ep + "norm1.weight", dg)
             grads[g].put(ep + "norm1.bias", db)
 

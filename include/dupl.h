@@ -306,6 +306,15 @@ int dupl_split_transpose_gelu(const float* src, const float* gelu_pre, int32_t R
  * in_lo/out_lo may be NULL.  Cc, ld, Rpad even. */
 int dupl_transpose_planes(const void* in_hi, const void* in_lo, int32_t R, int32_t Cc, int32_t ld, int32_t tokens,
                           int32_t np, int32_t first, void* out_hi, void* out_lo, int32_t Rpad, void* stream);
+/* The same for up to DUPL_MAX_TRANSPOSE_ITEMS dense plane pairs in ONE launch (all activations / weights one encoder block's
+ * wgrad and dgrad GEMMs consume, both students): in [R, ld >= Cc] -> out [Cc, Rpad] zero padded. */
+#define DUPL_MAX_TRANSPOSE_ITEMS 16
+typedef struct dupl_transpose_item {
+  const void* in_hi; const void* in_lo;
+  void* out_hi; void* out_lo;
+  int32_t R, Cc, ld, Rpad;
+} dupl_transpose_item;
+int dupl_transpose_planes_multi(const dupl_transpose_item* items, int32_t n_items, void* stream);
 /* out[c] = sum_r x[row(r)][c]  (bias gradients) */
 int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first, float* out,
                 void* stream);

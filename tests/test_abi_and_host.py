@@ -35,7 +35,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
              "dupl_attention_args": _lib.AttentionArgs, "dupl_mscam_args": _lib.MscamArgs,
              "dupl_cam_to_label_args": _lib.CamToLabelArgs, "dupl_refine_prologue_args": _lib.RefinePrologueArgs,
              "dupl_refine_epilogue_args": _lib.RefineEpilogueArgs, "dupl_attention_bwd_args": _lib.AttentionBwdArgs,
-             "dupl_crf_args": _lib.CrfArgs, "dupl_adamw_param": _lib.AdamwParam, "dupl_adamw_args": _lib.AdamwArgs}
+             "dupl_crf_args": _lib.CrfArgs, "dupl_adamw_param": _lib.AdamwParam, "dupl_adamw_args": _lib.AdamwArgs,
+             "dupl_transpose_item": _lib.TransposeItem}
     prog = '#include <stdio.h>\n#include "dupl.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     c = tmp_path / "sz.c"
