@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("groups", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("lda", C.c_int32), ("ldo", C.c_int32), ("epilogue", C.c_int32), ("nseg", C.c_int32),
                 ("ldw", C.c_int32), ("max_ksplit", C.c_int32), ("f32_rows", C.c_int32), ("passes", C.c_int32),
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
                 ("seg", Segment * MAX_SEGMENTS), ("g", GemmGroup * MAX_GROUPS)]
 
 

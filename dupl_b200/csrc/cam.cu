@@ -287,6 +287,218 @@ static int launch_mscam_columns(const MscamParams& p, cudaStream_t st) {
   return DUPL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-launch variant: a CLUSTER of MSCAM_CL CTAs owns one (image, class) plane, CTA `rank` its rows
+// [rank*rpc, (rank+1)*rpc).  Each CTA computes its un-normalised values ONCE into shared memory (a thread owns one
+// output column, as in mscam_kernel), the plane's min / max go through distributed shared memory (two cluster
+// barriers, no atomics, no second launch that recomputes every value), then the tile is normalised out of shared
+// memory and streamed to HBM.  Same arithmetic in the same order as mscam_kernel: bit-identical output.
+// ---------------------------------------------------------------------------------------------
+constexpr int MSCAM_CL = 8;
+
+__device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t mscam_mapa(const void* p, uint32_t rank) {
+  uint32_t r;
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mscam_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NS>
+__global__ void __launch_bounds__(512) mscam_cluster_kernel(MscamParams p, int rpc) {
+  extern __shared__ float sm[];
+  __shared__ int g_rlo[NS], g_nr[NS], g_off[NS + 1];
+  __shared__ float red_mn[16], red_mx[16];
+  __shared__ float cta_mm[2];  // this CTA's min / max, read by its 7 peers
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int plane = blockIdx.x / MSCAM_CL;  // img*K + k
+  const int img = plane / p.K, k = plane % p.K;
+  const int y_begin = min(static_cast<int>(rank) * rpc, p.H);
+  const int y_end = min(y_begin + rpc, p.H);
+  const int nrows = y_end - y_begin;  // 0 for the trailing CTAs of a short plane: they only take part in the barriers
+  const int nt = blockDim.x;
+
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int s = 0; s < NS; ++s) {
+      const int gh = p.gh[s], gw = p.gw[s];
+      int rlo = 0, rhi = -1;
+      if (nrows > 0) {
+        rlo = lin_coord(y_begin, gh, static_cast<float>(gh) / p.H).i0;
+        rhi = lin_coord(y_end - 1, gh, static_cast<float>(gh) / p.H).i1;
+      }
+      g_rlo[s] = rlo; g_nr[s] = rhi - rlo + 1;
+      g_off[s] = off;
+      off += 2 * g_nr[s] * gw;
+    }
+    g_off[NS] = off;
+  }
+  __syncthreads();
+  // full-width window of the low-res rows this CTA samples: image (A) and twin (B, stored pre-flipped along x)
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int gw = p.gw[s], n = p.gh[s] * gw;
+    const int nr = g_nr[s], rlo = g_rlo[s];
+    const float* a = p.lowres[s] + (static_cast<long>(img) * p.K + k) * n;
+    const float* bt = p.lowres[s] + (static_cast<long>(img + p.b) * p.K + k) * n;
+    float* A = sm + g_off[s];
+    float* B = A + nr * gw;
+    for (int i = threadIdx.x; i < nr * gw; i += nt) {
+      const int r = i / gw, c = i - r * gw;
+      A[i] = __ldg(a + (rlo + r) * gw + c);
+      B[i] = __ldg(bt + (rlo + r) * gw + (gw - 1 - c));
+    }
+  }
+  MscamRow* rows = reinterpret_cast<MscamRow*>(sm + ((g_off[NS] + 3) & ~3));
+  float2* wts = reinterpret_cast<float2*>(rows + rpc * NS);
+  int* flags = reinterpret_cast<int*>(wts + rpc * NS);
+  float* vals = reinterpret_cast<float*>(flags + ((rpc + 3) & ~3));  // [rpc][nt]
+  for (int i = threadIdx.x; i < nrows * NS; i += nt) {
+    const int r = i / NS, s = i - r * NS;
+    const Lin ly = lin_coord(y_begin + r, p.gh[s], static_cast<float>(p.gh[s]) / p.H);
+    rows[i] = MscamRow{ly.i0 - g_rlo[s], ly.i1 - g_rlo[s], ly.l0, ly.l1};
+    wts[i] = make_float2(ly.l0, ly.l1);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < nrows; r += nt) {
+    int f = 0;
+    for (int s = 0; s < NS; ++s)
+      if (r == 0 || rows[r * NS + s].i0 != rows[(r - 1) * NS + s].i0 || rows[r * NS + s].i1 != rows[(r - 1) * NS + s].i1) f |= 1 << s;
+    flags[r] = f;
+  }
+  __syncthreads();
+
+  const int x = threadIdx.x;
+  const bool active = x < p.W;
+  const int xc = min(x, p.W - 1);
+  int c0[NS], c1[NS], nc[NS];
+  float lx0[NS], lx1[NS], t0a[NS], t1a[NS], t0b[NS], t1b[NS];
+  const float* Ab[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const Lin lx = lin_coord(xc, p.gw[s], static_cast<float>(p.gw[s]) / p.W);
+    c0[s] = lx.i0; c1[s] = lx.i1; lx0[s] = lx.l0; lx1[s] = lx.l1;
+    nc[s] = p.gw[s];
+    Ab[s] = sm + g_off[s];
+    t0a[s] = t1a[s] = t0b[s] = t1b[s] = 0.0f;
+  }
+  float mn = INFINITY, mx = 0.0f;
+  float* vcol = vals + threadIdx.x;
+#pragma unroll 4
+  for (int r = 0; r < nrows; ++r) {
+    const int changed = flags[r];      // bit s: the source rows of scale s differ from the previous output row's
+    if (changed != 0) {                // block-uniform and rare: every H/gh output rows
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if ((changed >> s) & 1) {
+          const MscamRow rw = rows[r * NS + s];
+          const float* A0 = Ab[s] + rw.i0 * nc[s];
+          const float* A1 = Ab[s] + rw.i1 * nc[s];
+          const float* B0 = A0 + g_nr[s] * nc[s];
+          const float* B1 = A1 + g_nr[s] * nc[s];
+          t0a[s] = __fmaf_rn(lx0[s], A0[c0[s]], __fmul_rn(lx1[s], A0[c1[s]]));
+          t1a[s] = __fmaf_rn(lx0[s], A1[c0[s]], __fmul_rn(lx1[s], A1[c1[s]]));
+          t0b[s] = __fmaf_rn(lx0[s], B0[c0[s]], __fmul_rn(lx1[s], B0[c1[s]]));
+          t1b[s] = __fmaf_rn(lx0[s], B1[c0[s]], __fmul_rn(lx1[s], B1[c1[s]]));
+        }
+      }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float2 l = wts[r * NS + s];
+      const float va = __fmaf_rn(l.x, t0a[s], __fmul_rn(l.y, t1a[s]));
+      const float vb = __fmaf_rn(l.x, t0b[s], __fmul_rn(l.y, t1b[s]));
+      acc += fmaxf(fmaxf(va, vb), 0.0f);
+    }
+    vcol[r * nt] = acc;
+    mn = fminf(mn, acc);
+    mx = fmaxf(mx, acc);
+  }
+  if (!active) { mn = INFINITY; mx = 0.0f; }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_mn[threadIdx.x >> 5] = mn;
+    red_mx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wi = 1; wi < (nt >> 5); ++wi) {
+      mn = fminf(mn, red_mn[wi]);
+      mx = fmaxf(mx, red_mx[wi]);
+    }
+    cta_mm[0] = mn;
+    cta_mm[1] = mx;
+  }
+  mscam_cluster_sync();  // every CTA's min / max is published (release / acquire at cluster scope)
+  float lo = INFINITY, hi = 0.0f;
+#pragma unroll
+  for (uint32_t c = 0; c < MSCAM_CL; ++c) {
+    lo = fminf(lo, ld_cluster_f32(mscam_mapa(&cta_mm[0], c)));
+    hi = fmaxf(hi, ld_cluster_f32(mscam_mapa(&cta_mm[1], c)));
+  }
+  if (rank == 0 && threadIdx.x == 0) {  // the plane's extrema, as the two-pass kernels leave them
+    p.minmax[2 * plane] = __float_as_uint(lo);
+    p.minmax[2 * plane + 1] = __float_as_uint(hi);
+  }
+  const float shift = -lo;                   // cam + max(-cam)
+  const float denom = (hi + shift) + 1e-5f;  // max(cam) + 1e-5
+  const float rcp = __frcp_rn(denom);
+  if (active) {
+    float* o = p.out + (static_cast<long>(plane) * p.H + y_begin) * p.W + x;
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) __stcs(o + static_cast<long>(r) * p.W, div_rn_normal(vcol[r * nt] + shift, denom, rcp));
+  }
+  mscam_cluster_sync();  // no CTA leaves while a peer may still read its cta_mm
+}
+
+template <int NS>
+static int launch_mscam_cluster(const MscamParams& p, cudaStream_t st) {
+  const int nt = (p.W + 31) / 32 * 32;
+  if (nt > 512) return -1;
+  const int rpc = cdiv(p.H, MSCAM_CL);
+  size_t floats = 0;
+  for (int s = 0; s < NS; ++s) {
+    const int nr = min(p.gh[s], cdiv(rpc * p.gh[s], p.H) + 3);
+    floats += 2ull * nr * p.gw[s];
+  }
+  const size_t smem = (floats + 4) * sizeof(float) + static_cast<size_t>(rpc) * NS * (sizeof(MscamRow) + sizeof(float2)) +
+                      static_cast<size_t>((rpc + 3) & ~3) * sizeof(int) + static_cast<size_t>(rpc) * nt * sizeof(float);
+  if (smem > 200 * 1024) return -1;  // tall planes: the two-pass kernels
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_cluster_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.b * p.K * MSCAM_CL));
+  cfg.blockDim = dim3(nt);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MSCAM_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DUPL_CUDA_OK(cudaLaunchKernelEx(&cfg, mscam_cluster_kernel<NS>, p, rpc));
+  count_launch();
+  return DUPL_OK;
+}
+
 __global__ void mscam_init_minmax(unsigned int* mm, int planes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < planes) {
@@ -376,9 +588,18 @@ extern "C" int dupl_mscam_post(const dupl_mscam_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int planes_all = a->b * a->K;
   if (a->nscale <= 4 && planes_all <= 65535 * 32 && getenv("DUPL_MSCAM_GENERIC") == nullptr) {
+    int rc = -1;
+    if (getenv("DUPL_MSCAM_2PASS") == nullptr) {  // one launch: a cluster of 8 CTAs per plane, values computed once
+      switch (a->nscale) {
+        case 1: rc = launch_mscam_cluster<1>(p, st); break;
+        case 2: rc = launch_mscam_cluster<2>(p, st); break;
+        case 3: rc = launch_mscam_cluster<3>(p, st); break;
+        case 4: rc = launch_mscam_cluster<4>(p, st); break;
+      }
+      if (rc >= 0) return rc;
+    }
     mscam_init_minmax<<<cdiv(planes_all, 256), 256, 0, st>>>(p.minmax, planes_all);
     DUPL_LAUNCH_OK();
-    int rc = -1;
     switch (a->nscale) {
       case 1: rc = launch_mscam_columns<1>(p, st); break;
       case 2: rc = launch_mscam_columns<2>(p, st); break;

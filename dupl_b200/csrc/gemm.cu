@@ -51,6 +51,8 @@ struct GemmParamsDev {
   int kper;      // k-blocks per split
   int f32_rows;  // GELU_SPLIT: rows below this get the fp32 pre-activation side output
   int passes;    // 3: hi*hi + hi*lo + lo*hi;  4: + lo*lo (products whose SIGN is consumed downstream: PTC Gram)
+  int a_mn;      // A planes stored [K, M]: MN-major operand, staged as 64-column blocks of [BK rows x 128 B] (BK = 64 only)
+  int b_mn;      // W planes stored [K, N]: same for B (BN = 256 or 128: each CTA stages BN/2 = 128 or 64 columns)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -61,6 +63,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * BK * 2;  // one plane
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the W tile, one plane
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int MN_BLOCK = BK * 128;           // MN-major staging: [BK rows x 64 columns] per block
   static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // per epilogue warp: 32 x 33 fp32 tile for the residual rows
   static constexpr int MAX_STAGES = (227 * 1024 - 2048 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles_per_group = m_pairs * n_tiles;
   const int total_tiles = tiles_per_group * p.groups * p.ksplit;
-  const int k_blocks = p.K / BK;
+  const int k_blocks = (p.K + BK - 1) / BK;  // a ragged last block exists only with two MN-major operands: TMA fills rows >= K with zeros
   // work item t -> (group g, k-split ks, tile r): gs = t / tiles_per_group, g = gs / ksplit, ks = gs % ksplit
 
   if (warp == 0) {
@@ -142,10 +145,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes
-          tma_load_2d_pair(s, &G.tm_a_hi, lead_full, kb * BK, m0);
-          tma_load_2d_pair(s + Cfg::A_BYTES, &G.tm_a_lo, lead_full, kb * BK, m0);
-          tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &G.tm_b_hi, lead_full, kb * BK, n0 + rank * (BN / 2));
-          tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &G.tm_b_lo, lead_full, kb * BK, n0 + rank * (BN / 2));
+          if (!p.a_mn) {
+            tma_load_2d_pair(s, &G.tm_a_hi, lead_full, kb * BK, m0);
+            tma_load_2d_pair(s + Cfg::A_BYTES, &G.tm_a_lo, lead_full, kb * BK, m0);
+          } else {
+            // MN-major: the stored matrix is [K, M]; a box is 64 columns (128 B) x BK rows = one 8 KB block per 64 tile rows
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j) {
+              tma_load_2d_pair(s + j * Cfg::MN_BLOCK, &G.tm_a_hi, lead_full, m0 + 64 * j, kb * BK);
+              tma_load_2d_pair(s + Cfg::A_BYTES + j * Cfg::MN_BLOCK, &G.tm_a_lo, lead_full, m0 + 64 * j, kb * BK);
+            }
+          }
+          const int nb0 = n0 + rank * (BN / 2);
+          if (!p.b_mn) {
+            tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &G.tm_b_hi, lead_full, kb * BK, nb0);
+            tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &G.tm_b_lo, lead_full, kb * BK, nb0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < (BN / 2) / 64; ++j) {
+              tma_load_2d_pair(s + 2 * Cfg::A_BYTES + j * Cfg::MN_BLOCK, &G.tm_b_hi, lead_full, nb0 + 64 * j, kb * BK);
+              tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * Cfg::MN_BLOCK, &G.tm_b_lo, lead_full, nb0 + 64 * j, kb * BK);
+            }
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -156,7 +177,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, lane elected per op)
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN, 0, 0, 256);
+      const uint32_t idesc = umma_idesc_bf16(BN, 0, 0, 256) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+      // descriptor step per UMMA_K = 16: 32 B along a K-major row, 16 rows x 128 B of an MN-major block
+      const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
       const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -172,9 +195,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          auto desc = [](uint32_t addr) { return BK == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr); };
-          const uint64_t a_hi = desc(s), a_lo = desc(s + Cfg::A_BYTES);
-          const uint64_t b_hi = desc(s + 2 * Cfg::A_BYTES), b_lo = desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+          auto desc = [](uint32_t addr, int mn) {
+            return mn ? umma_desc_sw128_mn(addr, Cfg::MN_BLOCK) : (BK == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr));
+          };
+          const uint64_t a_hi = desc(s, p.a_mn), a_lo = desc(s + Cfg::A_BYTES, p.a_mn);
+          const uint64_t b_hi = desc(s + 2 * Cfg::A_BYTES, p.b_mn), b_lo = desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, p.b_mn);
 #pragma unroll
           for (int pass = 0; pass < 4; ++pass) {
             if (pass >= p.passes) break;
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             const uint64_t b = (pass == 1 || pass == 3) ? b_lo : b_hi;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              tc_mma_f16_pair(d_tmem, umma_desc_advance(a, k * 32), umma_desc_advance(b, k * 32), idesc,
+              tc_mma_f16_pair(d_tmem, umma_desc_advance(a, k * a_step), umma_desc_advance(b, k * b_step), idesc,
                               (kb | pass | k) != 0 ? 1u : 0u);
           }
           tc_commit_pair(&empty_bar[stage]);  // stage drained in both CTAs: tell both producers
@@ -432,7 +457,9 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   DUPL_CHECK_ARG(a != nullptr, "dupl_gemm_bf16x3: args is NULL");
   DUPL_CHECK_ARG(a->groups >= 1 && a->groups <= DUPL_MAX_GROUPS, "dupl_gemm_bf16x3: groups=%d", a->groups);
   DUPL_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "dupl_gemm_bf16x3: empty problem %dx%dx%d", a->M, a->N, a->K);
-  DUPL_CHECK_ARG(a->K % 64 == 0, "dupl_gemm_bf16x3: K=%d must be a multiple of 64", a->K);
+  const bool a_mn = a->a_mn_major != 0, b_mn = a->b_mn_major != 0;
+  DUPL_CHECK_ARG(a->K % 64 == 0 || (a_mn && b_mn), "dupl_gemm_bf16x3: K=%d must be a multiple of 64 (unless both operands are MN-major)",
+                 a->K);
   // k-block depth: 64 (128-byte swizzle, 3 stages) and 32 (64-byte swizzle, 7 stages) measure the same on
   // B200 (the kernel is not latency bound); DUPL_GEMM_BK=32 selects the deeper pipeline for experiments.
   static const int bk = [] {
@@ -445,8 +472,11 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     return e != nullptr && strcmp(e, "fixed") == 0;
   }();
   DUPL_CHECK_ARG(a->N % 16 == 0, "dupl_gemm_bf16x3: N=%d must be a multiple of 16", a->N);
-  DUPL_CHECK_ARG(a->lda % 8 == 0 && a->lda >= a->K, "dupl_gemm_bf16x3: lda=%d", a->lda);
-  DUPL_CHECK_ARG(a->ldw == 0 || (a->ldw % 8 == 0 && a->ldw >= a->K), "dupl_gemm_bf16x3: ldw=%d", a->ldw);
+  DUPL_CHECK_ARG(a->lda % 8 == 0 && a->lda >= (a_mn ? a->M : a->K), "dupl_gemm_bf16x3: lda=%d", a->lda);
+  DUPL_CHECK_ARG(a->ldw == 0 || (a->ldw % 8 == 0 && a->ldw >= (b_mn ? a->N : a->K)), "dupl_gemm_bf16x3: ldw=%d", a->ldw);
+  DUPL_CHECK_ARG(!(a_mn || b_mn) || bk == 64, "dupl_gemm_bf16x3: MN-major operands need the 64-deep k-block");
+  DUPL_CHECK_ARG(!b_mn || a->N >= 128, "dupl_gemm_bf16x3: an MN-major W needs N >= 128 (N=%d)", a->N);
+  DUPL_CHECK_ARG(!(a_mn || b_mn) || a->epilogue != DUPL_EPI_PATCH, "dupl_gemm_bf16x3: the PATCH epilogue takes K-major operands");
   DUPL_CHECK_ARG(a->ldo % 8 == 0 && a->ldo >= a->N, "dupl_gemm_bf16x3: ldo=%d", a->ldo);
   DUPL_CHECK_ARG(a->epilogue >= DUPL_EPI_F32 && a->epilogue <= DUPL_EPI_RELU_SPLIT, "dupl_gemm_bf16x3: epilogue=%d",
                  a->epilogue);
@@ -465,6 +495,8 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   P.f32_rows = a->f32_rows > 0 ? a->f32_rows : a->M;
   DUPL_CHECK_ARG(a->passes == 0 || a->passes == 3 || a->passes == 4, "dupl_gemm_bf16x3: passes=%d (3 or 4)", a->passes);
   P.passes = a->passes == 4 ? 4 : 3;
+  P.a_mn = a_mn ? 1 : 0;
+  P.b_mn = b_mn ? 1 : 0;
   P.nseg = 0;
   if (a->epilogue == DUPL_EPI_PATCH) {
     DUPL_CHECK_ARG(a->nseg >= 1 && a->nseg <= DUPL_MAX_SEGMENTS, "dupl_gemm_bf16x3: nseg=%d", a->nseg);
@@ -472,15 +504,17 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     for (int s = 0; s < a->nseg; ++s) P.seg[s] = a->seg[s];
   }
   // Wide tiles for wide outputs; N <= 128 (CAM-sized heads) uses the narrow instantiations.
-  int bn, ks = 1, kper = a->K / bk;
+  const int k_blocks = cdiv(a->K, bk);
+  int bn, ks = 1, kper = k_blocks;
   if (a->N < 256 || fixed_tiling || bk != 64) {
     bn = (a->N >= 256) ? 256 : ((a->N > 64) ? 128 : 64);
   } else {
-    choose_tiling(a->M, a->N, a->K / bk, a->groups, can_split ? a->max_ksplit : 1, true, bn, ks, kper);
+    // an MN-major W is staged in 64-column blocks per CTA: 256- and 128-wide tiles only
+    choose_tiling(a->M, a->N, k_blocks, a->groups, can_split ? a->max_ksplit : 1, !b_mn, bn, ks, kper);
   }
   P.ksplit = ks;
   P.kper = kper;
-  const int ldw = a->ldw > 0 ? a->ldw : a->K;
+  const int ldw = a->ldw > 0 ? a->ldw : (b_mn ? a->N : a->K);
   for (int g = 0; g < a->groups; ++g) {
     const dupl_gemm_group& G = a->g[g];
     DUPL_CHECK_ARG(G.a_hi && G.a_lo && G.w_hi && G.w_lo, "dupl_gemm_bf16x3: NULL operand plane in group %d", g);
@@ -489,10 +523,20 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
     DUPL_CHECK_ARG(f32_out || (G.out_hi && G.out_lo), "dupl_gemm_bf16x3: out_hi/out_lo is NULL in group %d", g);
     DUPL_CHECK_ARG(a->epilogue != DUPL_EPI_RESID || G.resid, "dupl_gemm_bf16x3: resid is NULL in group %d", g);
     int rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, ldw, bn / 2, bk))) return rc;
-    if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, ldw, bn / 2, bk))) return rc;
+    if (!a_mn) {
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->M, a->K, a->lda, GEMM_BM, bk))) return rc;
+    } else {  // stored [K, M]: boxes of 64 columns x bk rows; rows >= K and columns >= M read as zeros
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_hi, G.a_hi, a->K, a->M, a->lda, bk, 64))) return rc;
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_a_lo, G.a_lo, a->K, a->M, a->lda, bk, 64))) return rc;
+    }
+    if (!b_mn) {
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->N, a->K, ldw, bn / 2, bk))) return rc;
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->N, a->K, ldw, bn / 2, bk))) return rc;
+    } else {
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_hi, G.w_hi, a->K, a->N, ldw, bk, 64))) return rc;
+      if ((rc = make_tmap_bf16_2d(&P.g[g].tm_b_lo, G.w_lo, a->K, a->N, ldw, bk, 64))) return rc;
+    }
     P.g[g].bias = G.bias; P.g[g].resid = G.resid;
     P.g[g].out_f32 = ks > 1 ? G.splitk_ws : G.out_f32;
     P.g[g].out_hi = static_cast<__nv_bfloat16*>(G.out_hi);

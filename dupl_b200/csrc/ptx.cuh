@@ -240,6 +240,13 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand wider than one 64-element block: block j (elements 64j .. 64j+63 of the M / N dimension) is its own
+// [k rows x 128 B] region `block_bytes` after block j-1 — the descriptor's leading byte offset; 8-row groups along k stay
+// 1024 B apart (canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t block_bytes) {
+  return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (static_cast<uint64_t>((block_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
 // Same for rows of 64 bytes with the 64-byte swizzle (K-major only): 512 B between 8-row groups, layout = 4.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);

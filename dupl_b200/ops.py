@@ -40,13 +40,16 @@ def split_bf16(x, out=None):
     return hi, lo
 
 
-def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=None, ksplit=0, f32_rows=0, passes=3):
+def gemm_bf16x3(groups, M, N, K, epilogue, lda=None, ldo=None, segs=None, ldw=None, ksplit=0, f32_rows=0, passes=3,
+                a_mn=False, b_mn=False):
     """groups: list of dicts with keys a=(hi,lo), w=(hi,lo), bias, resid, out_f32, out=(hi,lo), pos=[...].
     ksplit > 1 lets the library split the contraction up to that many ways (plain F32 epilogue, no bias): the
-    partial sums go through a workspace allocated here and are added in a fixed order."""
+    partial sums go through a workspace allocated here and are added in a fixed order.
+    a_mn / b_mn: the operand planes are stored transposed ([K, M] resp. [K, N]) and are consumed in place."""
     a = L.GemmArgs()
     a.groups, a.M, a.N, a.K = len(groups), M, N, K
-    a.lda = K if lda is None else lda
+    a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
+    a.lda = (M if a_mn else K) if lda is None else lda
     a.ldo = N if ldo is None else ldo
     a.ldw = 0 if ldw is None else ldw
     a.max_ksplit = ksplit

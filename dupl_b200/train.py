@@ -8,6 +8,7 @@ reference).  Every arithmetic step is a libdupl.so kernel: tcgen05 split-bf16 GE
 dgrad and wgrad contractions, plus the HBM-bound kernels of train_kernels.cu.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -21,6 +22,13 @@ D = E.EMBED
 
 def _pad64(n):
     return (n + 63) // 64 * 64
+
+
+def _mn_major():
+    """wgrad / dgrad GEMMs read their transposed operands in place (MN-major tcgen05 operands: dupl_gemm_args.a_mn_major /
+    b_mn_major) instead of from transposed copies.  DUPL_MN_MAJOR=0 restores the copies (same products in the same order:
+    bit-identical gradients, tests/test_gpu_train.py)."""
+    return os.environ.get("DUPL_MN_MAJOR", "1") != "0"
 
 
 # ------------------------------------------------------------------ thin wrappers of the backward kernels
@@ -108,22 +116,29 @@ def wgrad(dyt_planes, xt_planes, n_rows, n_cols, k_contr, out=None):
     return out
 
 
-def dgrad_multi(pairs, M, n_out, k_contr):
-    """dgrad for several students in ONE grouped launch: pairs = [(dy_planes, wt_planes)] -> [dX]."""
+def dgrad_multi(pairs, M, n_out, k_contr, w_in_place=False):
+    """dgrad for several students in ONE grouped launch: pairs = [(dy_planes, wt_planes)] -> [dX].
+    w_in_place: the second plane pair is the weight as stored, [k_contr, n_out] (consumed as an MN-major operand)."""
     outs = [torch.empty(M, n_out, dtype=torch.float32, device=dy[0].device) for dy, _ in pairs]
-    ops.gemm_bf16x3([dict(a=dy, w=wt, out_f32=o) for (dy, wt), o in zip(pairs, outs)], M, n_out, k_contr, L.EPI_F32)
+    ops.gemm_bf16x3([dict(a=dy, w=wt, out_f32=o) for (dy, wt), o in zip(pairs, outs)], M, n_out, k_contr, L.EPI_F32,
+                    b_mn=w_in_place)
     return outs
 
 
-def wgrad_multi(pairs, n_rows, n_cols, k_contr, outs=None):
+def wgrad_multi(pairs, n_rows, n_cols, k_contr, outs=None, in_place=False):
     """wgrad for several students in ONE grouped launch: pairs = [(dyt_planes, xt_planes)], outs = per-student arena views or
-    None -> [dW [n_rows, n_cols]]."""
+    None -> [dW [n_rows, n_cols]].
+    in_place: the pairs are (dy_planes [k_contr, n_rows], x_planes [k_contr, n_cols]) as the forward / backward left them
+    (row stride = their own width); both are consumed as MN-major operands, k_contr need not be a multiple of 64."""
     outs = list(outs) if outs is not None else [None] * len(pairs)
     for i, (dyt, _) in enumerate(pairs):
         outs[i] = (torch.empty(n_rows, n_cols, dtype=torch.float32, device=dyt[0].device) if outs[i] is None
                    else outs[i].view(n_rows, n_cols))
+    kw = {}
+    if in_place:
+        kw = dict(a_mn=True, b_mn=True, lda=pairs[0][0][0].shape[1], ldw=pairs[0][1][0].shape[1])
     ops.gemm_bf16x3([dict(a=dyt, w=xt, out_f32=o) for (dyt, xt), o in zip(pairs, outs)], n_rows, n_cols, k_contr, L.EPI_F32,
-                    ksplit=L.MAX_KSPLIT)
+                    ksplit=L.MAX_KSPLIT, **kw)
     return outs
 
 
@@ -292,21 +307,27 @@ def _gmp_bwd(x_rows, w, dlogits, argmax, dx, S):
     return dw
 
 
-def _conv_bwd_multi(d_outs, acts, cols, wmat_ts, S, cin, d_ins, in_tokens, in_first, accumulate):
+def _conv_bwd_multi(d_outs, acts, cols, dec_planes, name, S, cin, d_ins, in_tokens, in_first, accumulate):
     """Backward of relu(conv3x3_d5(in)) for several students: d_outs fp32 [Mp, 512] each (grad wrt the relu output) ->
     d_ins (+)=, returns [dWmat [512, 9*cin]]; the dgrad and wgrad GEMMs are one grouped launch each."""
     dev = d_outs[0].device
     Mp = S.Mp
+    mn = _mn_major()
     dpls, dts = [], []
     for d_out, act in zip(d_outs, acts):
         L.check(L.lib().dupl_relu_bwd(L.ptr(d_out), L.ptr(act[0]), L.ptr(act[1]), d_out.numel(), _st(dev)), "dupl_relu_bwd")
-        dpl, dt = split_transpose(d_out, Mp, 512)
+        dpl, dt = split_transpose(d_out, Mp, 512, want_t=not mn)
         dpls.append(dpl)
         dts.append(dt)
-    dcols = dgrad_multi(list(zip(dpls, wmat_ts)), Mp, 9 * cin, 512)
+    if mn:
+        dcols = dgrad_multi([(dpl, dp.get(name)) for dpl, dp in zip(dpls, dec_planes)], Mp, 9 * cin, 512, w_in_place=True)
+    else:
+        dcols = dgrad_multi([(dpl, dp.get_t(name)) for dpl, dp in zip(dpls, dec_planes)], Mp, 9 * cin, 512)
     for dcol, d_in in zip(dcols, d_ins):
         L.check(L.lib().dupl_col2im3x3(L.ptr(dcol), L.ptr(d_in), S.B, S.gh, S.gw, cin, DECODER_DIL, d_in.shape[1], in_tokens, in_first,
                                        1 if accumulate else 0, _st(dev)), "dupl_col2im3x3")
+    if mn:
+        return wgrad_multi(list(zip(dpls, cols)), 512, 9 * cin, Mp, in_place=True)
     col_ts = [transpose_planes(c, Mp, 9 * cin) for c in cols]
     return wgrad_multi(list(zip(dts, col_ts)), 512, 9 * cin, _pad64(Mp))
 
@@ -332,6 +353,7 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
     if any((S.M, S.Mp, S.N, S.B, S.aux_idx) != (M, Mp, N, B, S0.aux_idx) for S in Ss):
         raise RuntimeError("grouped backward needs students with identical shapes")
     Mpad = _pad64(M)
+    mn = _mn_major()
     grads = [s if s is not None else _DictSink() for s in sinks]
     K = nets[0].num_classes - 1
 
@@ -365,11 +387,11 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
             grads[g].put("decoder.conv8.weight", dw8[i][:Cn].reshape(Cn, 512, 1, 1))
         # conv7 + relu, conv6 + relu
         d_h6 = [torch.empty(Mp, 512, **f32) for _ in with_seg]
-        dw7 = _conv_bwd_multi(d_h7, [Ss[g].h7 for g in with_seg], [Ss[g].col7 for g in with_seg], [dps[g].get_t("conv7") for g in with_seg],
+        dw7 = _conv_bwd_multi(d_h7, [Ss[g].h7 for g in with_seg], [Ss[g].col7 for g in with_seg], [dps[g] for g in with_seg], "conv7",
                               S0, 512, d_h6, 0, 0, False)
         for i, g in enumerate(with_seg):
             grads[g].put("decoder.conv7.weight", dw7[i].reshape(512, 3, 3, 512).permute(0, 3, 1, 2))
-        dw6 = _conv_bwd_multi(d_h6, [Ss[g].h6 for g in with_seg], [Ss[g].col6 for g in with_seg], [dps[g].get_t("conv6") for g in with_seg],
+        dw6 = _conv_bwd_multi(d_h6, [Ss[g].h6 for g in with_seg], [Ss[g].col6 for g in with_seg], [dps[g] for g in with_seg], "conv6",
                               S0, D, [d_xn[g] for g in with_seg], N, 1, True)
         for i, g in enumerate(with_seg):
             grads[g].put("decoder.conv6.weight", dw6[i].reshape(512, 3, 3, D).permute(0, 3, 1, 2))
@@ -398,38 +420,47 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
                 # cls_aux reads the output of this block: its gradient joins the residual-stream gradient here
                 grads[g].put("aux_classifier.weight",
                              None if g_aux[g] is None else _gmp_bwd(S.aux_src, S.wa, g_aux[g], S.arg_a, d_tok[g], S).reshape(K, D, 1, 1))
-        # every transposed operand of this block's wgrad (activations) and dgrad (weights) GEMMs, all students: ONE launch
         w_names = ("mlp.fc2", "mlp.fc1", "attn.proj", "attn.qkv")
-        items = []
-        for g in R:
-            items += [(bl[g].hid, M, 4 * D), (bl[g].xn2, M, D), (bl[g].att, M, D), (bl[g].xn1, M, D)]
-        for g in R:
-            for wn in w_names:
-                wp = pls[g].plane(bp + wn + ".weight")
-                items.append((wp, wp[0].shape[0], wp[0].shape[1]))
-        tr = transpose_planes_multi(items)
-        act_t = [dict(zip(("hid", "xn2", "att", "xn1"), tr[4 * g:4 * g + 4])) for g in R]
-        w_t = [dict(zip(w_names, tr[4 * G + 4 * g:4 * G + 4 * g + 4])) for g in R]
+        if mn:
+            # MN-major operands: the wgrad GEMMs read dY and the saved activation planes, the dgrad GEMMs the weight planes,
+            # exactly as they are stored
+            act_t = [dict(hid=bl[g].hid, xn2=bl[g].xn2, att=bl[g].att, xn1=bl[g].xn1) for g in R]
+            w_t = [{wn: pls[g].plane(bp + wn + ".weight") for wn in w_names} for g in R]
+        else:
+            # every transposed operand of this block's wgrad (activations) and dgrad (weights) GEMMs, all students: ONE launch
+            items = []
+            for g in R:
+                items += [(bl[g].hid, M, 4 * D), (bl[g].xn2, M, D), (bl[g].att, M, D), (bl[g].xn1, M, D)]
+            for g in R:
+                for wn in w_names:
+                    wp = pls[g].plane(bp + wn + ".weight")
+                    items.append((wp, wp[0].shape[0], wp[0].shape[1]))
+            tr = transpose_planes_multi(items)
+            act_t = [dict(zip(("hid", "xn2", "att", "xn1"), tr[4 * g:4 * g + 4])) for g in R]
+            w_t = [dict(zip(w_names, tr[4 * G + 4 * g:4 * G + 4 * g + 4])) for g in R]
+
+        def wgrad_of(act, n_rows, n_cols, pname):
+            """dW of one layer for all students: dY = dpl (in place) or dt (transposed copy), X = the saved activation."""
+            dw = wgrad_multi([((dpl if mn else dt)[g], act_t[g][act]) for g in R], n_rows, n_cols, M if mn else Mpad,
+                             outs=[grads[g].out(ep + pname) for g in R], in_place=mn)
+            for g in R:
+                grads[g].put(ep + pname, dw[g])
+
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
         dpl, dt = [None] * G, [None] * G
         for g in R:
-            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True, colsum_out=grads[g].out(ep + "mlp.fc2.bias"))
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_t=not mn, want_colsum=True,
+                                                colsum_out=grads[g].out(ep + "mlp.fc2.bias"))
             grads[g].put(ep + "mlp.fc2.bias", cs)
-        dw = wgrad_multi([(dt[g], act_t[g]["hid"]) for g in R], D, 4 * D, Mpad,
-                         outs=[grads[g].out(ep + "mlp.fc2.weight") for g in R])
-        for g in R:
-            grads[g].put(ep + "mlp.fc2.weight", dw[g])
-        d_hid = dgrad_multi([(dpl[g], w_t[g]["mlp.fc2"]) for g in R], M, 4 * D, D)
+        wgrad_of("hid", D, 4 * D, "mlp.fc2.weight")
+        d_hid = dgrad_multi([(dpl[g], w_t[g]["mlp.fc2"]) for g in R], M, 4 * D, D, w_in_place=mn)
         for g in R:
             # GELU'(fc1 pre-activation) is applied inside the split / transpose pass (dupl_split_transpose_gelu)
-            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_colsum=True, gelu_pre=bl[g].h_pre,
+            dpl[g], dt[g], cs = split_transpose(d_hid[g], M, 4 * D, want_t=not mn, want_colsum=True, gelu_pre=bl[g].h_pre,
                                                 colsum_out=grads[g].out(ep + "mlp.fc1.bias"))
             grads[g].put(ep + "mlp.fc1.bias", cs)
-        dw = wgrad_multi([(dt[g], act_t[g]["xn2"]) for g in R], 4 * D, D, Mpad,
-                         outs=[grads[g].out(ep + "mlp.fc1.weight") for g in R])
-        for g in R:
-            grads[g].put(ep + "mlp.fc1.weight", dw[g])
-        d_xn2 = dgrad_multi([(dpl[g], w_t[g]["mlp.fc1"]) for g in R], M, D, 4 * D)
+        wgrad_of("xn2", 4 * D, D, "mlp.fc1.weight")
+        d_xn2 = dgrad_multi([(dpl[g], w_t[g]["mlp.fc1"]) for g in R], M, D, 4 * D, w_in_place=mn)
         for g in R:
             dg, db = layernorm_bwd(d_xn2[g], bl[g].x_mid, pls[g].vec(bp + "norm2.weight"), d_tok[g],
                                    grads[g].out(ep + "norm2.weight"), grads[g].out(ep + "norm2.bias"))
@@ -437,23 +468,19 @@ def _backward_multi(nets, Ss, g_cls, g_seg, g_x4, g_aux, sinks):
             grads[g].put(ep + "norm2.bias", db)
         # ---- attention: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
         for g in R:
-            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_colsum=True, colsum_out=grads[g].out(ep + "attn.proj.bias"))
+            dpl[g], dt[g], cs = split_transpose(d_tok[g], M, D, want_t=not mn, want_colsum=True,
+                                                colsum_out=grads[g].out(ep + "attn.proj.bias"))
             grads[g].put(ep + "attn.proj.bias", cs)
-        dw = wgrad_multi([(dt[g], act_t[g]["att"]) for g in R], D, D, Mpad,
-                         outs=[grads[g].out(ep + "attn.proj.weight") for g in R])
-        for g in R:
-            grads[g].put(ep + "attn.proj.weight", dw[g])
+        wgrad_of("att", D, D, "attn.proj.weight")
         d_att = [(torch.empty(M, D, **bfk), torch.empty(M, D, **bfk)) for _ in R]   # dO as split planes: operand of the attention backward
-        ops.gemm_bf16x3([dict(a=dpl[g], w=w_t[g]["attn.proj"], out=d_att[g]) for g in R], M, D, D, L.EPI_SPLIT)
+        ops.gemm_bf16x3([dict(a=dpl[g], w=w_t[g]["attn.proj"], out=d_att[g]) for g in R], M, D, D, L.EPI_SPLIT, b_mn=mn)
         for g in R:
             d_qkv = ops.attention_bwd(bl[g].qkv, bl[g].att, d_att[g], bl[g].lse, B, N, E.HEADS, scale)
-            dpl[g], dt[g], cs = split_transpose(d_qkv, M, 3 * D, want_colsum=True, colsum_out=grads[g].out(ep + "attn.qkv.bias"))
+            dpl[g], dt[g], cs = split_transpose(d_qkv, M, 3 * D, want_t=not mn, want_colsum=True,
+                                                colsum_out=grads[g].out(ep + "attn.qkv.bias"))
             grads[g].put(ep + "attn.qkv.bias", cs)
-        dw = wgrad_multi([(dt[g], act_t[g]["xn1"]) for g in R], 3 * D, D, Mpad,
-                         outs=[grads[g].out(ep + "attn.qkv.weight") for g in R])
-        for g in R:
-            grads[g].put(ep + "attn.qkv.weight", dw[g])
-        d_xn1 = dgrad_multi([(dpl[g], w_t[g]["attn.qkv"]) for g in R], M, D, 3 * D)
+        wgrad_of("xn1", 3 * D, D, "attn.qkv.weight")
+        d_xn1 = dgrad_multi([(dpl[g], w_t[g]["attn.qkv"]) for g in R], M, D, 3 * D, w_in_place=mn)
         for g in R:
             dg, db = layernorm_bwd(d_xn1[g], bl[g].x_in, pls[g].vec(bp + "norm1.weight"), d_tok[g],
                                    grads[g].out(ep + "norm1.weight"), grads[g].out(ep + "norm1.bias"))

@@ -90,6 +90,10 @@ typedef struct {
 
 /* C[M,N] = A[M,K] * W[N,K]^T for `groups` independent problems of identical shape (the two
  * students).  K % 64 == 0, N % 16 == 0, 16-byte aligned planes and row strides.
+ * a_mn_major / b_mn_major: the operand is read in place from its transposed storage (MN-major tcgen05 operand: the
+ * contraction runs along the rows of the stored matrix) — what autograd's wgrad (dW = dY^T X: both operands) and dgrad
+ * (dX = dY W: the weight) need, without materialising transposed copies.  With BOTH operands MN-major K may be any positive
+ * number (rows past K read as zeros).
  * Tile width (256/192/128 columns per CTA pair) and, when max_ksplit > 1, a split-K factor are chosen per
  * shape so that the work items fill the 74 CTA pairs of a B200; split-K partial sums go through splitk_ws
  * and are added in a fixed order (bit-reproducible). */
@@ -103,6 +107,8 @@ typedef struct {
   int32_t max_ksplit;                   /* 0/1 = no split-K; else the workspace holds this many partials (F32 epilogue, no bias) */
   int32_t f32_rows;                     /* GELU_SPLIT: only rows < f32_rows get the out_f32 side output (0 = all rows) */
   int32_t passes;                       /* 0/3: hi*hi + hi*lo + lo*hi (error ~2^-16 of sum|a_i w_i|); 4: also lo*lo (fp32-level) */
+  int32_t a_mn_major;                   /* != 0: the A planes are stored [K, M] (row stride lda >= M): A is consumed TRANSPOSED in place */
+  int32_t b_mn_major;                   /* != 0: the W planes are stored [K, N] (row stride ldw >= N, 0 = N); needs N >= 128 */
   dupl_segment seg[DUPL_MAX_SEGMENTS];  /* PATCH only: patch row -> token row mapping */
   dupl_gemm_group g[DUPL_MAX_GROUPS];
 } dupl_gemm_args;

@@ -143,16 +143,41 @@ def test_refine_labels(dynamic):
 @pytest.mark.parametrize("b,K,H,W,grids", [(2, 20, 448, 448, [(28, 28), (14, 14), (42, 42)]), (1, 5, 64, 96, [(4, 6), (2, 3), (6, 9)]),
                                            (3, 7, 100, 130, [(6, 8)]), (1, 3, 224, 224, [(14, 14), (7, 7)])])
 def test_mscam_column_kernel_is_bit_identical_to_the_generic_kernel(b, K, H, W, grids, monkeypatch):
-    """The column-per-thread kernel hoists the horizontal interpolation out of the row loop; same fma order => same bits."""
+    """The single-launch cluster kernel (values computed once, min / max through distributed shared memory) and the two-pass
+    column-per-thread kernels hoist the horizontal interpolation out of the row loop; same fma order => same bits as the
+    generic kernel."""
     from dupl_b200 import ops
     g = torch.Generator().manual_seed(5)
     lowres = [torch.randn(2 * b, K, gh, gw, generator=g).cuda() for gh, gw in grids]
     fast = ops.mscam_post(lowres, b, H, W)
+    monkeypatch.setenv("DUPL_MSCAM_2PASS", "1")
+    two_pass = ops.mscam_post(lowres, b, H, W)
     monkeypatch.setenv("DUPL_MSCAM_GENERIC", "1")
     slow = ops.mscam_post(lowres, b, H, W)
     torch.cuda.synchronize()
     assert torch.isfinite(fast).all()
+    assert torch.equal(two_pass, slow)
     assert torch.equal(fast, slow)
+
+
+def test_mscam_cluster_kernel_short_and_ragged_planes():
+    """H smaller than the cluster (CTAs without rows), W not a multiple of 32, a plane that ReLU leaves all-zero."""
+    from dupl_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for b, K, H, W, grids in [(1, 2, 5, 37, [(2, 3)]), (2, 3, 30, 50, [(3, 5), (2, 2)])]:
+        lowres = [torch.randn(2 * b, K, gh, gw, generator=g).cuda() for gh, gw in grids]
+        for t in lowres:
+            t[0, 0] = -1.0          # image 0, class 0: negative everywhere in the image ...
+            t[b, 0] = -2.0          # ... and in its flipped twin -> value 0 everywhere -> 0 / 1e-5
+        out = ops.mscam_post(lowres, b, H, W)
+        import os
+        os.environ["DUPL_MSCAM_GENERIC"] = "1"
+        try:
+            ref = ops.mscam_post(lowres, b, H, W)
+        finally:
+            del os.environ["DUPL_MSCAM_GENERIC"]
+        assert torch.equal(out, ref)
+        assert (out[0, 0] == 0).all()
 
 
 @pytest.mark.parametrize("B,P,h,w,live", [(4, 42, 224, 224, [4, 6, 8, 10]), (2, 7, 50, 70, None), (1, 3, 24, 33, None),

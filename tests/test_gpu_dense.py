@@ -94,6 +94,42 @@ def test_gemm_split_k_is_exact_and_reproducible(M, N, K):
     assert rel_err(outs[0], plain.double()) < 3e-5
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,groups,ksplit",
+                         [(768, 3072, 3140, True, True, 2, 8),     # wgrad fc2: dY^T [768, M] x hid [M, 3072], ragged K
+                          (2304, 768, 3140, True, True, 1, 8),     # wgrad qkv
+                          (512, 6912, 3136, True, True, 2, 8),     # wgrad conv6
+                          (200, 128, 100, True, True, 1, 0),       # one 64-column block per CTA, two ragged k-blocks
+                          (3140, 3072, 768, False, True, 2, 0),    # dgrad fc2: dY [M, 768] x W [768, 3072] in place
+                          (3140, 768, 2304, False, True, 1, 0),    # dgrad qkv
+                          (333, 192, 128, False, True, 1, 0),      # N not a multiple of the 128-wide tile
+                          (768, 768, 640, True, False, 1, 0)])     # A alone
+def test_gemm_mn_major_operands_in_place(M, N, K, a_mn, b_mn, groups, ksplit):
+    """a_mn_major / b_mn_major: the operand is read from its transposed storage.  Same products in the same order as the
+    K-major launch on transposed copies => bit-identical; and both match fp64."""
+    L, ops = _ops()
+    gs_mn, gs_k, refs = [], [], []
+    Kp = (K + 63) // 64 * 64
+    for g in range(groups):
+        a, w = _rand(M, K, seed=40 + g), _rand(N, K, seed=50 + g, scale=0.05)
+        A, W = ops.split_bf16(a), ops.split_bf16(w)
+        pad = lambda pl: tuple(torch.nn.functional.pad(p, (0, Kp - K)).contiguous() for p in pl)   # noqa: E731
+        tr = lambda pl: tuple(p.t().contiguous() for p in pl)                                        # noqa: E731
+        o1 = torch.full((M, N), float("nan"), device="cuda")
+        o2 = torch.full((M, N), float("nan"), device="cuda")
+        gs_mn.append(dict(a=tr(A) if a_mn else A, w=tr(W) if b_mn else W, out_f32=o1))
+        gs_k.append(dict(a=pad(A), w=pad(W), out_f32=o2))
+        refs.append(a.double() @ w.double().t())
+    ops.gemm_bf16x3(gs_mn, M, N, K, L.EPI_F32, ksplit=ksplit, a_mn=a_mn, b_mn=b_mn)
+    ops.gemm_bf16x3(gs_k, M, N, Kp, L.EPI_F32, ksplit=ksplit)
+    for g in range(groups):
+        assert torch.isfinite(gs_mn[g]["out_f32"]).all()
+        assert rel_err(gs_mn[g]["out_f32"], refs[g]) < 3e-5
+        if ksplit == 0:     # every output element is one accumulator over the k-blocks in order, whatever the tile width
+            assert torch.equal(gs_mn[g]["out_f32"], gs_k[g]["out_f32"])
+        else:               # an MN-major W excludes the 192-wide tile, so the split-K factor may differ: same sums regrouped
+            assert rel_err(gs_mn[g]["out_f32"], gs_k[g]["out_f32"].double()) < 2e-6
+
+
 def test_gemm_gelu_side_output_row_limit():
     L, ops = _ops()
     M, N, K, keep = 700, 768, 256, 300

@@ -62,6 +62,27 @@ def test_student_forward_backward_matches_oracle_autograd(H, W):
     assert all(p.grad is None for p in m.branch1.parameters())  # the other student was not touched
 
 
+def test_in_place_operands_give_the_gradients_of_the_transposed_copies(monkeypatch):
+    """DUPL_MN_MAJOR=1 (default: wgrad / dgrad GEMMs read dY, the saved activations and the weights in place as MN-major
+    tcgen05 operands) vs =0 (transposed copies): the same products; only the split-K grouping of a few wgrad shapes may
+    differ (fp32 regrouping), everything without split-K is bit-identical."""
+    m, _ = _models()
+    x = synth_images(2, 64, 64, seed=21).cuda()
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DUPL_MN_MAJOR", mode)
+        m.zero_grad(set_to_none=True)
+        outs = m(x)
+        probes = _probe_weights(outs["branch1"], seed=5)
+        sum((o * w.cuda()).sum() for br in ("branch1", "branch2") for o, w in zip(outs[br], probes)).backward()
+        grads[mode] = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert grads["0"].keys() == grads["1"].keys() and len(grads["1"]) == 308
+    worst = max((_nrel(grads["1"][n], grads["0"][n]), n) for n in grads["0"])
+    assert worst[0] < 2e-6, worst
+    same = sum(torch.equal(grads["1"][n], grads["0"][n]) for n in grads["0"])
+    assert same >= 100, same          # biases / norms / classifier heads never see a GEMM regrouping
+
+
 def test_both_students_dict_output_and_need_sp_view():
     """model(x) -> {'branch1': 4-tuple, 'branch2': 4-tuple}; need_sp adds the 0.75x aug-view seg logits (model_dupl.py:190-205)."""
     from oracle import dupl_oracle as O
