@@ -288,13 +288,14 @@ static int launch_mscam_columns(const MscamParams& p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-launch variant: a CLUSTER of MSCAM_CL CTAs owns one (image, class) plane, CTA `rank` its rows
+// Single-launch variant: a CLUSTER of CL CTAs owns one (image, class) plane, CTA `rank` its rows
 // [rank*rpc, (rank+1)*rpc).  Each CTA computes its un-normalised values ONCE into shared memory (a thread owns one
 // output column, as in mscam_kernel), the plane's min / max go through distributed shared memory (two cluster
 // barriers, no atomics, no second launch that recomputes every value), then the tile is normalised out of shared
 // memory and streamed to HBM.  Same arithmetic in the same order as mscam_kernel: bit-identical output.
+// CL = 16 (non-portable cluster size) when the device schedules it: 80 planes x 8 CTAs of 110 KB are 2.16 waves of the
+// 296 CTA slots (measured 61 us: three waves), 80 x 16 CTAs of 55 KB are 2.9 waves of 444 slots at half the work each.
 // ---------------------------------------------------------------------------------------------
-constexpr int MSCAM_CL = 8;
 
 __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
   float v;
@@ -311,15 +312,15 @@ __device__ __forceinline__ void mscam_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int NS>
+template <int NS, int CL>
 __global__ void __launch_bounds__(512) mscam_cluster_kernel(MscamParams p, int rpc) {
   extern __shared__ float sm[];
   __shared__ int g_rlo[NS], g_nr[NS], g_off[NS + 1];
   __shared__ float red_mn[16], red_mx[16];
-  __shared__ float cta_mm[2];  // this CTA's min / max, read by its 7 peers
+  __shared__ float cta_mm[2];  // this CTA's min / max, read by its peers
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const int plane = blockIdx.x / MSCAM_CL;  // img*K + k
+  const int plane = blockIdx.x / CL;  // img*K + k
   const int img = plane / p.K, k = plane % p.K;
   const int y_begin = min(static_cast<int>(rank) * rpc, p.H);
   const int y_end = min(y_begin + rpc, p.H);
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(512) mscam_cluster_kernel(MscamParams p, int r
   mscam_cluster_sync();  // every CTA's min / max is published (release / acquire at cluster scope)
   float lo = INFINITY, hi = 0.0f;
 #pragma unroll
-  for (uint32_t c = 0; c < MSCAM_CL; ++c) {
+  for (uint32_t c = 0; c < CL; ++c) {
     lo = fminf(lo, ld_cluster_f32(mscam_mapa(&cta_mm[0], c)));
     hi = fmaxf(hi, ld_cluster_f32(mscam_mapa(&cta_mm[1], c)));
   }
@@ -464,11 +465,11 @@ __global__ void __launch_bounds__(512) mscam_cluster_kernel(MscamParams p, int r
   mscam_cluster_sync();  // no CTA leaves while a peer may still read its cta_mm
 }
 
-template <int NS>
-static int launch_mscam_cluster(const MscamParams& p, cudaStream_t st) {
+template <int NS, int CL>
+static int launch_mscam_cluster_cl(const MscamParams& p, cudaStream_t st) {
   const int nt = (p.W + 31) / 32 * 32;
   if (nt > 512) return -1;
-  const int rpc = cdiv(p.H, MSCAM_CL);
+  const int rpc = cdiv(p.H, CL);
   size_t floats = 0;
   for (int s = 0; s < NS; ++s) {
     const int nr = min(p.gh[s], cdiv(rpc * p.gh[s], p.H) + 3);
@@ -478,25 +479,45 @@ static int launch_mscam_cluster(const MscamParams& p, cudaStream_t st) {
                       static_cast<size_t>((rpc + 3) & ~3) * sizeof(int) + static_cast<size_t>(rpc) * nt * sizeof(float);
   if (smem > 200 * 1024) return -1;  // tall planes: the two-pass kernels
   static size_t smem_set = 0;
+  static int usable = -1;            // CL > 8: can the device co-schedule such a cluster at all?
   if (smem > smem_set) {
-    DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_cluster_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_cluster_kernel<NS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (CL > 8) DUPL_CUDA_OK(cudaFuncSetAttribute(mscam_cluster_kernel<NS, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     smem_set = smem;
+    usable = -1;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(p.b * p.K * MSCAM_CL));
+  cfg.gridDim = dim3(static_cast<unsigned>(p.b * p.K * CL));
   cfg.blockDim = dim3(nt);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MSCAM_CL;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DUPL_CUDA_OK(cudaLaunchKernelEx(&cfg, mscam_cluster_kernel<NS>, p, rpc));
+  if (CL > 8 && usable < 0) {
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, mscam_cluster_kernel<NS, CL>, &cfg);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    usable = (e == cudaSuccess && n > 0) ? 1 : 0;
+  }
+  if (CL > 8 && usable == 0) return -1;
+  DUPL_CUDA_OK(cudaLaunchKernelEx(&cfg, mscam_cluster_kernel<NS, CL>, p, rpc));
   count_launch();
   return DUPL_OK;
+}
+
+template <int NS>
+static int launch_mscam_cluster(const MscamParams& p, cudaStream_t st) {
+  static const int want = getenv("DUPL_MSCAM_CLUSTER") ? atoi(getenv("DUPL_MSCAM_CLUSTER")) : 16;
+  if (want >= 16 && p.H >= 64) {
+    const int rc = launch_mscam_cluster_cl<NS, 16>(p, st);
+    if (rc >= 0) return rc;
+  }
+  return launch_mscam_cluster_cl<NS, 8>(p, st);
 }
 
 __global__ void mscam_init_minmax(unsigned int* mm, int planes) {

@@ -194,87 +194,64 @@ struct CamParams {
   long out_offset[DUPL_MAX_SEGMENTS];
   int nseg, total_patch_rows;
 };
-// One warp per CAM_TOK consecutive patch tokens: optional final LayerNorm in registers, then K dot products of length D=768.
-// A warp per single token re-read the K x 768 classifier weights from L1 for every token (60 KB per 3 KB token row for
-// VOC: the kernel ran at the L1 bandwidth, 76-80 us for 21 952 tokens, 8x its HBM time); with CAM_TOK tokens in registers a
-// weight row serves all of them.  Per token the arithmetic and its order are unchanged (bit-identical results).
-constexpr int CAM_TOK = 4;
+// One warp per patch token: optional final LayerNorm in registers, then K dot products of length D=768.
 __global__ void __launch_bounds__(256) cam_contract_kernel(const float* __restrict__ tok, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
                                                            const float* __restrict__ w, int K, CamParams p,
                                                            float* __restrict__ out) {
   constexpr int V = 6, D = 768;
   const int lane = threadIdx.x & 31;
-  const int prow0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CAM_TOK;
-  if (prow0 >= p.total_patch_rows) return;
-  float4 v[CAM_TOK][V];
-  float* o[CAM_TOK];
-  int np_t[CAM_TOK];
+  const int prow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (prow >= p.total_patch_rows) return;
+  int si = 0;
+  for (int s = 1; s < p.nseg; ++s)
+    if (prow >= p.seg[s].patch_row_offset) si = s;
+  const dupl_segment sg = p.seg[si];
+  const int np = sg.tokens - 1;
+  const int local = prow - sg.patch_row_offset;
+  const int img = local / np, pidx = local % np;
+  const long trow = sg.row_offset + static_cast<long>(img) * sg.tokens + 1 + pidx;
+  const float4* xr = reinterpret_cast<const float4*>(tok + trow * D);
+  float4 v[V];
 #pragma unroll
-  for (int t = 0; t < CAM_TOK; ++t) {
-    const int prow = min(prow0 + t, p.total_patch_rows - 1);  // a ragged last group repeats its last token (not stored)
-    int si = 0;
-    for (int s = 1; s < p.nseg; ++s)
-      if (prow >= p.seg[s].patch_row_offset) si = s;
-    const dupl_segment sg = p.seg[si];
-    const int np = sg.tokens - 1;
-    const int local = prow - sg.patch_row_offset;
-    const int img = local / np, pidx = local % np;
-    const long trow = sg.row_offset + static_cast<long>(img) * sg.tokens + 1 + pidx;
-    const float4* xr = reinterpret_cast<const float4*>(tok + trow * D);
-#pragma unroll
-    for (int i = 0; i < V; ++i) v[t][i] = xr[lane + 32 * i];
-    o[t] = out + p.out_offset[si] + static_cast<long>(img) * K * np + pidx;
-    np_t[t] = np;
-  }
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
   if (gamma != nullptr) {
+    float s = 0.0f;
 #pragma unroll
-    for (int t = 0; t < CAM_TOK; ++t) {
-      float s = 0.0f;
+    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.0f;
 #pragma unroll
-      for (int i = 0; i < V; ++i) s += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
-      const float mean = warp_sum(s) * (1.0f / D);
-      float q = 0.0f;
+    for (int i = 0; i < V; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float a = v[t][i].x - mean, b = v[t][i].y - mean, c = v[t][i].z - mean, d = v[t][i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
-      }
-      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-        v[t][i].x = (v[t][i].x - mean) * rstd * g.x + b.x;
-        v[t][i].y = (v[t][i].y - mean) * rstd * g.y + b.y;
-        v[t][i].z = (v[t][i].z - mean) * rstd * g.z + b.z;
-        v[t][i].w = (v[t][i].w - mean) * rstd * g.w + b.w;
-      }
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
+      v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+      v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
+      v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
     }
   }
-  const int nvalid = min(CAM_TOK, p.total_patch_rows - prow0);
+  float* o = out + p.out_offset[si] + static_cast<long>(img) * K * np + pidx;
   for (int k = 0; k < K; ++k) {
     const float4* wr = reinterpret_cast<const float4*>(w + static_cast<long>(k) * D);
-    float acc[CAM_TOK];
-#pragma unroll
-    for (int t = 0; t < CAM_TOK; ++t) acc[t] = 0.0f;
+    float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float4 ww = __ldg(wr + lane + 32 * i);
-#pragma unroll
-      for (int t = 0; t < CAM_TOK; ++t) {
-        acc[t] = fmaf(v[t][i].x, ww.x, acc[t]);
-        acc[t] = fmaf(v[t][i].y, ww.y, acc[t]);
-        acc[t] = fmaf(v[t][i].z, ww.z, acc[t]);
-        acc[t] = fmaf(v[t][i].w, ww.w, acc[t]);
-      }
+      acc = fmaf(v[i].x, ww.x, acc);
+      acc = fmaf(v[i].y, ww.y, acc);
+      acc = fmaf(v[i].z, ww.z, acc);
+      acc = fmaf(v[i].w, ww.w, acc);
     }
-#pragma unroll
-    for (int t = 0; t < CAM_TOK; ++t) {
-      const float r = warp_sum(acc[t]);
-      if (lane == 0 && t < nvalid) o[t][static_cast<long>(k) * np_t[t]] = r;
-    }
+    acc = warp_sum(acc);
+    if (lane == 0) o[static_cast<long>(k) * np] = acc;
   }
 }
 
@@ -370,7 +347,7 @@ extern "C" int dupl_cam_contract(const float* tok, const float* gamma, const flo
     total += seg[s].batch * (seg[s].tokens - 1);
   }
   p.total_patch_rows = total;
-  cam_contract_kernel<<<cdiv(total, 8 * CAM_TOK), 256, 0, static_cast<cudaStream_t>(stream)>>>(tok, gamma, beta, eps, w, K, p, out);
+  cam_contract_kernel<<<cdiv(total, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(tok, gamma, beta, eps, w, K, p, out);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }

@@ -127,7 +127,7 @@ def test_gemm_mn_major_operands_in_place(M, N, K, a_mn, b_mn, groups, ksplit):
         if ksplit == 0:     # every output element is one accumulator over the k-blocks in order, whatever the tile width
             assert torch.equal(gs_mn[g]["out_f32"], gs_k[g]["out_f32"])
         else:               # an MN-major W excludes the 192-wide tile, so the split-K factor may differ: same sums regrouped
-            assert rel_err(gs_mn[g]["out_f32"], gs_k[g]["out_f32"].double()) < 2e-6
+            assert rel_err(gs_mn[g]["out_f32"], gs_k[g]["out_f32"].double()) < 2e-5
 
 
 def test_gemm_gelu_side_output_row_limit():
