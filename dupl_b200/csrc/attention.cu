@@ -67,6 +67,7 @@ enum {  // mbarrier slots
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __grid_constant__ AttnParamsDev p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
@@ -381,7 +382,7 @@ extern "C" int dupl_attention_fwd(const dupl_attention_args* a, void* stream) {
     DUPL_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  attention_fwd_kernel<<<total, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
-  DUPL_LAUNCH_OK();
+  DUPL_CUDA_OK(launch_pdl(attention_fwd_kernel, dim3(total), dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), P));
+  count_launch();
   return DUPL_OK;
 }

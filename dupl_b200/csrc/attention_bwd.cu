@@ -95,6 +95,7 @@ constexpr int AB_STAGES = 4;
 // ------------------------------------------------------------------------------------------------ dQ
 // grid (q tiles of 128, heads, images)
 __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdTcParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                     // hi | lo, 128 rows
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
 // ------------------------------------------------------------------------------------------------ dK, dV
 // grid (kv tiles of 128, heads, images)
 __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdTcParams p) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                   // hi | lo, 128 rows
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
 __global__ void __launch_bounds__(256) attn_bwd_d_kernel(const __nv_bfloat16* __restrict__ do_hi, const __nv_bfloat16* __restrict__ do_lo,
                                                          const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
                                                          float* __restrict__ Dvec, int row_offset, int rows, int heads) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (item >= rows * heads) return;
@@ -452,14 +455,15 @@ extern "C" int dupl_attention_bwd(const dupl_attention_bwd_args* a, void* stream
     attr_set = true;
   }
   const int rows = a->batch * a->tokens;
-  attn_bwd_d_kernel<<<cdiv(rows * a->heads, 8), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(a->do_hi), static_cast<const __nv_bfloat16*>(a->do_lo),
-      static_cast<const __nv_bfloat16*>(a->o_hi), static_cast<const __nv_bfloat16*>(a->o_lo), a->Dvec, a->row_offset, rows, a->heads);
-  DUPL_LAUNCH_OK();
+  DUPL_CUDA_OK(launch_pdl(attn_bwd_d_kernel, dim3(cdiv(rows * a->heads, 8)), dim3(256), 0, st,
+                          static_cast<const __nv_bfloat16*>(a->do_hi), static_cast<const __nv_bfloat16*>(a->do_lo),
+                          static_cast<const __nv_bfloat16*>(a->o_hi), static_cast<const __nv_bfloat16*>(a->o_lo), a->Dvec,
+                          a->row_offset, rows, a->heads));
+  count_launch();
   dim3 grid(cdiv(a->tokens, 128), a->heads, a->batch);
-  attn_bwd_dkv_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(P);
-  DUPL_LAUNCH_OK();
-  attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(P);
-  DUPL_LAUNCH_OK();
+  DUPL_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(AB_THREADS), AB_SMEM, st, P));
+  count_launch();
+  DUPL_CUDA_OK(launch_pdl(attn_bwd_dq_kernel, grid, dim3(AB_THREADS), AB_SMEM, st, P));
+  count_launch();
   return DUPL_OK;
 }

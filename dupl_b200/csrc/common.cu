@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -91,6 +93,14 @@ int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1
     return DUPL_ERR_CUDA;
   }
   return DUPL_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DUPL_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 
 int sm_count() {

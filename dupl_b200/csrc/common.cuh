@@ -56,4 +56,34 @@ int gemm_sms();  // SMs the persistent GEMM grid may occupy (dupl_set_gemm_sm_li
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (sm_90+): the ~800 kernels of a captured training step are short (median ~10 us) and each
+// boundary costs a launch latency once the previous grid has drained.  Kernels launched through launch_pdl() may be
+// SCHEDULED while their predecessor in the stream is still running: every such kernel starts with pdl_sync(), which
+// (1) lets its own successor be scheduled early and (2) blocks until the predecessor has completed and its writes are
+// visible — so no kernel touches global memory before the grid it depends on is done, and the order of all memory
+// operations is the stream order.  DUPL_PDL=0 launches without the attribute (pdl_sync() is then a no-op).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 }  // namespace dupl

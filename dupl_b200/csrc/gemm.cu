@@ -74,6 +74,7 @@ struct GemmCfg {
 template <int BN, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParamsDev p) {
   using Cfg = GemmCfg<BN, BK>;
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 // Deterministic split-K tail: out[i] = sum_s ws[s][i] in fixed order.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ out, int ks,
                                                             long n4) {
+  pdl_sync();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= n4) return;
   float4 a = __ldcs(ws + i);
@@ -391,13 +393,15 @@ static int launch_gemm(const GemmParamsDev& P, cudaStream_t stream) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   DUPL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<BN, BK>, P));
   count_launch();
   return DUPL_OK;
@@ -562,9 +566,9 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   if (ks > 1) {
     const long n4 = static_cast<long>(a->M) * a->ldo / 4;
     for (int g = 0; g < a->groups; ++g) {
-      splitk_reduce_kernel<<<static_cast<int>((n4 + 255) / 256), 256, 0, st>>>(
-          reinterpret_cast<const float4*>(a->g[g].splitk_ws), reinterpret_cast<float4*>(a->g[g].out_f32), ks, n4);
-      DUPL_LAUNCH_OK();
+      DUPL_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, st,
+                              reinterpret_cast<const float4*>(a->g[g].splitk_ws), reinterpret_cast<float4*>(a->g[g].out_f32), ks, n4));
+      count_launch();
     }
   }
   return DUPL_OK;

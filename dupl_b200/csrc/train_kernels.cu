@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
                                                               int Rpad, float* __restrict__ colsum_ws,
                                                               const float* __restrict__ gelu_pre) {
+  pdl_sync();
   __shared__ float tile[64][33];
   __shared__ float part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
 
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ ws, int ntiles, int Cc,
                                                             float* __restrict__ out) {
+  pdl_sync();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= Cc) return;
   float t = 0.0f;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, float* __restrict__ dres,
                                                             float* __restrict__ partial, int rows, float eps) {
   constexpr int COLS = V * 128;
+  pdl_sync();
   __shared__ float sbuf[8][COLS];  // cross-warp reduction buffer, used twice (dgamma then dbeta partials)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 ag[V], ab[V];
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // added in a fixed order (deterministic).  The one-thread-per-column version walked ~200 partials serially (13 us).
 __global__ void __launch_bounds__(256) layernorm_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int cols,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   __shared__ float sa[8][32], sb[8][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -408,13 +412,14 @@ static int split_transpose_impl(const float* src, int32_t R, int32_t Cc, int32_t
   const int rows = t_hi ? Rpad : R;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(cdiv(rows, 64), cdiv(Cc, 32));
-  split_transpose_kernel<<<grid, 256, 0, st>>>(src, R, Cc, ld, make_map(tokens, np, first), static_cast<__nv_bfloat16*>(hi),
-                                               static_cast<__nv_bfloat16*>(lo), static_cast<__nv_bfloat16*>(t_hi),
-                                               static_cast<__nv_bfloat16*>(t_lo), Rpad, colsum_ws, gelu_pre);
-  DUPL_LAUNCH_OK();
+  DUPL_CUDA_OK(launch_pdl(split_transpose_kernel, grid, dim3(256), 0, st, src, R, Cc, ld, make_map(tokens, np, first),
+                          static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), static_cast<__nv_bfloat16*>(t_hi),
+                          static_cast<__nv_bfloat16*>(t_lo), Rpad, colsum_ws, gelu_pre));
+  count_launch();
   if (colsum != nullptr) {
-    colsum_finish_kernel<<<cdiv(Cc, 256), 256, 0, st>>>(colsum_ws, static_cast<int>(grid.x), Cc, colsum);
-    DUPL_LAUNCH_OK();
+    DUPL_CUDA_OK(launch_pdl(colsum_finish_kernel, dim3(cdiv(Cc, 256)), dim3(256), 0, st, static_cast<const float*>(colsum_ws),
+                            static_cast<int>(grid.x), Cc, colsum));
+    count_launch();
   }
   return DUPL_OK;
 }
@@ -482,10 +487,11 @@ extern "C" int dupl_layernorm_bwd(const float* dy, const float* x, const float* 
   DUPL_CHECK_ARG(rows > 0 && cols == 768, "dupl_layernorm_bwd: rows=%d cols=%d (768 columns are built)", rows, cols);
   const int nb = cdiv(rows, LNB_ROWS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  layernorm_bwd_kernel<6><<<nb, 256, 0, st>>>(dy, x, gamma, dres, partial, rows, eps);
-  DUPL_LAUNCH_OK();
-  layernorm_bwd_finish_kernel<<<cdiv(cols, 32), 256, 0, st>>>(partial, nb, cols, dgamma, dbeta);
-  DUPL_LAUNCH_OK();
+  DUPL_CUDA_OK(launch_pdl(layernorm_bwd_kernel<6>, dim3(nb), dim3(256), 0, st, dy, x, gamma, dres, partial, rows, eps));
+  count_launch();
+  DUPL_CUDA_OK(launch_pdl(layernorm_bwd_finish_kernel, dim3(cdiv(cols, 32)), dim3(256), 0, st, static_cast<const float*>(partial), nb,
+                          cols, dgamma, dbeta));
+  count_launch();
   return DUPL_OK;
 }
 

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32,
                                                               int rows, float eps) {
   constexpr int COLS = V * 128;
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -283,11 +284,12 @@ extern "C" int dupl_layernorm_split(const float* x, const float* gamma, const fl
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(out_lo);
   switch (cols / 128) {
-#define LN_CASE(V) case V: layernorm_split_kernel<V><<<grid, 256, 0, st>>>(x, gamma, beta, hi, lo, out_f32, rows, eps); break;
+#define LN_CASE(V) \
+  case V: DUPL_CUDA_OK(launch_pdl(layernorm_split_kernel<V>, dim3(grid), dim3(256), 0, st, x, gamma, beta, hi, lo, out_f32, rows, eps)); break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
   }
-  DUPL_LAUNCH_OK();
+  count_launch();
   return DUPL_OK;
 }
 
