@@ -293,8 +293,9 @@ static int launch_mscam_columns(const MscamParams& p, cudaStream_t st) {
 // output column, as in mscam_kernel), the plane's min / max go through distributed shared memory (two cluster
 // barriers, no atomics, no second launch that recomputes every value), then the tile is normalised out of shared
 // memory and streamed to HBM.  Same arithmetic in the same order as mscam_kernel: bit-identical output.
-// CL = 16 (non-portable cluster size) when the device schedules it: 80 planes x 8 CTAs of 110 KB are 2.16 waves of the
-// 296 CTA slots (measured 61 us: three waves), 80 x 16 CTAs of 55 KB are 2.9 waves of 444 slots at half the work each.
+// CL = 8: 80 planes x 8 CTAs of 110 KB are 2.16 waves of the 296 CTA slots (measured 61 us per call, three waves; the
+// two-pass kernels took 85 us).  CL = 16 (non-portable cluster size; 55 KB per CTA, 2.9 waves of 444 slots at half the work
+// each) measured SLOWER (81 us: 16-CTA clusters place badly) and stays an experiment switch, DUPL_MSCAM_CLUSTER=16.
 // ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
@@ -512,7 +513,7 @@ static int launch_mscam_cluster_cl(const MscamParams& p, cudaStream_t st) {
 
 template <int NS>
 static int launch_mscam_cluster(const MscamParams& p, cudaStream_t st) {
-  static const int want = getenv("DUPL_MSCAM_CLUSTER") ? atoi(getenv("DUPL_MSCAM_CLUSTER")) : 16;
+  static const int want = getenv("DUPL_MSCAM_CLUSTER") ? atoi(getenv("DUPL_MSCAM_CLUSTER")) : 8;
   if (want >= 16 && p.H >= 64) {
     const int rc = launch_mscam_cluster_cl<NS, 16>(p, st);
     if (rc >= 0) return rc;

@@ -98,7 +98,7 @@ int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("DUPL_PDL");
-    return e == nullptr || atoi(e) != 0;
+    return e != nullptr && atoi(e) != 0;
   }();
   return on;
 }
