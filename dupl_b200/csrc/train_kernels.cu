@@ -36,14 +36,23 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 // gelu_pre != nullptr: src is the gradient w.r.t. GELU's OUTPUT and every element is first multiplied by GELU'(pre) — the
 // separate element-wise pass over the [M, 3072] hidden gradient (read + read + write of 38.6 MB each) disappears.
+// colsum_out != nullptr: the column sums are finished in THIS launch — every CTA of a 32-column strip takes a ticket after
+// publishing its partial sums, and the CTA that takes the last one adds the strip's partials in row-tile order (the order
+// colsum_finish_kernel uses: same bits, whichever CTA comes last) and resets the ticket for the next launch.  98 launches
+// of a 4 us kernel per training step disappear.
+constexpr int COLSUM_TICKET_SETS = 32, COLSUM_TICKET_STRIPS = 128;
+__device__ unsigned int g_colsum_tickets[COLSUM_TICKET_SETS * COLSUM_TICKET_STRIPS];  // zero at load, self-resetting
+
 __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, int R, int Cc, int ld, RowMap map,
                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                               __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
                                                               int Rpad, float* __restrict__ colsum_ws,
-                                                              const float* __restrict__ gelu_pre) {
+                                                              const float* __restrict__ gelu_pre, float* __restrict__ colsum_out,
+                                                              unsigned int* __restrict__ tickets) {
   pdl_sync();
   __shared__ float tile[64][33];
   __shared__ float part[8][32];
+  __shared__ bool last_of_strip;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   const int c = c0 + lane;
@@ -84,6 +93,24 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
         *reinterpret_cast<uint32_t*>(t_hi + static_cast<long>(co) * Rpad + r) = h2;
         *reinterpret_cast<uint32_t*>(t_lo + static_cast<long>(co) * Rpad + r) = l2;
       }
+    }
+  }
+  if (colsum_out != nullptr) {
+    if (warp == 0) {
+      __threadfence();  // this CTA's partial row of colsum_ws is visible device-wide before its ticket is
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned int t = atomicAdd(tickets + blockIdx.y, 1u);
+        last_of_strip = (t == gridDim.x - 1);
+        if (last_of_strip) tickets[blockIdx.y] = 0;  // every CTA of the strip has taken its ticket
+      }
+    }
+    __syncthreads();
+    if (last_of_strip && warp == 0 && c < Cc) {
+      __threadfence();
+      float t = 0.0f;
+      for (int k = 0; k < static_cast<int>(gridDim.x); ++k) t += __ldcg(colsum_ws + static_cast<long>(k) * Cc + c);
+      colsum_out[c] = t;
     }
   }
 }
@@ -412,11 +439,21 @@ static int split_transpose_impl(const float* src, int32_t R, int32_t Cc, int32_t
   const int rows = t_hi ? Rpad : R;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(cdiv(rows, 64), cdiv(Cc, 32));
+  // column sums finished by the last CTA of every 32-column strip (DUPL_COLSUM_2PASS=1: the separate finish kernel)
+  static const bool two_pass = getenv("DUPL_COLSUM_2PASS") != nullptr;
+  static unsigned int* ticket_base = nullptr;
+  static unsigned int next_set = 0;
+  const bool fused = colsum != nullptr && !two_pass && grid.y <= static_cast<unsigned>(COLSUM_TICKET_STRIPS);
+  unsigned int* tickets = nullptr;
+  if (fused) {
+    if (ticket_base == nullptr) DUPL_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&ticket_base), g_colsum_tickets));
+    tickets = ticket_base + (next_set++ % COLSUM_TICKET_SETS) * COLSUM_TICKET_STRIPS;  // launches in flight never share a set
+  }
   DUPL_CUDA_OK(launch_pdl(split_transpose_kernel, grid, dim3(256), 0, st, src, R, Cc, ld, make_map(tokens, np, first),
                           static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), static_cast<__nv_bfloat16*>(t_hi),
-                          static_cast<__nv_bfloat16*>(t_lo), Rpad, colsum_ws, gelu_pre));
+                          static_cast<__nv_bfloat16*>(t_lo), Rpad, colsum_ws, gelu_pre, fused ? colsum : nullptr, tickets));
   count_launch();
-  if (colsum != nullptr) {
+  if (colsum != nullptr && !fused) {
     DUPL_CUDA_OK(launch_pdl(colsum_finish_kernel, dim3(cdiv(Cc, 256)), dim3(256), 0, st, static_cast<const float*>(colsum_ws),
                             static_cast<int>(grid.x), Cc, colsum));
     count_launch();

@@ -17,6 +17,7 @@ from dupl_b200.train_step import Args, TrainStep, make_optimizer  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--phase", default="B", choices=["B", "C"])
 ap.add_argument("--table", action="store_true")
+ap.add_argument("--gaps", action="store_true", help="with --table: idle time between consecutive kernels of the replay, by the kernel that follows the gap")
 a = ap.parse_args()
 m = siamese_network("deit_base_patch16_224", num_classes=21, pretrained=False, aux_layer=-3)
 m.load_state_dict(init_state_dict(21), strict=True)
@@ -34,6 +35,26 @@ if a.table:
         step(x, cls, box, n0 + 5)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=72))
+    if a.gaps:
+        import collections
+        ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                     if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()), key=lambda t: t[0])
+        span = ev[-1][1] - ev[0][0]
+        busy, gaps, by_next, hist = 0.0, 0.0, collections.defaultdict(lambda: [0.0, 0]), collections.Counter()
+        end = ev[0][0]
+        for s0, s1, name in ev:
+            g = max(0.0, s0 - end)
+            gaps += g
+            key = name.split("(")[0].replace("void ", "").replace("dupl::", "")[:48]
+            by_next[key][0] += g
+            by_next[key][1] += 1
+            hist[min(int(g), 20)] += 1
+            busy += max(0.0, s1 - max(s0, end))
+            end = max(end, s1)
+        print(f"\nGAPS: {len(ev)} device activities, span {span / 1e3:.3f} ms, busy {busy / 1e3:.3f} ms, idle between activities {gaps / 1e3:.3f} ms")
+        print("gap histogram (us -> count):", dict(sorted(hist.items())))
+        for k, (g, n) in sorted(by_next.items(), key=lambda kv: -kv[1][0])[:25]:
+            print(f"  {g:9.1f} us before {n:4d} x {k}  ({g / n:.2f} us each)")
 else:
     torch.cuda.profiler.start()
     step(x, cls, box, n0 + 5)
