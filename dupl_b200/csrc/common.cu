@@ -103,20 +103,6 @@ bool pdl_enabled() {
   return on;
 }
 
-void prefer_max_smem(const void* kernel) {
-  static const bool on = [] {
-    const char* e = getenv("DUPL_SMEM_CARVEOUT");
-    return e != nullptr && atoi(e) != 0;
-  }();
-  if (!on) return;
-  static const void* seen[64];
-  static int nseen = 0;
-  for (int i = 0; i < nseen; ++i)
-    if (seen[i] == kernel) return;
-  if (nseen < 64) seen[nseen++] = kernel;
-  (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -66,9 +66,6 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // recorded duration) and cost more than the launch latency they hide.  OFF by default; DUPL_PDL=1 enables it (without
 // the attribute pdl_sync() is a no-op).
 bool pdl_enabled();
-// Experiment (DUPL_SMEM_CARVEOUT=1): the small kernels between two 200-KB-shared-memory GEMM / attention launches ask for
-// the maximum shared-memory carve-out too, so that the SMs are not re-partitioned (L1 <-> shared) at every kernel boundary.
-void prefer_max_smem(const void* kernel);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -82,7 +79,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  prefer_max_smem(reinterpret_cast<const void*>(kernel));
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

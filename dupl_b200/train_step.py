@@ -6,10 +6,19 @@ calls into the model / helpers is fused where it costs launches (classification 
 up-sampling + CE, AdamW) and stock torch for the rest (F.interpolate of the CAMs, loss weighting); everything the reference
 reaches through model(...), cam_helper, PAR and model.losses runs in libdupl.so.
 
-Differences from the script, none of which changes a number:
+Differences from the script:
   * the per-image high threshold is computed on the device (masked max) instead of through
-    torch.nonzero + a Python loop (train_final_voc.py:268-275) — no host sync;
-  * the up-sampling of the seg logits and the seg loss are one kernel pair (model.losses.get_seg_loss_upsampled);
+    torch.nonzero + a Python loop (train_final_voc.py:268-275) — no host sync, same numbers;
+  * the up-sampling of the seg logits and the seg loss are one kernel pair (model.losses.get_seg_loss_upsampled), same numbers;
+  * phase C: the GMM noise filter (train_final_voc.py:358-394, scikit-learn on the host in the reference) runs on the device
+    with deterministic Lloyd iterations in place of scikit-learn's k-means++ seeding.  Pinned against scikit-learn 1.9 on
+    unimodal, weakly bimodal and well-separated CE histograms (oracle/gmm_ref.py, tests/test_gmm_oracle.py): the `|d mean| > 1`
+    gate decides identically and the masks differ by <= 2 pixels of 36 864 — the band scikit-learn shows against itself with
+    another random_state.  It is NOT bit-pinned to the reference's scikit-learn 1.0.2;
+  * phase C without `inputs_aug`: the strong augmentation (utils/imutils.augment_data_strong, PIL on the host in the
+    reference) runs on the device, bit-exact with Pillow for the same operation draw (utils/imutils.py of this package);
+  * the refined pseudo-labels handed back by `losses()` are the step's own buffers (graph-static under capture=True and
+    overwritten — also by the GMM filter, in place — on the next call): clone them to keep them;
   * no logging / validation / checkpointing.
 """
 import math
@@ -282,7 +291,7 @@ class TrainStep:
 
     def losses(self, inputs, cls_label, img_box, n_iter, inputs_aug=None):
         """-> (loss, dict of parts, (refined_label_1, refined_label_2) or None).  inputs_aug: the strongly augmented view
-        (imutils.augment_data_strong, CPU PIL in the reference: the caller's business); required once n_iter >= gmm_iters."""
+        (imutils.augment_data_strong; CPU PIL in the reference); once n_iter >= gmm_iters it is drawn on the device when None."""
         a = self.args
         cls_f = cls_label.float()
         one = inputs.new_ones(())

@@ -33,6 +33,8 @@ if a.table:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step(x, cls, box, n0 + 5)
+        if a.gaps:
+            step(x, cls, box, n0 + 6)      # two replays: the idle time BETWEEN two steps shows up as well
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=72))
     if a.gaps:
@@ -51,6 +53,14 @@ if a.table:
             hist[min(int(g), 20)] += 1
             busy += max(0.0, s1 - max(s0, end))
             end = max(end, s1)
+        t0 = ev[0][0]
+        end, prev = ev[0][0], "-"
+        print("\nidle periods > 3 us (offset ms: previous activity -> idle us -> next activity):")
+        for s0, s1, name in ev:
+            if s0 - end > 3.0:
+                print(f"  {(s0 - t0) / 1e3:8.3f}: {prev[:56]:56s} -> {s0 - end:8.1f} -> {name[:70]}")
+            if s1 >= end:
+                end, prev = s1, name
         print(f"\nGAPS: {len(ev)} device activities, span {span / 1e3:.3f} ms, busy {busy / 1e3:.3f} ms, idle between activities {gaps / 1e3:.3f} ms")
         print("gap histogram (us -> count):", dict(sorted(hist.items())))
         for k, (g, n) in sorted(by_next.items(), key=lambda kv: -kv[1][0])[:25]:
