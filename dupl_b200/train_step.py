@@ -235,11 +235,12 @@ class TrainStep:
             net = model.module if hasattr(model, "module") else model
             group = None
             world = self._world()
-            # Measured on B200 (profiles/r02_summary.md): at 2 ranks ONE all-reduce per student after the backward is fastest
-            # (52.9 ms vs 53.2-53.8 chunked: the 733 MB take 1.8 ms over NVLink and overlapping costs more SM time than it hides);
-            # at 8 ranks chunked + overlapped wins (50.6 ms vs 51.3) when NCCL is kept to 16 CTAs and the persistent GEMM grid
-            # leaves 16 SMs alone — without that reservation the collective's CTAs delay statically assigned GEMM tiles (55.8 ms).
-            overlap = os.environ.get("DUPL_GRAD_OVERLAP", "1" if world >= 4 else "0") != "0"
+            # Measured on B200 (profiles/r02_summary.md §4): the gradients are averaged chunk by chunk while the backward runs,
+            # NCCL kept to 16 CTAs and the persistent GEMM grid leaving 16 SMs alone — without that reservation the
+            # collective's CTAs delay statically assigned GEMM tiles (55.8 vs 50.6 ms at 8 ranks).  At the end of round 2:
+            # 2 ranks 47.85 ms chunked + overlapped vs 48.2-48.9 with ONE all-reduce after the backward (8 / 8 and 24 / 24:
+            # 48.7 / 48.4); 8 ranks 50.6 vs 51.3 (mid-round build).  DUPL_GRAD_OVERLAP=0 selects the single all-reduce.
+            overlap = os.environ.get("DUPL_GRAD_OVERLAP", "1" if world >= 2 else "0") != "0"
             chunk = int(os.environ.get("DUPL_GRAD_CHUNK_ELEMS", str(6 << 20 if overlap else 1 << 30)))
             if world > 1 and overlap:
                 import torch.distributed as dist
