@@ -226,6 +226,14 @@ def train_workload(dataset, K, phase):
     return f"{dataset}{K + 1}_dual_student_phase{phase}_step_448_bs4"
 
 
+def train_config(dataset, K, phase, world):
+    """`config` of the training-step line — identical for this repo's arm and the reference arm (the driver compares them);
+    what is specific to how THIS implementation runs the workload goes into the line's `notes` object."""
+    return {"workload": train_workload(dataset, K, phase), "per_gpu_batch": BATCH, "image": SIZE, "classes": K + 1,
+            "parallelism": f"dp{world}" if world > 1 else "single GPU",
+            "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush"}
+
+
 def train_n_iter(K, phase_c):
     from dupl_b200.train_step import Args
     targs = Args if K == 20 else Args.coco()
@@ -273,7 +281,7 @@ def run_reference(args):
         for i in range(args.steps):
             times.append(arm(x, cls, box, n_iter + i))
         metric, imgs = "train_images_per_sec", 1.0
-        config = {"workload": train_workload(args.dataset, K, "B"), "per_gpu_batch": BATCH, "image": SIZE, "classes": K + 1}
+        config = train_config(args.dataset, K, "B", int(os.environ.get("WORLD_SIZE", "1")))
         if torch.cuda.is_available() and K == 20 and not args.no_reference_gpu:
             dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
             torch.cuda.set_device(dev)
@@ -787,13 +795,12 @@ def run_train(h, args):
             "metric": "train_images_per_sec", "value": imgs / (ms_step / 1000.0), "unit": UNIT, "n_gpus": h.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": train_workload(args.dataset, K, args.phase), "per_gpu_batch": BATCH, "image": SIZE,
-                       "classes": K + 1, "n_iter": t["n_iter"],
-                       "parallelism": (f"dp{h.world} (gradients averaged over NCCL " +
-                                       ("inside the captured graph)" if t.get("capture") else "by the DistributedDataParallel reducer)")) if h.world > 1 else "single GPU",
-                       "l2_policy": "per-step working set of several GB >> 126 MB L2; no explicit flush",
-                       "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images",
-                       "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half only (DDP reducer needs eager autograd)"},
+            "config": train_config(args.dataset, K, args.phase, h.world),
+            "notes": {"n_iter": t["n_iter"],
+                      "gradient_average": ("none (single GPU)" if h.world == 1 else "NCCL all-reduce of the gradient arenas inside the captured graph"
+                                           if t.get("capture") else "DistributedDataParallel reducer"),
+                      "forward_reuse": "training forward starts from the MS-CAM pass activations of the un-flipped scale-1.0 images",
+                      "cuda_graph": "whole iteration" if t.get("capture") else "CAM + PAR half only (DDP reducer needs eager autograd)"},
             "e2e": {"value": imgs / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": t["d2h"],
                     "ms_per_step": e2e_ms},
             "gpu_launches": t.get("launches"), "clocks": t["clocks"], "loss": t["loss"], "peak_mem_gb": round(t["peak_mem_gb"], 2),

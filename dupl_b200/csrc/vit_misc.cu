@@ -1,6 +1,8 @@
 // HBM-bound companions of the tcgen05 GEMMs in the ViT encoder: operand splitting, LayerNorm,
 // patch extraction (fused with the multi-scale resize + flip), pos-embed resize, cls rows and
 // the CAM class contraction.  All are one-pass, 128-bit vectorised, warp-shuffle reduced.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "resample.cuh"
@@ -195,64 +197,89 @@ struct CamParams {
   long out_offset[DUPL_MAX_SEGMENTS];
   int nseg, total_patch_rows;
 };
-// One warp per patch token: optional final LayerNorm in registers, then K dot products of length D=768.
-__global__ void __launch_bounds__(256) cam_contract_kernel(const float* __restrict__ tok, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float eps,
-                                                           const float* __restrict__ w, int K, CamParams p,
-                                                           float* __restrict__ out) {
+// One warp per TOK consecutive patch tokens: optional final LayerNorm in registers, then K dot products of length D=768.
+// ncu (profiles/r02_ncu_hbm2.md): with one token per warp the kernel sits at 62-68 % of the LSU wavefront peak — the
+// K x 768 classifier rows are re-read from L1 for every token (60 KB per 3 KB token row for VOC) — and takes 70-85 us for
+// 21 952 tokens, 7x its HBM time.  With TOK tokens in registers a weight row serves all of them.  TOK = 4 (147 registers,
+// one CTA per SM) measured no faster: too few warps to cover the load latency; TOK = 2 keeps two CTAs per SM.
+// Per token the arithmetic and its order do not depend on TOK (bit-identical results).
+template <int TOK>
+__global__ void __launch_bounds__(256, TOK <= 2 ? 2 : 1) cam_contract_kernel(const float* __restrict__ tok, const float* __restrict__ gamma,
+                                                                             const float* __restrict__ beta, float eps,
+                                                                             const float* __restrict__ w, int K, CamParams p,
+                                                                             float* __restrict__ out) {
   constexpr int V = 6, D = 768;
   const int lane = threadIdx.x & 31;
-  const int prow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (prow >= p.total_patch_rows) return;
-  int si = 0;
-  for (int s = 1; s < p.nseg; ++s)
-    if (prow >= p.seg[s].patch_row_offset) si = s;
-  const dupl_segment sg = p.seg[si];
-  const int np = sg.tokens - 1;
-  const int local = prow - sg.patch_row_offset;
-  const int img = local / np, pidx = local % np;
-  const long trow = sg.row_offset + static_cast<long>(img) * sg.tokens + 1 + pidx;
-  const float4* xr = reinterpret_cast<const float4*>(tok + trow * D);
-  float4 v[V];
+  const int prow0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TOK;
+  if (prow0 >= p.total_patch_rows) return;
+  float4 v[TOK][V];
+  float* o[TOK];
+  int np_t[TOK];
 #pragma unroll
-  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  for (int t = 0; t < TOK; ++t) {
+    const int prow = min(prow0 + t, p.total_patch_rows - 1);  // a ragged last group repeats its last token (not stored)
+    int si = 0;
+    for (int s = 1; s < p.nseg; ++s)
+      if (prow >= p.seg[s].patch_row_offset) si = s;
+    const dupl_segment sg = p.seg[si];
+    const int np = sg.tokens - 1;
+    const int local = prow - sg.patch_row_offset;
+    const int img = local / np, pidx = local % np;
+    const long trow = sg.row_offset + static_cast<long>(img) * sg.tokens + 1 + pidx;
+    const float4* xr = reinterpret_cast<const float4*>(tok + trow * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[t][i] = xr[lane + 32 * i];
+    o[t] = out + p.out_offset[si] + static_cast<long>(img) * K * np + pidx;
+    np_t[t] = np;
+  }
   if (gamma != nullptr) {
-    float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.0f;
+    for (int t = 0; t < TOK; ++t) {
+      float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+      for (int i = 0; i < V; ++i) s += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
+      const float mean = warp_sum(s) * (1.0f / D);
+      float q = 0.0f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
-      v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
-      v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
-      v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
+      for (int i = 0; i < V; ++i) {
+        const float a = v[t][i].x - mean, b = v[t][i].y - mean, c = v[t][i].z - mean, d = v[t][i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        v[t][i].x = (v[t][i].x - mean) * rstd * g.x + b.x;
+        v[t][i].y = (v[t][i].y - mean) * rstd * g.y + b.y;
+        v[t][i].z = (v[t][i].z - mean) * rstd * g.z + b.z;
+        v[t][i].w = (v[t][i].w - mean) * rstd * g.w + b.w;
+      }
     }
   }
-  float* o = out + p.out_offset[si] + static_cast<long>(img) * K * np + pidx;
+  const int nvalid = min(TOK, p.total_patch_rows - prow0);
   for (int k = 0; k < K; ++k) {
     const float4* wr = reinterpret_cast<const float4*>(w + static_cast<long>(k) * D);
-    float acc = 0.0f;
+    float acc[TOK];
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) acc[t] = 0.0f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float4 ww = __ldg(wr + lane + 32 * i);
-      acc = fmaf(v[i].x, ww.x, acc);
-      acc = fmaf(v[i].y, ww.y, acc);
-      acc = fmaf(v[i].z, ww.z, acc);
-      acc = fmaf(v[i].w, ww.w, acc);
+#pragma unroll
+      for (int t = 0; t < TOK; ++t) {
+        acc[t] = fmaf(v[t][i].x, ww.x, acc[t]);
+        acc[t] = fmaf(v[t][i].y, ww.y, acc[t]);
+        acc[t] = fmaf(v[t][i].z, ww.z, acc[t]);
+        acc[t] = fmaf(v[t][i].w, ww.w, acc[t]);
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) o[static_cast<long>(k) * np] = acc;
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+      const float r = warp_sum(acc[t]);
+      if (lane == 0 && t < nvalid) o[t][static_cast<long>(k) * np_t[t]] = r;
+    }
   }
 }
 
@@ -349,7 +376,11 @@ extern "C" int dupl_cam_contract(const float* tok, const float* gamma, const flo
     total += seg[s].batch * (seg[s].tokens - 1);
   }
   p.total_patch_rows = total;
-  cam_contract_kernel<<<cdiv(total, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(tok, gamma, beta, eps, w, K, p, out);
+  static const int tok_per_warp = getenv("DUPL_CAM_TOK") ? atoi(getenv("DUPL_CAM_TOK")) : 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tok_per_warp >= 4) cam_contract_kernel<4><<<cdiv(total, 32), 256, 0, st>>>(tok, gamma, beta, eps, w, K, p, out);
+  else if (tok_per_warp == 2) cam_contract_kernel<2><<<cdiv(total, 16), 256, 0, st>>>(tok, gamma, beta, eps, w, K, p, out);
+  else cam_contract_kernel<1><<<cdiv(total, 8), 256, 0, st>>>(tok, gamma, beta, eps, w, K, p, out);
   DUPL_LAUNCH_OK();
   return DUPL_OK;
 }
