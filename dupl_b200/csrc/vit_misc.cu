@@ -200,8 +200,9 @@ struct CamParams {
 // One warp per TOK consecutive patch tokens: optional final LayerNorm in registers, then K dot products of length D=768.
 // ncu (profiles/r02_ncu_hbm2.md): with one token per warp the kernel sits at 62-68 % of the LSU wavefront peak — the
 // K x 768 classifier rows are re-read from L1 for every token (60 KB per 3 KB token row for VOC) — and takes 70-85 us for
-// 21 952 tokens, 7x its HBM time.  With TOK tokens in registers a weight row serves all of them.  TOK = 4 (147 registers,
-// one CTA per SM) measured no faster: too few warps to cover the load latency; TOK = 2 keeps two CTAs per SM.
+// 21 952 tokens, 7x its HBM time.  With TOK tokens in registers a weight row serves all of them.  Measured in the captured
+// step: TOK = 1: 77.3 us, TOK = 2 (128 registers, two CTAs per SM): 61.3 us, TOK = 4 (194 registers, one CTA per SM: too few
+// warps to cover the load latency): 65.6 us.  Default 2 (DUPL_CAM_TOK overrides).
 // Per token the arithmetic and its order do not depend on TOK (bit-identical results).
 template <int TOK>
 __global__ void __launch_bounds__(256, TOK <= 2 ? 2 : 1) cam_contract_kernel(const float* __restrict__ tok, const float* __restrict__ gamma,
@@ -376,7 +377,7 @@ extern "C" int dupl_cam_contract(const float* tok, const float* gamma, const flo
     total += seg[s].batch * (seg[s].tokens - 1);
   }
   p.total_patch_rows = total;
-  static const int tok_per_warp = getenv("DUPL_CAM_TOK") ? atoi(getenv("DUPL_CAM_TOK")) : 1;
+  static const int tok_per_warp = getenv("DUPL_CAM_TOK") ? atoi(getenv("DUPL_CAM_TOK")) : 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tok_per_warp >= 4) cam_contract_kernel<4><<<cdiv(total, 32), 256, 0, st>>>(tok, gamma, beta, eps, w, K, p, out);
   else if (tok_per_warp == 2) cam_contract_kernel<2><<<cdiv(total, 16), 256, 0, st>>>(tok, gamma, beta, eps, w, K, p, out);
