@@ -66,3 +66,21 @@ def test_crf_label_variants_run_and_agree_with_oracle():
     out = dcrf.crf_inference_label(img, lab, t=3, n_labels=21, gt_prob=0.7)
     assert out.shape == lab.shape and out.dtype == np.int64
     assert (out == lab).mean() > 0.5
+
+
+def test_numpy_interface_through_the_pinned_staging_buffers():
+    """A probability map above 256 K elements takes the page-locked staging path (utils/dcrf.py): numpy in / numpy out must
+    equal the device-tensor path bit for bit, and every call must hand back its own array (the staging buffers are reused)."""
+    from dupl_b200.utils.dcrf import DenseCRF
+    img, p = _case(160, 200, 21, seed=5)
+    img2, p2 = _case(160, 200, 21, seed=6)
+    assert p.size > (1 << 18)
+    crf = DenseCRF(5, 1, 1, 4, 121, 5)
+    a = crf(img, p)
+    keep = a.copy()
+    b = crf(img2, p2)
+    assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == p.shape
+    assert np.array_equal(a, keep) and not np.array_equal(a, b)        # the second call did not overwrite the first result
+    dev = crf(torch.from_numpy(img).cuda(), torch.from_numpy(p).cuda())
+    assert torch.is_tensor(dev) and dev.is_cuda
+    assert np.array_equal(dev.cpu().numpy(), a)
