@@ -31,7 +31,7 @@
 namespace dupl {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9 epilogue (two warps per TMEM lane quadrant)
 
 struct GemmGroupDev {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
@@ -53,6 +53,7 @@ struct GemmParamsDev {
   int passes;    // 3: hi*hi + hi*lo + lo*hi;  4: + lo*lo (products whose SIGN is consumed downstream: PTC Gram)
   int a_mn;      // A planes stored [K, M]: MN-major operand, staged as 64-column blocks of [BK rows x 128 B] (BK = 64 only)
   int b_mn;      // W planes stored [K, N]: same for B (BN = 256 or 128: each CTA stages BN/2 = 128 or 64 columns)
+  int epi_halves;  // 2: warps 6-9 take every other 32-column chunk of the epilogue; 1: warps 2-5 alone (RESID always)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 256);  // leader's copy collects the epilogue threads of BOTH CTAs
+        mbar_init(&tmem_empty[a], 256 * p.epi_halves);  // leader's copy collects the epilogue threads of BOTH CTAs
       }
       fence_mbar_init();
     }
@@ -222,9 +223,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+  } else if (((warp - 2) >> 2) < p.epi_halves) {
+    // ------------------------------------------------------------------ epilogue (warps 2..5, and 6..9 when epi_halves == 2)
+    // With 4 warps the GELU(erf) + split epilogue of a 256-wide tile (256 elements x ~50 instructions per thread) takes
+    // ~3/4 of the tile's MMA time at K = 768 and every hiccup shows: ncu saw the tensor pipe 63 % (fc1) / 76 % (qkv) busy
+    // on those launches against 93 % with the light residual epilogue.  Two warps per TMEM lane quadrant split the
+    // 32-column chunks between them.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * half; c0 < BN; c0 += 32 * p.epi_halves) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
         const int col0 = n0 + c0;
@@ -501,6 +507,9 @@ extern "C" int dupl_gemm_bf16x3(const dupl_gemm_args* a, void* stream) {
   P.passes = a->passes == 4 ? 4 : 3;
   P.a_mn = a_mn ? 1 : 0;
   P.b_mn = b_mn ? 1 : 0;
+  // the residual epilogue stages its rows through 4 per-warp shared-memory tiles and is light anyway: 4 warps
+  static const int epi_halves = (getenv("DUPL_GEMM_EPI_WARPS") && atoi(getenv("DUPL_GEMM_EPI_WARPS")) == 4) ? 1 : 2;
+  P.epi_halves = a->epilogue == DUPL_EPI_RESID ? 1 : epi_halves;
   P.nseg = 0;
   if (a->epilogue == DUPL_EPI_PATCH) {
     DUPL_CHECK_ARG(a->nseg >= 1 && a->nseg <= DUPL_MAX_SEGMENTS, "dupl_gemm_bf16x3: nseg=%d", a->nseg);
