@@ -115,6 +115,76 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
   }
 }
 
+// Same split without transposed outputs (what the MN-major GEMM operands leave to do), vectorised: a lane owns 4 consecutive
+// columns of a 64-row x 128-column tile (float4 loads, 8-byte stores per plane, the 8 rows of a warp in flight together).
+// The transposing kernel above moved 2 bytes per lane and store: 25 us per launch on average against ~8 us of HBM time.
+// Row -> warp assignment, partial sums and their order are those of split_transpose_kernel: bit-identical planes and sums.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int R, int Cc, int ld,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                         float* __restrict__ colsum_ws, const float* __restrict__ gelu_pre,
+                                                         float* __restrict__ colsum_out, unsigned int* __restrict__ tickets) {
+  pdl_sync();
+  __shared__ float part[8][128];
+  __shared__ bool last_of_strip;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 64 + warp * 8, c0 = blockIdx.y * 128;
+  const int c = c0 + 4 * lane;
+  const bool col_ok = c < Cc;  // Cc % 4 == 0: a lane's 4 columns are all inside or all outside
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && r0 + i < R) v[i] = *reinterpret_cast<const float4*>(src + static_cast<long>(r0 + i) * ld + c);
+  }
+  if (gelu_pre != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (col_ok && r0 + i < R) {
+        const float4 g = *reinterpret_cast<const float4*>(gelu_pre + static_cast<long>(r0 + i) * Cc + c);
+        v[i].x *= gelu_grad(g.x); v[i].y *= gelu_grad(g.y); v[i].z *= gelu_grad(g.z); v[i].w *= gelu_grad(g.w);
+      }
+    }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+    if (hi != nullptr && col_ok && r0 + i < R) {
+      uint32_t h0, l0, h1, l1;
+      split2_bf16(v[i].x, v[i].y, h0, l0);
+      split2_bf16(v[i].z, v[i].w, h1, l1);
+      *reinterpret_cast<uint2*>(hi + static_cast<long>(r0 + i) * Cc + c) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(lo + static_cast<long>(r0 + i) * Cc + c) = make_uint2(l0, l1);
+    }
+  }
+  if (colsum_ws == nullptr) return;
+  *reinterpret_cast<float4*>(&part[warp][4 * lane]) = acc;
+  __syncthreads();
+  const int t = threadIdx.x, col = c0 + t;
+  if (t < 128 && col < Cc) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += part[k][t];
+    colsum_ws[static_cast<long>(blockIdx.x) * Cc + col] = sum;
+  }
+  if (colsum_out != nullptr) {
+    __threadfence();  // this CTA's partial row of colsum_ws is visible device-wide before its ticket is taken
+    __syncthreads();
+    if (t == 0) {
+      const unsigned int tk = atomicAdd(tickets + blockIdx.y, 1u);
+      last_of_strip = (tk == gridDim.x - 1);
+      if (last_of_strip) tickets[blockIdx.y] = 0;  // every CTA of the strip has taken its ticket
+    }
+    __syncthreads();
+    if (last_of_strip && t < 128 && col < Cc) {
+      __threadfence();
+      float sum = 0.0f;
+      for (int k = 0; k < static_cast<int>(gridDim.x); ++k) sum += __ldcg(colsum_ws + static_cast<long>(k) * Cc + col);
+      colsum_out[col] = sum;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ ws, int ntiles, int Cc,
                                                             float* __restrict__ out) {
   pdl_sync();
@@ -448,6 +518,22 @@ static int split_transpose_impl(const float* src, int32_t R, int32_t Cc, int32_t
   if (fused) {
     if (ticket_base == nullptr) DUPL_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&ticket_base), g_colsum_tickets));
     tickets = ticket_base + (next_set++ % COLSUM_TICKET_SETS) * COLSUM_TICKET_STRIPS;  // launches in flight never share a set
+  }
+  // no transposed outputs, identity row map, 16-byte aligned rows: the vectorised kernel (DUPL_SPLIT_ROWS=0: the tile kernel)
+  static const bool rows_kernel = !(getenv("DUPL_SPLIT_ROWS") && atoi(getenv("DUPL_SPLIT_ROWS")) == 0);
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (rows_kernel && t_hi == nullptr && tokens == 0 && Cc % 4 == 0 && ld % 4 == 0 && aligned16(src) && aligned16(hi) && aligned16(lo) &&
+      (gelu_pre == nullptr || aligned16(gelu_pre)) && cdiv(Cc, 128) <= COLSUM_TICKET_STRIPS) {
+    dim3 g2(cdiv(R, 64), cdiv(Cc, 128));
+    DUPL_CUDA_OK(launch_pdl(split_rows_kernel, g2, dim3(256), 0, st, src, R, Cc, ld, static_cast<__nv_bfloat16*>(hi),
+                            static_cast<__nv_bfloat16*>(lo), colsum_ws, gelu_pre, fused ? colsum : nullptr, tickets));
+    count_launch();
+    if (colsum != nullptr && !fused) {
+      DUPL_CUDA_OK(launch_pdl(colsum_finish_kernel, dim3(cdiv(Cc, 256)), dim3(256), 0, st, static_cast<const float*>(colsum_ws),
+                              static_cast<int>(g2.x), Cc, colsum));
+      count_launch();
+    }
+    return DUPL_OK;
   }
   DUPL_CUDA_OK(launch_pdl(split_transpose_kernel, grid, dim3(256), 0, st, src, R, Cc, ld, make_map(tokens, np, first),
                           static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), static_cast<__nv_bfloat16*>(t_hi),
