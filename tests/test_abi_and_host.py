@@ -131,3 +131,37 @@ def test_gemm_plan_fills_the_74_cta_pairs_for_the_training_shapes():
     assert plan(200, 32, 768)[0] == 64 and plan(260, 128, 256)[0] == 128   # narrow heads keep the narrow instantiations
     with __import__("pytest").raises(RuntimeError):
         plan(16, 16, 60)
+
+
+def test_mn_major_gemm_argument_rules_without_a_gpu():
+    """include/dupl.h: a ragged K is accepted only when BOTH operands are MN-major; an MN-major W needs N >= 128; the leading
+    dimensions then count the transposed storage ([K, M] / [K, N])."""
+    from dupl_b200 import _lib
+    lib = _lib.lib()
+    a = _lib.GemmArgs()
+    a.groups, a.M, a.N, a.K, a.epilogue = 1, 768, 768, 3140, _lib.EPI_F32
+    a.lda, a.ldo, a.ldw = 768, 768, 768
+    a.a_mn_major, a.b_mn_major = 1, 0
+    assert lib.dupl_gemm_bf16x3(ctypes.byref(a), None) == -1 and b"multiple of 64" in lib.dupl_last_error()
+    a.a_mn_major, a.b_mn_major, a.N, a.ldo, a.ldw = 1, 1, 64, 64, 64
+    assert lib.dupl_gemm_bf16x3(ctypes.byref(a), None) == -1 and b"N >= 128" in lib.dupl_last_error()
+    a.N, a.ldo, a.ldw, a.lda = 768, 768, 768, 760                      # lda < M for the [K, M] storage
+    assert lib.dupl_gemm_bf16x3(ctypes.byref(a), None) == -1 and b"lda" in lib.dupl_last_error()
+    a.lda = 768                                                          # now well-formed: fails only on the NULL planes
+    assert lib.dupl_gemm_bf16x3(ctypes.byref(a), None) == -1 and b"NULL operand plane" in lib.dupl_last_error()
+
+
+def test_bench_arms_share_one_config():
+    """bench.py: `config` of the training-step line is built by one function for this repo's arm and for --impl reference (the
+    driver compares the two lines); nothing implementation-specific lives in it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c1 = bench.train_config("voc", 20, "B", 1)
+    assert c1 == {"workload": "voc21_dual_student_phaseB_step_448_bs4", "per_gpu_batch": 4, "image": 448, "classes": 21,
+                  "parallelism": "single GPU", "l2_policy": c1["l2_policy"]}
+    assert "L2" in c1["l2_policy"]
+    assert bench.train_config("coco", 80, "C", 8)["parallelism"] == "dp8"
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("train_config(args.dataset, K,") == 2              # both arms call it
