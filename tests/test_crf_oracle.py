@@ -37,3 +37,41 @@ def test_zero_iterations_returns_the_softmax_of_the_unary():
     img, p = _tiny(seed=1)
     q = DenseCRF(0, 1, 1, 4, 121, 5)(img, p)
     assert np.abs(q - p).max() < 1e-5
+
+
+def _photo_like(H, W, C, seed):
+    """Smoothed noise over piecewise-constant colour regions, logits that favour one class per region."""
+    import torch
+    rng = np.random.RandomState(seed)
+    img = rng.randint(0, 255, (H, W, 3)).astype(np.uint8)
+    t = torch.from_numpy(img).permute(2, 0, 1).float()[None]
+    img = torch.nn.functional.avg_pool2d(t, 7, 1, 3, count_include_pad=False)[0].permute(1, 2, 0).round().numpy()
+    yy, xx = np.mgrid[0:H, 0:W]
+    region = ((yy // (H // 3)) * 3 + xx // (W // 3)) % 5
+    pal = rng.randint(30, 220, (5, 3))
+    img = (0.6 * pal[region] + 0.4 * img).clip(0, 255).astype(np.uint8)
+    lg = rng.randn(C, H // 8 + 1, W // 8 + 1).astype(np.float32) * 2
+    lg = torch.nn.functional.interpolate(torch.from_numpy(lg)[None], size=(H, W), mode="bilinear", align_corners=False)[0].numpy()
+    for k in range(5):
+        lg[k + 1][region == k] += 2.0
+    p = np.exp(lg - lg.max(0))
+    p /= p.sum(0, keepdims=True)
+    return img, p.astype(np.float32)
+
+
+@pytest.mark.parametrize("H,W,params,mean_bar,agree_bar", [
+    (64, 80, (10, 1, 1, 4, 121, 5), 3e-3, 0.985),     # tools/eval_seg_voc.py:104-111 = tools/eval_seg_coco_ddp.py:156-163
+    (48, 64, (10, 3, 3, 10, 80, 13), 1e-2, 0.97),     # utils/dcrf.py:7-24 crf_inference
+    (48, 64, (10, 3, 3, 10, 50, 5), 1e-2, 0.94)])     # utils/dcrf.py:26-40 crf_inference_label
+def test_reference_parameter_sets_at_21_classes_track_the_exact_mean_field(H, W, params, mean_bar, agree_bar):
+    """pydensecrf cannot be pinned offline, so the restatement is bounded against the exact O(N^2) mean-field with the three
+    parameter sets the reference uses, 21 classes, T = 10, on a photo-like image.  Measured: eval set 7e-4 mean |dQ|, 99.4 %
+    label agreement; the compat-10 sets saturate Q, so single bistable pixels differ by ~0.7-0.9 in Q while 96-100 % of the
+    labels agree — the bound is on the mean and on the labels."""
+    img, p = _photo_like(H, W, 21, seed=0)
+    crf = DenseCRF(*params)
+    q, qb = crf(img, p), crf.bruteforce(img, p)
+    assert np.abs(q.sum(0) - 1).max() < 1e-5
+    assert np.abs(q - qb).mean() < mean_bar
+    assert (q.argmax(0) == qb.argmax(0)).mean() > agree_bar
+    assert (q.argmax(0) != p.argmax(0)).mean() > 0.2        # the CRF does real work on this input
