@@ -93,7 +93,7 @@ def colsum(x, R, Cc, tokens=0, np_=0, first=0):
 def layernorm_bwd(dy, x, gamma, dres, dg_out=None, db_out=None):
     rows, cols = x.shape
     dev = x.device
-    partial = torch.empty(2 * cols * ((rows + 15) // 16), dtype=torch.float32, device=dev)
+    partial = torch.empty(2 * cols * ((rows + 7) // 8), dtype=torch.float32, device=dev)
     dg = torch.empty(cols, dtype=torch.float32, device=dev) if dg_out is None else dg_out.view(cols)
     db = torch.empty(cols, dtype=torch.float32, device=dev) if db_out is None else db_out.view(cols)
     L.check(L.lib().dupl_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(dres), L.ptr(partial), L.ptr(dg), L.ptr(db),

@@ -325,7 +325,7 @@ int dupl_transpose_planes_multi(const dupl_transpose_item* items, int32_t n_item
 int dupl_colsum(const float* x, int32_t R, int32_t Cc, int32_t ld, int32_t tokens, int32_t np, int32_t first, float* out,
                 void* stream);
 /* LayerNorm backward (vit.py:146,152,256): dres[rows, cols] += dL/dx; dgamma, dbeta [cols];
- * partial: scratch of 2*cols*ceil(rows/16) floats.  cols == 768. */
+ * partial: scratch of 2*cols*ceil(rows/8) floats.  cols == 768. */
 int dupl_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dres, float* partial, float* dgamma,
                        float* dbeta, int32_t rows, int32_t cols, float eps, void* stream);
 /* d[i] *= gelu'(pre[i]) (exact erf form) */
