@@ -280,8 +280,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // dres[row] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // partial[blk][0][c] = sum_rows dy * xhat, partial[blk][1][c] = sum_rows dy   (rows of this block)
 // ------------------------------------------------------------------------------------------------
-// LNB_ROWS rows per block: 3140 training rows -> 197 blocks with 16 (32 rows gave 99 blocks on 148 SMs), 393 blocks with 8
-// (one row per warp: 2.6 blocks per SM keep more loads in flight; DUPL_LNB_ROWS selects, the scratch holds either).
+// LNB_ROWS rows per block: 3140 training rows -> 197 blocks with 16 (32 rows gave 99 blocks on 148 SMs).  8 rows (393 blocks,
+// one row per warp) measured no better in the captured step (45.22 vs 45.05 ms): 16 stays, DUPL_LNB_ROWS=8 selects the other
+// instantiation (the scratch holds either).
 template <int V, int LNB_ROWS>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, float* __restrict__ dres,
@@ -609,7 +610,7 @@ extern "C" int dupl_layernorm_bwd(const float* dy, const float* x, const float* 
                                   float* dgamma, float* dbeta, int32_t rows, int32_t cols, float eps, void* stream) {
   DUPL_CHECK_ARG(dy && x && gamma && dres && partial && dgamma && dbeta, "dupl_layernorm_bwd: NULL pointer");
   DUPL_CHECK_ARG(rows > 0 && cols == 768, "dupl_layernorm_bwd: rows=%d cols=%d (768 columns are built)", rows, cols);
-  static const int lnb_rows = (getenv("DUPL_LNB_ROWS") && atoi(getenv("DUPL_LNB_ROWS")) == 16) ? 16 : 8;
+  static const int lnb_rows = (getenv("DUPL_LNB_ROWS") && atoi(getenv("DUPL_LNB_ROWS")) == 8) ? 8 : 16;
   const int nb = cdiv(rows, lnb_rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lnb_rows == 16) DUPL_CUDA_OK(launch_pdl(layernorm_bwd_kernel<6, 16>, dim3(nb), dim3(256), 0, st, dy, x, gamma, dres, partial, rows, eps));
