@@ -317,3 +317,27 @@ def test_phase_c_augments_on_the_device_and_runs_captured():
     cap = TrainStep(m2, make_optimizer(m2, capturable=True), capture=True)
     ls = [cap(x, cls, box, 9000 + i)[0].item() for i in range(3)]
     assert all(torch.isfinite(torch.tensor(ls))) and len(set(ls)) > 1      # different operations / updated weights per step
+
+
+@pytest.mark.parametrize("R,Cc,gelu", [(3140, 768, False), (3140, 3072, True), (3140, 2304, False), (3136, 512, False),
+                                        (34, 768, False), (130, 3072, True)])
+def test_vectorised_split_kernel_matches_the_tile_kernel(R, Cc, gelu):
+    """split_rows_kernel (no transposed output: float4 loads, column sums finished by the last CTA of a strip) vs
+    split_transpose_kernel (64x32 tiles, also writes the transposed planes): identical planes and identical bias sums —
+    same row -> warp assignment and the same order of the partial sums — and the sums agree with fp64."""
+    from dupl_b200 import train
+    g = torch.Generator().manual_seed(R + Cc)
+    src = torch.randn(R, Cc, generator=g).cuda()
+    pre = torch.randn(R, Cc, generator=g).cuda() if gelu else None
+    (hi, lo), _, cs = train.split_transpose(src, R, Cc, want_t=False, want_colsum=True, gelu_pre=pre)
+    (hi2, lo2), (thi, tlo), cs2 = train.split_transpose(src, R, Cc, want_t=True, want_colsum=True, gelu_pre=pre)
+    torch.cuda.synchronize()
+    assert torch.equal(hi, hi2) and torch.equal(lo, lo2)
+    assert torch.equal(cs, cs2)
+    assert torch.equal(thi[:, :R].t().contiguous(), hi) and torch.equal(tlo[:, :R].t().contiguous(), lo)
+    ref = src.double()
+    if gelu:
+        p = pre.double()
+        ref = ref * (0.5 * (1 + torch.erf(p * 0.7071067811865476)) + p * torch.exp(-0.5 * p * p) * 0.3989422804014327)
+    assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 2e-6
+    assert rel_err(hi.float() + lo.float(), ref) < 1e-4 if gelu else rel_err(hi.float() + lo.float(), ref) < 2e-5
