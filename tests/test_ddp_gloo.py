@@ -103,19 +103,22 @@ def _worker_arena(rank, world, port, out):
 
 
 @pytest.mark.timeout(300)
-def test_gradient_arena_chunked_all_reduce_averages_over_ranks():
+@pytest.mark.parametrize("world", [2, 4])
+def test_gradient_arena_chunked_all_reduce_averages_over_ranks(world):
     """grad_arena.GradArena (what the captured multi-rank step does instead of DDP's reducer): gradients written / accumulated
     in place, finished chunks all-reduced in arena order while the backward pass is still running, mean over ranks,
-    parameters without a gradient keep .grad = None, .grad are views of the arena."""
-    port = 29900 + os.getpid() % 90
+    parameters without a gradient keep .grad = None, .grad are views of the arena.  World sizes 2 and 4."""
+    port = 29900 + os.getpid() % 90 + world
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker_arena, args=(2, port, out), nprocs=2, join=True)
-        assert out[0][:5] == out[1][:5]
+        mp.spawn(_worker_arena, args=(world, port, out), nprocs=world, join=True)
+        for r in range(1, world):
+            assert out[0][:5] == out[r][:5]
+            assert out[0][5] == out[r][5]                 # every rank enqueued the same sequence of collectives
         w2, b2, w1, unused_none, is_view, log = out[0]
-        # second step: rank r contributes (r+1)*2*(1 + 2) to w2 / w1 and (r+1)*2*1 to b2; mean over ranks 1 and 2 = 1.5 x
-        assert abs(w2 - 1.5 * 6) < 1e-6 and abs(w1 - 1.5 * 6) < 1e-6 and abs(b2 - 1.5 * 2) < 1e-6
+        # second step: rank r contributes (r+1)*2*(1 + 2) to w2 / w1 and (r+1)*2*1 to b2; the mean of (r+1) over the ranks
+        m = (world + 1) / 2
+        assert abs(w2 - m * 6) < 1e-6 and abs(w1 - m * 6) < 1e-6 and abs(b2 - m * 2) < 1e-6
         assert unused_none and is_view
-        assert out[0][5] == out[1][5]                     # every rank enqueued the same sequence of collectives
         half = len(log) // 2
         assert log[:half] == log[half:] and [lo for lo, _ in log[:half]] == sorted(lo for lo, _ in log[:half])
