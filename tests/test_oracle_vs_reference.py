@@ -236,3 +236,31 @@ def test_phase_c_loop_matches_the_reference_functions_composed_like_the_script()
         assert abs(got[k].item() - want[k].item()) < 1e-5 * max(1.0, abs(want[k].item())), k
     assert abs(got_loss.item() - loss.item()) < 1e-5
     assert torch.equal(labels[0], lab_1) and torch.equal(labels[1], lab_2)
+
+
+def test_oracle_loop_matches_the_unmodified_reference_loop_at_448():
+    """The chain CUDA <-> oracle <-> reference closed at the BASELINE size: one 448x448 image (N = 785 / 197 / 1765 tokens in
+    the MS-CAM pass) through the reference's own loop body (baseline/ref_step.py: the statements of train_final_voc.py:186-472
+    on the reference's modules, CPU) and through oracle.train_losses — every loss part, the total loss, and (after the
+    reference's backward + PolyWarmupAdamW step) that the comparison ran in phase B."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from baseline import compat
+    if not compat.available():
+        pytest.skip("baseline/_ref not installed (baseline/install_ref.sh)")
+    from baseline.ref_step import ReferenceStep
+    from dupl_b200.train_step import Args
+    from helpers import init_state_dict, synth_boxes, synth_cls_labels, synth_images
+    P = init_state_dict(21)
+    b, S, n_iter = 1, 448, 3000
+    x, cls, box = synth_images(b, S, S, seed=40), synth_cls_labels(b, 20, seed=41), synth_boxes(b, S, S, seed=42)
+    ref_step = ReferenceStep(torch.device("cpu"), state_dict={k: v.clone() for k, v in P.items()}, samples_per_gpu=b)
+    ref_loss, ref_parts = ref_step(x, cls, box, n_iter)
+    with torch.no_grad():
+        loss, parts, _ = O.train_losses(P, x, cls, box, n_iter, O.VOC_CFG, thres_target=list(Args.high_thres_target))
+    for k in ("cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
+        assert abs(float(parts[k]) - ref_parts[k]) < 2e-5 * max(1.0, abs(ref_parts[k])), (k, float(parts[k]), ref_parts[k])
+    assert abs(loss.item() - ref_loss.item()) < 2e-5 * max(1.0, abs(ref_loss.item()))
+    assert ref_parts["seg_loss"] != 1.0                       # phase B: the seg loss was really computed
