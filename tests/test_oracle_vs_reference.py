@@ -241,8 +241,8 @@ def test_phase_c_loop_matches_the_reference_functions_composed_like_the_script()
 def test_oracle_loop_matches_the_unmodified_reference_loop_at_448():
     """The chain CUDA <-> oracle <-> reference closed at the BASELINE size: one 448x448 image (N = 785 / 197 / 1765 tokens in
     the MS-CAM pass) through the reference's own loop body (baseline/ref_step.py: the statements of train_final_voc.py:186-472
-    on the reference's modules, CPU) and through oracle.train_losses — every loss part, the total loss, and (after the
-    reference's backward + PolyWarmupAdamW step) that the comparison ran in phase B."""
+    on the reference's modules, CPU) and through oracle.train_losses — every loss part, the total loss, and all 308 parameter
+    gradients of the reference's own backward against the oracle's autograd."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -257,10 +257,27 @@ def test_oracle_loop_matches_the_unmodified_reference_loop_at_448():
     b, S, n_iter = 1, 448, 3000
     x, cls, box = synth_images(b, S, S, seed=40), synth_cls_labels(b, 20, seed=41), synth_boxes(b, S, S, seed=42)
     ref_step = ReferenceStep(torch.device("cpu"), state_dict={k: v.clone() for k, v in P.items()}, samples_per_gpu=b)
-    ref_loss, ref_parts = ref_step(x, cls, box, n_iter)
-    with torch.no_grad():
-        loss, parts, _ = O.train_losses(P, x, cls, box, n_iter, O.VOC_CFG, thres_target=list(Args.high_thres_target))
+    ref_loss, ref_parts = ref_step(x, cls, box, n_iter)       # forward, backward, optimizer step: .grad keeps the gradients
+    Pg = {k: v.clone().requires_grad_("pos_embed" not in k and ".head." not in k) for k, v in P.items()}
+    loss, parts, _ = O.train_losses(Pg, x, cls, box, n_iter, O.VOC_CFG, thres_target=list(Args.high_thres_target))
+    loss.backward()
     for k in ("cls_loss", "ptc_loss", "seg_loss", "sim_loss"):
         assert abs(float(parts[k]) - ref_parts[k]) < 2e-5 * max(1.0, abs(ref_parts[k])), (k, float(parts[k]), ref_parts[k])
     assert abs(loss.item() - ref_loss.item()) < 2e-5 * max(1.0, abs(ref_loss.item()))
     assert ref_parts["seg_loss"] != 1.0                       # phase B: the seg loss was really computed
+    # all 2 x 154 parameter gradients of the reference's own autograd vs the oracle's (norm-relative)
+    errs = {}
+    for name, p in ref_step.model.named_parameters():
+        if ".head." in name or "pos_embed" in name:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        g, w = Pg[name].grad.double(), p.grad.double()
+        errs[name] = float((g - w).norm() / w.norm().clamp_min(1e-30))
+    assert len(errs) == 308
+    worst = max((e, n) for n, e in errs.items())
+    median = sorted(errs.values())[len(errs) // 2]
+    print("oracle vs reference gradients at 448: worst", worst, "median", median)
+    # two fp32 CPU implementations of the same backward: measured worst 2.1e-4 (decoder.conv6.weight, a 3136-row contraction
+    # summed in another order), median 1e-6; the bar is the north_star's 1e-3
+    assert worst[0] < 1e-3, worst
+    assert median < 1e-4, median
